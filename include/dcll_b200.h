@@ -1,0 +1,157 @@
+/* dcll_b200.h -- C ABI of the B200-native DCLL hot path (libdcll_b200.so).
+ *
+ * Plain pointers and sizes only: no torch / C++ types cross this boundary.  Every
+ * pointer marked "device" is a CUDA device pointer owned by the caller (the Python
+ * host mirror allocates them as torch tensors and passes data_ptr()).  All entry
+ * points enqueue work on `stream` (a cudaStream_t passed as void*) and never
+ * synchronise the host.  They return 0 on success or a negative DCLL_E* code;
+ * dcll_last_error() returns a static message for the calling thread.
+ *
+ * The reference (ohjay/snn-modulation-classification) has no FFI of its own: its
+ * boundary is the Python class API.  Each entry point below therefore cites the
+ * reference *method* whose arithmetic it replaces (paths relative to the reference
+ * root); the Python classes that keep the reference's signatures and call these
+ * functions live in snn_modulation_classification_b200/dcll/pytorch_libdcll.py.
+ */
+#ifndef DCLL_B200_H
+#define DCLL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCLL_ABI_VERSION 3
+
+enum { DCLL_OK = 0, DCLL_EINVAL = -1, DCLL_ECUDA = -2, DCLL_EUNSUPPORTED = -3 };
+
+/* time-constant storage: the reference keeps alpha/alphas/tau_m__dt/tau_s__dt either as (1,)
+ * tensors or, with random_tau, as (Cin,H,W) tensors holding one value per input channel
+ * (dcll/pytorch_libdcll.py:349-356, :391-405). */
+enum { DCLL_COEF_SCALAR = 0, DCLL_COEF_CHANNEL = 1, DCLL_COEF_ELEMENT = 2 };
+/* layer input: dense float32 [B,Cin,H,W] spikes, or (layer 0 only, Cin == 1) the encoder's
+ * int32 [B,2] (row, col) cell of the single spike of each sample. */
+enum { DCLL_X_DENSE = 0, DCLL_X_CELLS = 1 };
+/* loss classes train.py:173 can select; gradient of the mean-reduced loss. */
+enum { DCLL_LOSS_SMOOTHL1 = 0, DCLL_LOSS_MSE = 1, DCLL_LOSS_L1 = 2,
+       DCLL_LOSS_EXTERNAL = 3 /* any other loss class: the host supplies dL/dpvoutput (and dL/doutput) */ };
+/* conv arithmetic: FP32 CUDA-core FMA (parity mode) or split-bf16 x3 on tcgen05 tensor cores. */
+enum { DCLL_PREC_FP32 = 0, DCLL_PREC_BF16X3 = 1 };
+
+/* torch.optim.Adam hyper-parameters + state of one parameter group
+ * (dcll/pytorch_libdcll.py:634-638; train.py:164-168). */
+typedef struct dcll_adam {
+    double lr, beta1, beta2, eps, weight_decay;
+    int64_t step;          /* number of updates already applied; incremented by the update call */
+    float *m_w, *v_w;      /* device: exp_avg / exp_avg_sq of the weight */
+    float *m_b, *v_b;      /* device: exp_avg / exp_avg_sq of the bias   */
+} dcll_adam;
+
+/* One Conv2dDCLLlayer (dcll/pytorch_libdcll.py:512-612) with its i2h core
+ * (ContinuousConv2D :296-429 or ContinuousRelativeRefractoryConv2D :432-509). */
+typedef struct dcll_conv_layer {
+    int32_t B, Cin, H, W;            /* input  [B,Cin,H,W]                                   */
+    int32_t Cout, KH, KW, padH, padW; /* stride 1, dilation 1, groups 1 (every shipped spec)  */
+    int32_t poolH, poolW;            /* 1 or 2 per axis (MaxPool2d k = stride, pad (k-1)//2) */
+    int32_t K;                       /* target_size                                          */
+    int32_t output_layer;            /* trainable output_ read-out present (:577-579)        */
+    int32_t coef_mode;               /* DCLL_COEF_*                                          */
+    int32_t x_mode;                  /* DCLL_X_*                                             */
+    int32_t precision;               /* DCLL_PREC_*                                          */
+    int32_t cur;                     /* which half of eps0/eps1 holds the current state;
+                                        flipped by every forward step                        */
+    int32_t write_pvmem;             /* materialise the membrane tensor (API path) or skip   */
+    float alpharp, wrp;              /* wrp > 0: refractory variant                          */
+    const float *alpha, *alphas, *tau_m, *tau_s; /* device                                   */
+    float *weight;                   /* device [Cout,Cin,KH,KW]  (the nn.Parameter)          */
+    float *weight_t;                 /* device [Cin,KH*KW,CoutPad] kernel-side copy,
+                                        CoutPad = 32*ceil(Cout/32); dcll_conv_sync_weights   */
+    float *bias;                     /* device [Cout]                                        */
+    const float *wo, *bo;            /* device [K,F], [K]   frozen local read-out i2o        */
+    float *wout, *bout;              /* device [K,F], [K]   output_ or NULL                  */
+    float *eps0[2], *eps1[2];        /* device [B,Cin,H,W]  ping-pong state                  */
+    float *arp;                      /* device [B,Cout,Hc,Wc] or NULL                        */
+    /* per-step outputs (device) */
+    float *spikes;                   /* [B,Cout,Hp,Wp] pooled spikes                         */
+    float *pv;                       /* [B,Cout,Hp,Wp] pooled sigmoid                        */
+    float *pvmem;                    /* [B,Cout,Hc,Wc] or NULL                               */
+    uint8_t *pool_idx;               /* [B,Cout,Hp,Wp] argmax inside the pool window, or NULL
+                                        when poolH == poolW == 1                             */
+    float *pvoutput;                 /* [B,K]                                                */
+    float *output;                   /* [B,K] logits of output_, or NULL                     */
+    float *g_u;                      /* [B,Cout,Hp,Wp] training scratch: dL/d(membrane) at the
+                                        pool argmax                                          */
+    void *workspace;                 /* device scratch, dcll_conv_workspace_bytes()          */
+    size_t workspace_bytes;
+} dcll_conv_layer;
+
+typedef struct dcll_train_args {
+    const float *target;             /* device [B,K] one-hot                                 */
+    const float *g_o_ext, *g_o2_ext; /* device [B,K]: DCLL_LOSS_EXTERNAL only                */
+    int32_t loss_kind;               /* DCLL_LOSS_*                                          */
+    int32_t apply_update;            /* 1: fused Adam; 0: only write gradients (DP: allreduce
+                                        then dcll_conv_apply_update)                         */
+    dcll_adam adam_i2h;              /* optimizer  over i2h.{weight,bias}                    */
+    dcll_adam adam_out;              /* optimizer2 over output_.{weight,bias}                */
+    float *grad_w, *grad_b;          /* device, optional (NULL) unless apply_update == 0     */
+    float *grad_wout, *grad_bout;    /* device, optional                                     */
+    float *loss_out;                 /* device [1] or NULL: value of the local loss          */
+} dcll_train_args;
+
+/* -- library ------------------------------------------------------------------------------ */
+int dcll_abi_version(void);
+const char *dcll_last_error(void);
+size_t dcll_sizeof_conv_layer(void);
+size_t dcll_sizeof_train_args(void);
+
+/* -- encoder: data/utils.py:43-87 (iq2spiketrain) ------------------------------------------ *
+ * x: device float32 [B,2,N]; cells: device int32 [T,B,2] = (cell_Q, cell_I) for samples
+ * t_start .. t_start+T-1.  Bit-exact with the reference's torch-CPU arithmetic.              */
+int dcll_iq_encode(const float *x, int B, int N, double min_I, double max_I, double min_Q, double max_Q,
+                   int out_w, int out_h, int t_start, int T, int do_gamma, int32_t *cells, void *stream);
+/* dense one-hot frames [T,B,1,H,W] float32 (what data/utils.py:57,81-82 materialises) */
+int dcll_cells_to_frames(const int32_t *cells, int T, int B, int H, int W, float *frames, void *stream);
+
+/* -- conv layer step ------------------------------------------------------------------------ */
+size_t dcll_conv_workspace_bytes(const dcll_conv_layer *L);
+/* refresh weight_t from weight (after load_state_dict / external assignment) */
+int dcll_conv_sync_weights(const dcll_conv_layer *L, void *stream);
+/* Conv2dDCLLlayer.forward (:599-608) incl. i2h.forward (:407-426 / :485-509): trace update,
+ * conv, refractory, sigmoid, threshold, pool, read-outs.  x: dense [B,Cin,H,W] or cells [B,2].
+ * clout (device int32 [B], optional): argmax of pvoutput (or of output on the output layer),
+ * DCLLClassification.forward :724-728.  Flips L->cur.                                        */
+int dcll_conv_step_fwd(dcll_conv_layer *L, const void *x, int32_t *clout, void *stream);
+/* i2h.forward alone (ContinuousConv2D.forward :407-426): like the above without pooling-independent
+ * read-outs; L->poolH/poolW must be 1 so that spikes/pv are the un-pooled tensors.  Flips L->cur. */
+int dcll_conv_core_fwd(dcll_conv_layer *L, const void *x, void *stream);
+/* DCLLBase.train_dcll :692-714 after the forward: local loss gradient, weight gradient and the
+ * Adam step(s).  Increments a->adam_*.step when apply_update.                                */
+int dcll_conv_step_bwd_update(dcll_conv_layer *L, dcll_train_args *a, void *stream);
+/* Adam on gradients already in a->grad_* (data-parallel path, after the allreduce) */
+int dcll_conv_apply_update(dcll_conv_layer *L, dcll_train_args *a, void *stream);
+
+/* -- whole window: the T-loop of train.py:249-251 / test_radio_ml.py:144-145 ----------------- *
+ * Runs `T` timesteps of ConvNetwork.learn (train != 0) or .test over `n_layers` chained
+ * layers.  x0: layer-0 input for all timesteps, dense [T,B,Cin,H,W] or cells [T,B,2].
+ * target: [B,K] (t_stride 0) or [T,B,K] (t_stride B*K).  iter0[l]: DCLLBase.iter of slice l
+ * before the window (reset() sets 0).  clout: device int32 [T,n_layers,B] (rows before
+ * burn-in are written too; the host keeps the reference's counting rule).                    */
+int dcll_net_window(dcll_conv_layer *layers, dcll_train_args *train, int n_layers, const void *x0,
+                    const float *target, int64_t target_t_stride, int T, int train_mode, int burnin,
+                    const int32_t *iter0, int32_t *clout, void *stream);
+
+/* -- vote: dcll/pytorch_libdcll.py:44-61 ------------------------------------------------------ *
+ * pred[b] = most frequent class of clout[t0..T,b] (first-seen wins ties, as Counter does).    */
+int dcll_vote(const int32_t *clout, int T, int t_stride, int B, int K, int32_t *pred, void *stream);
+
+/* -- quantised weights (defined by this repo, no reference counterpart; oracle/quant.py) ------ *
+ * per-output-channel symmetric int8: s = max|w|/127 (1 if 0), q = clamp(rint(w/s),-127,127).  */
+int dcll_quantize(const float *w, int rows, int cols, int8_t *codes, float *scales, void *stream);
+int dcll_dequantize(const int8_t *codes, const float *scales, int rows, int cols, float *w, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCLL_B200_H */

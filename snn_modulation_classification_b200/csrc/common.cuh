@@ -1,0 +1,120 @@
+// Shared helpers for libdcll_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dcll_b200.h"
+
+namespace dcll {
+
+void set_error(const char *fmt, ...);
+
+#define DCLL_REQUIRE(cond, code, ...)              \
+    do {                                           \
+        if (!(cond)) {                             \
+            ::dcll::set_error(__VA_ARGS__);        \
+            return (code);                         \
+        }                                          \
+    } while (0)
+
+#define DCLL_CUDA_OK(expr)                                                                      \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            ::dcll::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                              __LINE__);                                                        \
+            return DCLL_ECUDA;                                                                  \
+        }                                                                                       \
+    } while (0)
+
+#define DCLL_LAUNCH_OK(name)                                                                         \
+    do {                                                                                             \
+        cudaError_t _e = cudaGetLastError();                                                         \
+        if (_e != cudaSuccess) {                                                                     \
+            ::dcll::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));              \
+            return DCLL_ECUDA;                                                                       \
+        }                                                                                            \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Derived geometry of a layer.
+struct Geo {
+    int Hc, Wc, Hp, Wp, F, Ktot, CoutPad, nW;
+};
+static inline Geo geo_of(const dcll_conv_layer *L) {
+    Geo g;
+    g.Hc = L->H + 2 * L->padH - L->KH + 1;
+    g.Wc = L->W + 2 * L->padW - L->KW + 1;
+    g.Hp = g.Hc / L->poolH;
+    g.Wp = g.Wc / L->poolW;
+    g.F = L->Cout * g.Hp * g.Wp;
+    g.Ktot = L->K * (L->output_layer ? 2 : 1);
+    g.CoutPad = ceil_div(L->Cout, 32) * 32;
+    g.nW = L->Cout * L->Cin * L->KH * L->KW;
+    return g;
+}
+
+// Workspace carve-up (offsets in bytes, 256-B aligned).
+struct WsLayout {
+    int n_ro;            // read-out partial blocks
+    int n_split;         // weight-gradient position splits
+    size_t off_ro_part;  // float [n_ro][B][Ktot]
+    size_t off_go;       // float [B][K]   dL/dpvoutput
+    size_t off_go2;      // float [B][K]   dL/doutput (output layer)
+    size_t off_wg_part;  // float [n_split][nW + Cout]
+    size_t total;
+};
+WsLayout ws_layout(const dcll_conv_layer *L);
+
+// Launchers implemented in the individual .cu files (all asynchronous on `st`).
+int launch_conv_fwd(const dcll_conv_layer *L, const void *x, cudaStream_t st);
+int launch_readout_fwd(const dcll_conv_layer *L, const float *target, int loss_kind, int32_t *clout,
+                       float *loss_out, cudaStream_t st);
+int launch_loss_grad(const dcll_conv_layer *L, const float *target, int loss_kind, float *loss_out, cudaStream_t st);
+int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st);
+int launch_wgrad(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st);
+int wgrad_splits(const dcll_conv_layer *L);
+struct AdamScalars;
+int launch_adam_flat(float *w, const float *g, float *m, float *v, size_t n, const AdamScalars &sc, cudaStream_t st);
+
+// Scalars of one Adam step, computed on the host in double exactly as torch does
+// (torch/optim/adam.py: bias_correction1/2, step_size, bias_correction2_sqrt).
+struct AdamScalars {
+    float wd, beta1, one_minus_beta1, beta2, one_minus_beta2, neg_step_size, bc2_sqrt, eps;
+};
+AdamScalars adam_scalars(const dcll_adam &a, int64_t step_after);
+
+__device__ __forceinline__ void adam_elem(float &w, float g, float &m, float &v, const AdamScalars &s) {
+    if (s.wd != 0.f) g = __fmaf_rn(s.wd, w, g);                       // grad.add(param, alpha=wd)
+    // exp_avg.lerp_(grad, 1-beta1)
+    if (s.one_minus_beta1 < 0.5f) m = __fmaf_rn(s.one_minus_beta1, __fsub_rn(g, m), m);
+    else m = __fsub_rn(g, __fmul_rn(__fsub_rn(g, m), __fsub_rn(1.f, s.one_minus_beta1)));
+    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
+    v = __fadd_rn(__fmul_rn(v, s.beta2), __fmul_rn(__fmul_rn(s.one_minus_beta2, g), g));
+    float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), s.bc2_sqrt), s.eps);
+    w = __fadd_rn(w, __fdiv_rn(__fmul_rn(s.neg_step_size, m), denom)); // addcdiv_(m, denom, -step_size)
+}
+
+__device__ __forceinline__ float sigmoidf_ref(float x) {
+    // 1/(1+exp(-x)) with IEEE division: matches torch-CPU sigmoid to ~1 ulp
+    return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x)));
+}
+
+// d(mean-reduced loss)/d(pred): torch multiplies by norm = float(1/numel) (float(2/numel) for MSE),
+// aten/src/ATen/native/cpu/PointwiseOpsKernel.cpp (smooth_l1_backward, mse_backward).
+__device__ __forceinline__ float loss_grad_elem(float d, int kind, int numel) {
+    if (kind == DCLL_LOSS_MSE) return __fmul_rn((float)(2.0 / (double)numel), d);
+    const float norm = (float)(1.0 / (double)numel);
+    if (kind == DCLL_LOSS_SMOOTHL1) return d < -1.f ? -norm : (d > 1.f ? norm : __fmul_rn(norm, d));
+    return d > 0.f ? norm : (d < 0.f ? -norm : 0.f);
+}
+__device__ __forceinline__ float loss_value_elem(float d, int kind) {
+    if (kind == DCLL_LOSS_SMOOTHL1) return fabsf(d) < 1.f ? 0.5f * d * d : fabsf(d) - 0.5f;
+    if (kind == DCLL_LOSS_MSE) return d * d;
+    return fabsf(d);
+}
+
+}  // namespace dcll

@@ -1,0 +1,319 @@
+// C-ABI glue of libdcll_b200: argument checks, workspace carve-up, the per-layer step entry points and the
+// whole-window driver that replaces the Python T-loop of train.py:249-251 / test_radio_ml.py:144-145.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace dcll {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+WsLayout ws_layout(const dcll_conv_layer *L) {
+    Geo g = geo_of(L);
+    WsLayout w;
+    w.n_ro = max(1, min(ceil_div(g.F, 32), 148));
+    w.n_split = wgrad_splits(L);
+    size_t off = 0;
+    w.off_ro_part = off;
+    off = align_up(off + sizeof(float) * (size_t)w.n_ro * L->B * g.Ktot, 256);
+    w.off_go = off;
+    off = align_up(off + sizeof(float) * (size_t)L->B * L->K, 256);
+    w.off_go2 = off;
+    off = align_up(off + sizeof(float) * (size_t)L->B * L->K, 256);
+    w.off_wg_part = off;
+    off = align_up(off + sizeof(float) * (size_t)w.n_split * (g.nW + L->Cout), 256);
+    w.total = off;
+    return w;
+}
+
+AdamScalars adam_scalars(const dcll_adam &a, int64_t step_after) {
+    // torch/optim/adam.py (_single_tensor_adam), python-float arithmetic
+    double bc1 = 1.0 - pow(a.beta1, (double)step_after);
+    double bc2 = 1.0 - pow(a.beta2, (double)step_after);
+    double step_size = a.lr / bc1;
+    AdamScalars s;
+    s.wd = (float)a.weight_decay;
+    s.beta1 = (float)a.beta1;
+    s.one_minus_beta1 = (float)(1.0 - a.beta1);
+    s.beta2 = (float)a.beta2;
+    s.one_minus_beta2 = (float)(1.0 - a.beta2);
+    s.neg_step_size = (float)(-step_size);
+    s.bc2_sqrt = (float)sqrt(bc2);
+    s.eps = (float)a.eps;
+    return s;
+}
+
+static int check_layer(const dcll_conv_layer *L, const char *who) {
+    DCLL_REQUIRE(L, DCLL_EINVAL, "%s: null layer", who);
+    DCLL_REQUIRE(L->B > 0 && L->Cin > 0 && L->H > 0 && L->W > 0 && L->Cout > 0 && L->K > 0, DCLL_EINVAL,
+                 "%s: non-positive dimension", who);
+    Geo g = geo_of(L);
+    DCLL_REQUIRE(g.Hc > 0 && g.Wc > 0, DCLL_EINVAL, "%s: kernel larger than the padded input", who);
+    DCLL_REQUIRE(L->poolH >= 1 && L->poolH <= 2 && L->poolW >= 1 && L->poolW <= 2, DCLL_EUNSUPPORTED,
+                 "%s: pooling (%d,%d): each axis must be 1 or 2", who, L->poolH, L->poolW);
+    DCLL_REQUIRE(g.Hp > 0 && g.Wp > 0, DCLL_EINVAL, "%s: pooled output is empty (%dx%d conv output, pooling (%d,%d))", who,
+                 g.Hc, g.Wc, L->poolH, L->poolW);
+    DCLL_REQUIRE(L->precision == DCLL_PREC_FP32, DCLL_EUNSUPPORTED, "%s: precision mode %d not built", who, L->precision);
+    DCLL_REQUIRE(L->alpha && L->alphas && L->tau_m && L->tau_s && L->weight && L->weight_t && L->bias && L->wo && L->bo,
+                 DCLL_EINVAL, "%s: null parameter pointer", who);
+    DCLL_REQUIRE(!L->output_layer || (L->wout && L->bout && L->output), DCLL_EINVAL, "%s: output layer without output_", who);
+    DCLL_REQUIRE(L->eps0[0] && L->eps0[1] && L->eps1[0] && L->eps1[1], DCLL_EINVAL, "%s: null state pointer", who);
+    DCLL_REQUIRE(!(L->wrp > 0.f) || L->arp, DCLL_EINVAL, "%s: refractory layer without arp state", who);
+    DCLL_REQUIRE(L->spikes && L->pv && L->pvoutput, DCLL_EINVAL, "%s: null output pointer", who);
+    DCLL_REQUIRE(L->poolH * L->poolW == 1 || L->pool_idx, DCLL_EINVAL, "%s: pooled layer without pool_idx", who);
+    DCLL_REQUIRE(L->x_mode == DCLL_X_DENSE || (L->x_mode == DCLL_X_CELLS && L->Cin == 1), DCLL_EINVAL,
+                 "%s: cell input needs Cin == 1", who);
+    DCLL_REQUIRE(L->workspace && L->workspace_bytes >= ws_layout(L).total, DCLL_EINVAL,
+                 "%s: workspace too small (%zu < %zu)", who, L->workspace_bytes, ws_layout(L).total);
+    const void *al[] = {L->arp, L->spikes, L->pv, L->pvmem, L->weight_t, L->workspace};
+    for (const void *q : al) DCLL_REQUIRE(((uintptr_t)q & 15) == 0, DCLL_EINVAL, "%s: tensor not 16-byte aligned", who);
+    return DCLL_OK;
+}
+
+static int step_fwd(dcll_conv_layer *L, const void *x, const float *target, int loss_kind, int32_t *clout, float *loss_out,
+                    cudaStream_t st) {
+    int rc = launch_conv_fwd(L, x, st);
+    if (rc != DCLL_OK) return rc;
+    L->cur ^= 1;
+    return launch_readout_fwd(L, target, loss_kind, clout, loss_out, st);
+}
+
+static int step_bwd(dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st) {
+    int rc = launch_readout_bwd(L, a, st);
+    if (rc != DCLL_OK) return rc;
+    rc = launch_wgrad(L, a, st);
+    if (rc != DCLL_OK) return rc;
+    if (a->apply_update) {
+        a->adam_i2h.step += 1;
+        if (L->output_layer) a->adam_out.step += 1;
+    }
+    return DCLL_OK;
+}
+
+static int check_train(const dcll_conv_layer *L, const dcll_train_args *a, const char *who) {
+    DCLL_REQUIRE(a, DCLL_EINVAL, "%s: null train args", who);
+    DCLL_REQUIRE(L->g_u, DCLL_EINVAL, "%s: null g_u scratch", who);
+    DCLL_REQUIRE(a->loss_kind >= DCLL_LOSS_SMOOTHL1 && a->loss_kind <= DCLL_LOSS_EXTERNAL, DCLL_EINVAL, "%s: unknown loss", who);
+    DCLL_REQUIRE(a->loss_kind != DCLL_LOSS_EXTERNAL || (a->g_o_ext && (!L->output_layer || a->g_o2_ext)), DCLL_EINVAL,
+                 "%s: external loss gradient missing", who);
+    if (a->apply_update) {
+        DCLL_REQUIRE(a->adam_i2h.m_w && a->adam_i2h.v_w && a->adam_i2h.m_b && a->adam_i2h.v_b, DCLL_EINVAL,
+                     "%s: null Adam state (i2h)", who);
+        DCLL_REQUIRE(!L->output_layer || (a->adam_out.m_w && a->adam_out.v_w && a->adam_out.m_b && a->adam_out.v_b),
+                     DCLL_EINVAL, "%s: null Adam state (output_)", who);
+    } else {
+        DCLL_REQUIRE(a->grad_w && a->grad_b, DCLL_EINVAL, "%s: apply_update == 0 needs gradient buffers", who);
+        DCLL_REQUIRE(!L->output_layer || (a->grad_wout && a->grad_bout), DCLL_EINVAL, "%s: needs output_ gradient buffers",
+                     who);
+    }
+    return DCLL_OK;
+}
+
+__global__ void vote_kernel(const int32_t *__restrict__ clout, int T, int t_stride, int B, int K, int32_t *__restrict__ pred) {
+    // Counter(...).most_common(1): highest count, first-seen wins ties (dcll/pytorch_libdcll.py:51)
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int cnt[64], first[64];
+    for (int k = 0; k < 64; ++k) cnt[k] = 0, first[k] = 0x7fffffff;
+    for (int t = 0; t < T; ++t) {
+        int c = clout[(size_t)t * t_stride + b];
+        if (c >= 0 && c < K) {
+            if (cnt[c] == 0) first[c] = t;
+            cnt[c]++;
+        }
+    }
+    int best = 0;
+    for (int k = 1; k < K; ++k)
+        if (cnt[k] > cnt[best] || (cnt[k] == cnt[best] && first[k] < first[best])) best = k;
+    pred[b] = best;
+}
+
+__global__ void quantize_kernel(const float *__restrict__ w, int rows, int cols, int8_t *__restrict__ codes,
+                                float *__restrict__ scales) {
+    // one CTA per output channel: s = max|w| / 127 (1 if the row is all zero), q = clamp(rint(w / s), -127, 127)
+    __shared__ float red[32];
+    __shared__ float s_scale;
+    const int r = blockIdx.x;
+    const float *row = w + (size_t)r * cols;
+    float m = 0.f;
+    for (int i = threadIdx.x; i < cols; i += blockDim.x) m = fmaxf(m, fabsf(row[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mm = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) mm = fmaxf(mm, red[i]);
+        float s = mm > 0.f ? __fdiv_rn(mm, 127.f) : 1.f;
+        s_scale = s;
+        scales[r] = s;
+    }
+    __syncthreads();
+    const float s = s_scale;
+    for (int i = threadIdx.x; i < cols; i += blockDim.x) {
+        float q = rintf(__fdiv_rn(row[i], s));
+        q = fminf(fmaxf(q, -127.f), 127.f);
+        codes[(size_t)r * cols + i] = (int8_t)q;
+    }
+}
+
+__global__ void dequantize_kernel(const int8_t *__restrict__ codes, const float *__restrict__ scales, int rows, int cols,
+                                  float *__restrict__ w) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * cols) return;
+    w[i] = __fmul_rn((float)codes[i], scales[i / cols]);
+}
+
+}  // namespace dcll
+
+using namespace dcll;
+
+extern "C" __attribute__((visibility("default"))) int dcll_abi_version(void) { return DCLL_ABI_VERSION; }
+extern "C" __attribute__((visibility("default"))) const char *dcll_last_error(void) { return g_err; }
+extern "C" __attribute__((visibility("default"))) size_t dcll_sizeof_conv_layer(void) { return sizeof(dcll_conv_layer); }
+extern "C" __attribute__((visibility("default"))) size_t dcll_sizeof_train_args(void) { return sizeof(dcll_train_args); }
+
+extern "C" __attribute__((visibility("default"))) size_t dcll_conv_workspace_bytes(const dcll_conv_layer *L) {
+    if (!L || L->B <= 0 || L->Cin <= 0 || L->Cout <= 0 || L->K <= 0) return 0;
+    return ws_layout(L).total;
+}
+
+extern "C" __attribute__((visibility("default"))) int dcll_conv_step_fwd(dcll_conv_layer *L, const void *x, int32_t *clout, void *stream) {
+    int rc = check_layer(L, "dcll_conv_step_fwd");
+    if (rc != DCLL_OK) return rc;
+    DCLL_REQUIRE(x, DCLL_EINVAL, "dcll_conv_step_fwd: null input");
+    return step_fwd(L, x, nullptr, 0, clout, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int dcll_conv_core_fwd(dcll_conv_layer *L, const void *x, void *stream) {
+    DCLL_REQUIRE(L && x, DCLL_EINVAL, "dcll_conv_core_fwd: null argument");
+    DCLL_REQUIRE(L->poolH == 1 && L->poolW == 1, DCLL_EINVAL, "dcll_conv_core_fwd: the i2h core has no pooling");
+    DCLL_REQUIRE(L->alpha && L->alphas && L->tau_m && L->tau_s && L->weight_t && L->bias && L->eps0[0] && L->eps0[1] &&
+                     L->eps1[0] && L->eps1[1] && L->spikes && L->pv && (!(L->wrp > 0.f) || L->arp),
+                 DCLL_EINVAL, "dcll_conv_core_fwd: null tensor");
+    DCLL_REQUIRE(L->x_mode == DCLL_X_DENSE || L->Cin == 1, DCLL_EINVAL, "dcll_conv_core_fwd: cell input needs Cin == 1");
+    int rc = launch_conv_fwd(L, x, (cudaStream_t)stream);
+    if (rc == DCLL_OK) L->cur ^= 1;
+    return rc;
+}
+
+extern "C" __attribute__((visibility("default"))) int dcll_conv_step_bwd_update(dcll_conv_layer *L, dcll_train_args *a, void *stream) {
+    int rc = check_layer(L, "dcll_conv_step_bwd_update");
+    if (rc != DCLL_OK) return rc;
+    rc = check_train(L, a, "dcll_conv_step_bwd_update");
+    if (rc != DCLL_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->loss_kind == DCLL_LOSS_EXTERNAL) {
+        WsLayout ws = ws_layout(L);
+        char *base = (char *)L->workspace;
+        size_t n = sizeof(float) * (size_t)L->B * L->K;
+        DCLL_CUDA_OK(cudaMemcpyAsync(base + ws.off_go, a->g_o_ext, n, cudaMemcpyDeviceToDevice, st));
+        if (L->output_layer) DCLL_CUDA_OK(cudaMemcpyAsync(base + ws.off_go2, a->g_o2_ext, n, cudaMemcpyDeviceToDevice, st));
+    } else {
+        DCLL_REQUIRE(a->target, DCLL_EINVAL, "dcll_conv_step_bwd_update: null target");
+        if (a->loss_out) DCLL_CUDA_OK(cudaMemsetAsync(a->loss_out, 0, sizeof(float), st));
+        rc = launch_loss_grad(L, a->target, a->loss_kind, a->loss_out, st);
+        if (rc != DCLL_OK) return rc;
+    }
+    return step_bwd(L, a, st);
+}
+
+extern "C" __attribute__((visibility("default"))) int dcll_conv_apply_update(dcll_conv_layer *L, dcll_train_args *a, void *stream) {
+    int rc = check_layer(L, "dcll_conv_apply_update");
+    if (rc != DCLL_OK) return rc;
+    DCLL_REQUIRE(a && a->grad_w && a->grad_b, DCLL_EINVAL, "dcll_conv_apply_update: null gradients");
+    cudaStream_t st = (cudaStream_t)stream;
+    Geo g = geo_of(L);
+    AdamScalars sc = adam_scalars(a->adam_i2h, a->adam_i2h.step + 1);
+    rc = launch_adam_flat(L->weight, a->grad_w, a->adam_i2h.m_w, a->adam_i2h.v_w, (size_t)g.nW, sc, st);
+    if (rc != DCLL_OK) return rc;
+    rc = launch_adam_flat(L->bias, a->grad_b, a->adam_i2h.m_b, a->adam_i2h.v_b, (size_t)L->Cout, sc, st);
+    if (rc != DCLL_OK) return rc;
+    a->adam_i2h.step += 1;
+    if (L->output_layer) {
+        DCLL_REQUIRE(a->grad_wout && a->grad_bout, DCLL_EINVAL, "dcll_conv_apply_update: null output_ gradients");
+        AdamScalars so = adam_scalars(a->adam_out, a->adam_out.step + 1);
+        rc = launch_adam_flat(L->wout, a->grad_wout, a->adam_out.m_w, a->adam_out.v_w, (size_t)L->K * g.F, so, st);
+        if (rc != DCLL_OK) return rc;
+        rc = launch_adam_flat(L->bout, a->grad_bout, a->adam_out.m_b, a->adam_out.v_b, (size_t)L->K, so, st);
+        if (rc != DCLL_OK) return rc;
+        a->adam_out.step += 1;
+    }
+    return dcll_conv_sync_weights(L, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int dcll_net_window(dcll_conv_layer *layers, dcll_train_args *train, int n_layers, const void *x0,
+                               const float *target, int64_t target_t_stride, int T, int train_mode, int burnin,
+                               const int32_t *iter0, int32_t *clout, void *stream) {
+    DCLL_REQUIRE(layers && n_layers > 0 && x0 && T > 0 && iter0, DCLL_EINVAL, "dcll_net_window: bad arguments");
+    DCLL_REQUIRE(!train_mode || (train && target), DCLL_EINVAL, "dcll_net_window: training needs train args and a target");
+    for (int l = 0; l < n_layers; ++l) {
+        int rc = check_layer(&layers[l], "dcll_net_window");
+        if (rc != DCLL_OK) return rc;
+        if (train_mode) {
+            rc = check_train(&layers[l], &train[l], "dcll_net_window");
+            if (rc != DCLL_OK) return rc;
+            DCLL_REQUIRE(train[l].apply_update, DCLL_EINVAL, "dcll_net_window: apply_update must be set");
+            DCLL_REQUIRE(train[l].loss_kind != DCLL_LOSS_EXTERNAL, DCLL_EUNSUPPORTED,
+                         "dcll_net_window: external loss gradients need the per-step API");
+        }
+        if (l > 0) {
+            Geo gp = geo_of(&layers[l - 1]);
+            DCLL_REQUIRE(layers[l].x_mode == DCLL_X_DENSE && layers[l].Cin == layers[l - 1].Cout && layers[l].H == gp.Hp &&
+                             layers[l].W == gp.Wp && layers[l].B == layers[0].B,
+                         DCLL_EINVAL, "dcll_net_window: layer %d does not chain onto layer %d", l, l - 1);
+        }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const dcll_conv_layer &L0 = layers[0];
+    const size_t x_stride = L0.x_mode == DCLL_X_CELLS ? (size_t)L0.B * 2 * sizeof(int32_t)
+                                                      : (size_t)L0.B * L0.Cin * L0.H * L0.W * sizeof(float);
+    for (int t = 0; t < T; ++t) {
+        const float *tgt = target ? target + (size_t)t * target_t_stride : nullptr;
+        for (int l = 0; l < n_layers; ++l) {
+            dcll_conv_layer *L = &layers[l];
+            const void *x = l == 0 ? (const void *)((const char *)x0 + (size_t)t * x_stride) : (const void *)layers[l - 1].spikes;
+            const int it = iter0[l] + t + 1;                       // DCLLBase.forward :656
+            const bool do_train = train_mode && it >= burnin;      // train_dcll :692
+            int32_t *co = clout ? clout + ((size_t)t * n_layers + l) * L->B : nullptr;
+            int rc = step_fwd(L, x, do_train ? tgt : nullptr, do_train ? train[l].loss_kind : 0, co, nullptr, st);
+            if (rc != DCLL_OK) return rc;
+            if (do_train) {
+                rc = step_bwd(L, &train[l], st);
+                if (rc != DCLL_OK) return rc;
+            }
+        }
+    }
+    return DCLL_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dcll_vote(const int32_t *clout, int T, int t_stride, int B, int K, int32_t *pred, void *stream) {
+    DCLL_REQUIRE(clout && pred && T > 0 && B > 0 && K > 0 && K <= 64, DCLL_EINVAL, "dcll_vote: bad arguments (K <= 64)");
+    vote_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(clout, T, t_stride, B, K, pred);
+    DCLL_LAUNCH_OK("vote_kernel");
+    return DCLL_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dcll_quantize(const float *w, int rows, int cols, int8_t *codes, float *scales, void *stream) {
+    DCLL_REQUIRE(w && codes && scales && rows > 0 && cols > 0, DCLL_EINVAL, "dcll_quantize: bad arguments");
+    quantize_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(w, rows, cols, codes, scales);
+    DCLL_LAUNCH_OK("quantize_kernel");
+    return DCLL_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dcll_dequantize(const int8_t *codes, const float *scales, int rows, int cols, float *w, void *stream) {
+    DCLL_REQUIRE(w && codes && scales && rows > 0 && cols > 0, DCLL_EINVAL, "dcll_dequantize: bad arguments");
+    size_t n = (size_t)rows * cols;
+    dequantize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(codes, scales, rows, cols, w);
+    DCLL_LAUNCH_OK("dequantize_kernel");
+    return DCLL_OK;
+}

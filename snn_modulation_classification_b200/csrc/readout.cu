@@ -1,0 +1,337 @@
+// Local read-outs of a Conv2dDCLLlayer and the local-loss gradient.
+//
+// Replaces (reference, dcll/pytorch_libdcll.py):
+//   :602-603  pvoutput = i2o(flatten(pool(pv)))                     -> readout_fwd_kernel (+ finish)
+//   :605-606  output   = output_(flatten.detach())  (last layer)    -> same kernel, extra K rows
+//   :694-697  SmoothL1Loss(pvoutput, target) [+ (output, target)]   -> readout_finish_kernel (gradient only)
+//   :724-728  clout.append(argmax)                                  -> readout_finish_kernel (device side)
+//   :704      autograd: d loss / d membrane through i2o, pool, sigmoid -> readout_bwd_kernel
+//             d loss / d output_.{weight,bias} + optimizer2.step()  -> wout_grad_adam_kernel
+//
+// The read-out is a skinny GEMM [B,F] x [F,Ktot] whose frozen matrix (4*K*F bytes, 50 MB per layer at
+// 128x128) must be amortised over the batch, so it is a separate HBM-bound pass over pv rather than an
+// epilogue of the convolution: every CTA keeps a 32-wide slice of Wo in shared memory and sweeps it
+// over all samples.  Partials are reduced in a fixed order (no float atomics): results are
+// deterministic run to run.
+#include "common.cuh"
+
+namespace dcll {
+
+constexpr int RO_BM = 64;   // samples per tile
+constexpr int RO_BK = 32;   // features per tile
+constexpr int RO_PITCH = RO_BK + 4;
+
+// partial[blk][b][kt] = sum over this CTA's feature tiles of pv[b,f] * Wcat[kt,f],  Wcat = [wo ; wout]
+template <int KJ>
+__global__ void __launch_bounds__(256) readout_fwd_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
+                                                          const float *__restrict__ wout, int B, int F, int K, int Ktot,
+                                                          float *__restrict__ partial) {
+    __shared__ __align__(16) float pvs[RO_BM * RO_PITCH];
+    __shared__ __align__(16) float wos[16 * KJ * RO_PITCH];
+    const int tid = threadIdx.x;
+    const int tb = tid & 15, tk = tid >> 4;
+    const int n_ft = (F + RO_BK - 1) / RO_BK;
+    const int lr = tid >> 5, lc = tid & 31;  // loader: 8 rows x 32 columns per pass
+
+    for (int b0 = 0; b0 < B; b0 += RO_BM) {
+        float acc[4][KJ];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < KJ; ++j) acc[i][j] = 0.f;
+        for (int ft = blockIdx.x; ft < n_ft; ft += gridDim.x) {
+            const int f = ft * RO_BK + lc;
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < RO_BM; r += 8) {
+                int b = b0 + r + lr;
+                pvs[(r + lr) * RO_PITCH + lc] = (b < B && f < F) ? __ldg(pv + (size_t)b * F + f) : 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < 16 * KJ; r += 8) {
+                int k = r + lr;
+                float v = 0.f;
+                if (f < F && k < Ktot) v = k < K ? __ldg(wo + (size_t)k * F + f) : __ldg(wout + (size_t)(k - K) * F + f);
+                wos[k * RO_PITCH + lc] = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int f4 = 0; f4 < RO_BK; f4 += 4) {
+                float4 a[4], w[KJ];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4 *>(pvs + (tb + 16 * i) * RO_PITCH + f4);
+#pragma unroll
+                for (int j = 0; j < KJ; ++j) w[j] = *reinterpret_cast<const float4 *>(wos + (tk + 16 * j) * RO_PITCH + f4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < KJ; ++j) {
+                        acc[i][j] = fmaf(a[i].x, w[j].x, acc[i][j]);
+                        acc[i][j] = fmaf(a[i].y, w[j].y, acc[i][j]);
+                        acc[i][j] = fmaf(a[i].z, w[j].z, acc[i][j]);
+                        acc[i][j] = fmaf(a[i].w, w[j].w, acc[i][j]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int b = b0 + tb + 16 * i;
+#pragma unroll
+            for (int j = 0; j < KJ; ++j) {
+                int k = tk + 16 * j;
+                if (b < B && k < Ktot) partial[((size_t)blockIdx.x * B + b) * Ktot + k] = acc[i][j];
+            }
+        }
+    }
+}
+
+// One CTA per sample: fixed-order reduction of the partials, + bias, loss gradient, argmax.
+__global__ void __launch_bounds__(256) readout_finish_kernel(const float *__restrict__ partial, int n_part, int B, int K,
+                                                             int Ktot, const float *__restrict__ bo,
+                                                             const float *__restrict__ bout, const float *__restrict__ target,
+                                                             int loss_kind, float *__restrict__ pvoutput,
+                                                             float *__restrict__ output, float *__restrict__ g_o,
+                                                             float *__restrict__ g_o2, int32_t *__restrict__ clout,
+                                                             float *__restrict__ loss_out) {
+    __shared__ float red[4][64];
+    __shared__ float vals[64];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int kk = tid & 63, sl = tid >> 6;
+    float s = 0.f;
+    if (kk < Ktot)
+        for (int c = sl; c < n_part; c += 4) s += partial[((size_t)c * B + b) * Ktot + kk];
+    red[sl][kk] = s;
+    __syncthreads();
+    float lsum = 0.f;
+    if (tid < Ktot) {
+        const bool second = tid >= K;
+        const int k = second ? tid - K : tid;
+        float v = ((red[0][tid] + red[1][tid]) + red[2][tid]) + red[3][tid];
+        v += second ? bout[k] : bo[k];
+        vals[tid] = v;
+        (second ? output : pvoutput)[(size_t)b * K + k] = v;
+        if (target) {
+            float d = v - target[(size_t)b * K + k];
+            float g = loss_grad_elem(d, loss_kind, B * K);
+            (second ? g_o2 : g_o)[(size_t)b * K + k] = g;
+            lsum = loss_value_elem(d, loss_kind) / (float)(B * K);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // DCLLClassification.forward :725-728 -- argmax of output on the output layer, else of pvoutput;
+        // first maximum wins, as torch.argmax does.
+        if (clout) {
+            const int base = (Ktot > K) ? K : 0;
+            int best = 0;
+            float bv = vals[base];
+            for (int k = 1; k < K; ++k)
+                if (vals[base + k] > bv) bv = vals[base + k], best = k;
+            clout[b] = best;
+        }
+    }
+    if (loss_out && target) {
+        // diagnostic only (train_dcll returns it, ConvNetwork.learn drops it): order-dependent atomics are fine
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+        if ((tid & 31) == 0 && tid < 64 && lsum != 0.f) atomicAdd(loss_out, lsum);
+    }
+}
+
+// g_u[b,f] = (sum_k g_o[b,k] Wo[k,f]) * (1 - pv) * pv      (gradient w.r.t. the membrane at the pool argmax)
+// Thread = one feature column of Wo held in registers, swept over a slice of the batch.
+template <int KMAX>
+__global__ void __launch_bounds__(256) readout_bwd_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
+                                                          const float *__restrict__ g_o, int B, int F, int K, int b_per_blk,
+                                                          float *__restrict__ g_u) {
+    __shared__ float gs[64][KMAX];
+    const int tid = threadIdx.x;
+    const int f = blockIdx.x * 256 + tid;
+    float w[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) w[k] = (k < K && f < F) ? __ldg(wo + (size_t)k * F + f) : 0.f;
+    const int b_begin = blockIdx.y * b_per_blk, b_end = min(B, b_begin + b_per_blk);
+    for (int b0 = b_begin; b0 < b_end; b0 += 64) {
+        const int nb = min(64, b_end - b0);
+        __syncthreads();
+        for (int i = tid; i < 64 * KMAX; i += 256) {
+            int bb = i / KMAX, k = i - bb * KMAX;
+            gs[bb][k] = (bb < nb && k < K) ? g_o[(size_t)(b0 + bb) * K + k] : 0.f;
+        }
+        __syncthreads();
+        if (f < F) {
+            for (int bb = 0; bb < nb; ++bb) {
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) s = fmaf(gs[bb][k], w[k], s);
+                size_t o = (size_t)(b0 + bb) * F + f;
+                float pvv = __ldg(pv + o);
+                g_u[o] = s * (1.f - pvv) * pvv;
+            }
+        }
+    }
+}
+
+// output_ read-out (last layer): gWout[k,f] = sum_b g_o2[b,k] pv[b,f], gbout[k] = sum_b g_o2[b,k],
+// followed by optimizer2.step() (Adam, lr 1e-4, torch defaults; dcll/pytorch_libdcll.py:636-638,713-714).
+template <int KMAX>
+__global__ void __launch_bounds__(256) wout_grad_adam_kernel(const float *__restrict__ pv, const float *__restrict__ g_o2,
+                                                             int B, int F, int K, float *__restrict__ wout,
+                                                             float *__restrict__ bout, float *__restrict__ m_w,
+                                                             float *__restrict__ v_w, float *__restrict__ m_b,
+                                                             float *__restrict__ v_b, float *__restrict__ grad_w,
+                                                             float *__restrict__ grad_b, int apply, AdamScalars sc) {
+    __shared__ float gs[64][KMAX];
+    const int tid = threadIdx.x;
+    const int f = blockIdx.x * 256 + tid;
+    float acc[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
+    float bsum = 0.f;  // block 0, tid < K: bias gradient
+    for (int b0 = 0; b0 < B; b0 += 64) {
+        const int nb = min(64, B - b0);
+        __syncthreads();
+        for (int i = tid; i < 64 * KMAX; i += 256) {
+            int bb = i / KMAX, k = i - bb * KMAX;
+            gs[bb][k] = (bb < nb && k < K) ? g_o2[(size_t)(b0 + bb) * K + k] : 0.f;
+        }
+        __syncthreads();
+        if (f < F) {
+            for (int bb = 0; bb < nb; ++bb) {
+                float pvv = __ldg(pv + (size_t)(b0 + bb) * F + f);
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) acc[k] = fmaf(gs[bb][k], pvv, acc[k]);
+            }
+        }
+        if (blockIdx.x == 0 && tid < K)
+            for (int bb = 0; bb < nb; ++bb) bsum += gs[bb][tid];
+    }
+    if (f < F) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            if (k < K) {
+                size_t o = (size_t)k * F + f;
+                if (grad_w) grad_w[o] = acc[k];
+                if (apply) {
+                    float w = wout[o], m = m_w[o], v = v_w[o];
+                    adam_elem(w, acc[k], m, v, sc);
+                    wout[o] = w, m_w[o] = m, v_w[o] = v;
+                }
+            }
+        }
+    }
+    if (blockIdx.x == 0 && tid < K) {
+        if (grad_b) grad_b[tid] = bsum;
+        if (apply) {
+            float w = bout[tid], m = m_b[tid], v = v_b[tid];
+            adam_elem(w, bsum, m, v, sc);
+            bout[tid] = w, m_b[tid] = m, v_b[tid] = v;
+        }
+    }
+}
+
+// g_o / g_o2 from stored read-outs (layer-level API: the target is only known after forward returned)
+__global__ void loss_grad_kernel(const float *__restrict__ pvoutput, const float *__restrict__ output,
+                                 const float *__restrict__ target, int B, int K, int loss_kind, float *__restrict__ g_o,
+                                 float *__restrict__ g_o2, float *__restrict__ loss_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lsum = 0.f;
+    if (i < B * K) {
+        float t = target[i];
+        float d = pvoutput[i] - t;
+        g_o[i] = loss_grad_elem(d, loss_kind, B * K);
+        lsum = loss_value_elem(d, loss_kind) / (float)(B * K);
+        if (output) {
+            float d2 = output[i] - t;
+            g_o2[i] = loss_grad_elem(d2, loss_kind, B * K);
+            lsum += loss_value_elem(d2, loss_kind) / (float)(B * K);
+        }
+    }
+    if (loss_out) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+        if ((threadIdx.x & 31) == 0 && lsum != 0.f) atomicAdd(loss_out, lsum);
+    }
+}
+
+// generic Adam over a flat parameter (data-parallel path: gradients arrive from the allreduce)
+__global__ void adam_flat_kernel(float *__restrict__ w, const float *__restrict__ g, float *__restrict__ m,
+                                 float *__restrict__ v, size_t n, AdamScalars sc) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float wv = w[i], mv = m[i], vv = v[i];
+    adam_elem(wv, g[i], mv, vv, sc);
+    w[i] = wv, m[i] = mv, v[i] = vv;
+}
+
+int launch_readout_fwd(const dcll_conv_layer *L, const float *target, int loss_kind, int32_t *clout, float *loss_out,
+                       cudaStream_t st) {
+    Geo g = geo_of(L);
+    WsLayout ws = ws_layout(L);
+    char *base = (char *)L->workspace;
+    float *partial = (float *)(base + ws.off_ro_part);
+    float *g_o = (float *)(base + ws.off_go), *g_o2 = (float *)(base + ws.off_go2);
+    const int kj = ceil_div(g.Ktot, 16);
+    DCLL_REQUIRE(kj >= 1 && kj <= 4, DCLL_EUNSUPPORTED, "read-out width %d > 64 unsupported", g.Ktot);
+#define RO_CASE(J)                                                                                                   \
+    case J:                                                                                                          \
+        readout_fwd_kernel<J><<<ws.n_ro, 256, 0, st>>>(L->pv, L->wo, L->wout, L->B, g.F, L->K, g.Ktot, partial);     \
+        break;
+    switch (kj) { RO_CASE(1) RO_CASE(2) RO_CASE(3) RO_CASE(4) }
+#undef RO_CASE
+    DCLL_LAUNCH_OK("readout_fwd_kernel");
+    readout_finish_kernel<<<L->B, 256, 0, st>>>(partial, ws.n_ro, L->B, L->K, g.Ktot, L->bo, L->bout, target, loss_kind,
+                                                 L->pvoutput, L->output, g_o, g_o2, clout, loss_out);
+    DCLL_LAUNCH_OK("readout_finish_kernel");
+    return DCLL_OK;
+}
+
+int launch_loss_grad(const dcll_conv_layer *L, const float *target, int loss_kind, float *loss_out, cudaStream_t st) {
+    WsLayout ws = ws_layout(L);
+    char *base = (char *)L->workspace;
+    float *g_o = (float *)(base + ws.off_go), *g_o2 = (float *)(base + ws.off_go2);
+    int n = L->B * L->K;
+    loss_grad_kernel<<<ceil_div(n, 256), 256, 0, st>>>(L->pvoutput, L->output_layer ? L->output : nullptr, target, L->B, L->K,
+                                                        loss_kind, g_o, g_o2, loss_out);
+    DCLL_LAUNCH_OK("loss_grad_kernel");
+    return DCLL_OK;
+}
+
+int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st) {
+    Geo g = geo_of(L);
+    WsLayout ws = ws_layout(L);
+    char *base = (char *)L->workspace;
+    const float *g_o = (const float *)(base + ws.off_go), *g_o2 = (const float *)(base + ws.off_go2);
+    DCLL_REQUIRE(L->K <= 32, DCLL_EUNSUPPORTED, "target_size %d > 32 unsupported in the backward read-out", L->K);
+    const int fblk = ceil_div(g.F, 256);
+    // enough CTAs to fill the machine: slice the batch when F is small
+    int slices = max(1, min(ceil_div(L->B, 64), ceil_div(2 * 148, fblk)));
+    int b_per = ceil_div(ceil_div(L->B, slices), 64) * 64;
+    slices = ceil_div(L->B, b_per);
+    dim3 grid(fblk, slices);
+    if (L->K <= 16)
+        readout_bwd_kernel<16><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u);
+    else
+        readout_bwd_kernel<32><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u);
+    DCLL_LAUNCH_OK("readout_bwd_kernel");
+    if (L->output_layer) {
+        AdamScalars sc = adam_scalars(a->adam_out, a->adam_out.step + 1);
+        dcll_adam &o = a->adam_out;
+        if (L->K <= 16)
+            wout_grad_adam_kernel<16><<<fblk, 256, 0, st>>>(L->pv, g_o2, L->B, g.F, L->K, L->wout, L->bout, o.m_w, o.v_w,
+                                                            o.m_b, o.v_b, a->grad_wout, a->grad_bout, a->apply_update, sc);
+        else
+            wout_grad_adam_kernel<32><<<fblk, 256, 0, st>>>(L->pv, g_o2, L->B, g.F, L->K, L->wout, L->bout, o.m_w, o.v_w,
+                                                            o.m_b, o.v_b, a->grad_wout, a->grad_bout, a->apply_update, sc);
+        DCLL_LAUNCH_OK("wout_grad_adam_kernel");
+    }
+    return DCLL_OK;
+}
+
+int launch_adam_flat(float *w, const float *g, float *m, float *v, size_t n, const AdamScalars &sc, cudaStream_t st) {
+    adam_flat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, g, m, v, n, sc);
+    DCLL_LAUNCH_OK("adam_flat_kernel");
+    return DCLL_OK;
+}
+
+}  // namespace dcll

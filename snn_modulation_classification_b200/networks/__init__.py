@@ -1,0 +1,191 @@
+"""Network assembly: mirror of the reference's ``networks/__init__.py`` (ref lines cited inline).
+
+``ConvNetwork`` keeps the reference API (``learn`` / ``test`` / ``reset`` / ``accuracy`` /
+``confusion_matrix`` / ``write_stats``, ``dcll_slices`` ModuleList, state_dict keys) and adds
+``learn_window`` / ``test_window``: the whole T-loop of train.py:249-251 / test_radio_ml.py:144-145 in one
+C call (``dcll_net_window``), with no per-timestep Python, host sync or allocation.
+"""
+import ctypes
+import os
+from ast import literal_eval as make_tuple
+
+import torch
+import yaml
+
+from .. import _lib
+from ..dcll.pytorch_libdcll import (Conv2dDCLLlayer, DCLLClassification, SpikeCells, _as_cuda_f32, _fill_adam,
+                                    _is_plain_adam, _loss_kind, _store_steps, device)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+# Values of the reference's networks/*.yaml, available by name so that nothing needs the reference tree.
+BUILTIN_SPECS = {
+    'radio_ml_conv': [dict(out_channels=32, kernel_size=7, padding=3, pooling=1) for _ in range(3)],
+    'mnist_conv': [dict(out_channels=16, kernel_size=7, padding=2, pooling=2),
+                   dict(out_channels=24, kernel_size=7, padding=2, pooling=1),
+                   dict(out_channels=32, kernel_size=7, padding=2, pooling=2)],
+    'radio_ml_conv_ref': [dict(out_channels=64, kernel_size=(1, 3), padding=(0, 1), pooling=(1, 2))
+                          for _ in range(7)],
+}
+
+
+def load_network_spec(yaml_path):
+    """ref:10-18.  ``yaml_path``: a YAML file with the reference's schema
+    (``conv_layers: [{out_channels, kernel_size, padding, pooling}]``, ints or tuple strings such as
+    "(1, 3)"), or the bare name of a built-in spec ('radio_ml_conv', 'mnist_conv', 'radio_ml_conv_ref')."""
+    key = os.path.splitext(os.path.basename(str(yaml_path)))[0]
+    if not os.path.isfile(yaml_path):
+        local = os.path.join(_HERE, key + '.yaml')
+        if os.path.isfile(local):
+            yaml_path = local
+        elif key in BUILTIN_SPECS:
+            return [dict(c) for c in BUILTIN_SPECS[key]]
+        else:
+            raise FileNotFoundError(yaml_path)
+    with open(yaml_path, 'r') as f:
+        network_spec = yaml.safe_load(f)
+    convs = network_spec['conv_layers']
+    for layer_spec in convs:
+        for k, v in layer_spec.items():
+            if type(v) != int:
+                layer_spec[k] = make_tuple(v)      # e.g. the string "(2, 0)" -> (2, 0)
+    return convs
+
+
+class ConvNetwork(torch.nn.Module):
+    def __init__(self, args, im_dims, batch_size, convs, target_size, act, loss, opt, opt_param, learning_rates,
+                 DCLLSlice=DCLLClassification, burnin=50):
+        super(ConvNetwork, self).__init__()
+        self.batch_size = batch_size
+        self.num_layers = len(convs)
+        self.dcll_slices = torch.nn.ModuleList()
+        n = im_dims
+        for i, conf in enumerate(convs):                                # ref:148-172
+            layer = Conv2dDCLLlayer(in_channels=n[0],
+                                    out_channels=int(conf['out_channels'] * args.netscale),
+                                    kernel_size=conf['kernel_size'], padding=conf['padding'],
+                                    pooling=conf['pooling'], im_dims=n[1:3], target_size=target_size,
+                                    alpha=args.alpha, alphas=args.alphas, alpharp=args.alpharp, wrp=args.arp,
+                                    act=act, lc_ampl=args.lc_ampl, random_tau=args.random_tau, spiking=True,
+                                    lc_dropout=False, output_layer=(i == self.num_layers - 1)
+                                    ).to(device).init_hiddens(batch_size)
+            n = torch.Size([layer.out_channels]) + layer.output_shape
+            layer_opt_param = opt_param.copy()
+            if learning_rates is not None:
+                layer_opt_param['lr'] = learning_rates[min(i, len(learning_rates) - 1)]
+            self.dcll_slices.append(DCLLSlice(dclllayer=layer, name='conv%d' % i, batch_size=batch_size, loss=loss,
+                                              optimizer=opt, kwargs_optimizer=layer_opt_param, collect_stats=True,
+                                              burnin=burnin))
+        self._win = None
+
+    # -- reference per-timestep API -------------------------------------------------------------
+    def learn(self, x, labels):                                         # ref:175-180
+        spikes = x
+        for s in self.dcll_slices:
+            spikes, _, _, _, _ = s.train_dcll(spikes, labels, regularize=False)
+
+    def test(self, x):                                                  # ref:182-185
+        spikes = x
+        for s in self.dcll_slices:
+            spikes, _, _, _ = s.forward(spikes, ignore_burnin=True)
+
+    def reset(self, init_states=False):                                 # ref:187-189
+        for s in self.dcll_slices:
+            s.init(self.batch_size, init_states=init_states)
+
+    def write_stats(self, writer, epoch, comment=''):                   # ref:191-193
+        for s in self.dcll_slices:
+            s.write_stats(writer, label='test' + comment, epoch=epoch)
+
+    def accuracy(self, labels):                                         # ref:195-196
+        return [s.accuracy(labels) for s in self.dcll_slices]
+
+    def confusion_matrix(self, labels):                                 # ref:198-199
+        return self.dcll_slices[-1].confusion_matrix(labels)
+
+    # -- whole-window fast path --------------------------------------------------------------------
+    def _window_buffers(self, batch):
+        key = (batch, self.dcll_slices[0].dclllayer.i2h.weight.device)
+        if self._win is not None and self._win['key'] == key:
+            return self._win
+        dev = key[1]
+        outs = []
+        for s in self.dcll_slices:
+            lay = s.dclllayer
+            hp, wp = lay.get_output_shape()
+            pooled = (batch, lay.out_channels, hp, wp)
+            outs.append(dict(spikes=torch.empty(pooled, device=dev), pv=torch.empty(pooled, device=dev), pvmem=None,
+                             pvoutput=torch.empty((batch, lay.target_size), device=dev),
+                             output=torch.empty((batch, lay.target_size), device=dev) if lay.output_layer else None))
+        self._win = dict(key=key, outs=outs)
+        return self._win
+
+    def _run_window(self, x, labels, train):
+        """x: dense spikes [T,B,C,H,W] (tensor) or SpikeCells-like (cells [T,B,2]); labels [B,K] or [T,B,K]."""
+        n = self.num_layers
+        if isinstance(x, SpikeCells):
+            x_t, x_mode = x.cells, _lib.X_CELLS
+            T, batch = int(x_t.shape[0]), int(x_t.shape[1])
+        else:
+            x_t, x_mode = _as_cuda_f32(x), _lib.X_DENSE
+            T, batch = int(x_t.shape[0]), int(x_t.shape[1])
+        for s in self.dcll_slices:
+            i2h = s.dclllayer.i2h
+            if i2h.state.eps0.shape[0] != batch:
+                import logging
+                logging.warning("Batch size changed from {} to {} since last iteration. Reallocating states."
+                                .format(i2h.state.eps0.shape[0], batch))
+                i2h.init_state(batch, s.dclllayer.im_dims)
+        win = self._window_buffers(batch)
+        Layers, Trains = _lib.ConvLayer * n, _lib.TrainArgs * n
+        layers, trains = Layers(), Trains()
+        olds, states = [], []
+        for i, s in enumerate(self.dcll_slices):
+            old, _ = s.dclllayer._fill_desc(layers[i], batch, x_mode if i == 0 else _lib.X_DENSE, win['outs'][i])
+            olds.append(old)
+            if train:
+                lay = s.dclllayer
+                if not (_is_plain_adam(s.optimizer) and (not lay.output_layer or _is_plain_adam(s.optimizer2))):
+                    raise NotImplementedError('learn_window needs torch.optim.Adam slices; use learn() per timestep')
+                kind = _loss_kind(s.crit)
+                if kind == _lib.LOSS_EXTERNAL:
+                    raise NotImplementedError('learn_window implements SmoothL1Loss / MSELoss / L1Loss; use learn()')
+                trains[i].loss_kind, trains[i].apply_update = kind, 1
+                st = [_fill_adam(trains[i].adam_i2h, s.optimizer, lay.i2h.weight, lay.i2h.bias)]
+                if lay.output_layer:
+                    st.append(_fill_adam(trains[i].adam_out, s.optimizer2, lay.output_.weight, lay.output_.bias))
+                states.append(st)
+        target, t_stride = None, 0
+        if labels is not None:
+            target = _as_cuda_f32(labels)
+            if target.dim() == 3:
+                t_stride = target.shape[1] * target.shape[2]
+                if target.shape[0] > 1 and bool((target[0] == target[-1]).all()) and target.shape[0] != T:
+                    raise ValueError('labels [T,B,K] must cover the window')
+        iter0 = (ctypes.c_int32 * n)(*[int(s.iter) for s in self.dcll_slices])
+        clout = torch.empty((T, n, batch), dtype=torch.int32, device=x_t.device)
+        burnin = int(self.dcll_slices[0].burnin)
+        _lib.check(_lib.lib.dcll_net_window(layers, trains if train else None, n, _lib.ptr(x_t), _lib.ptr(target),
+                                            t_stride, T, 1 if train else 0, burnin, iter0, _lib.ptr(clout),
+                                            _lib.current_stream()))
+        for i, s in enumerate(self.dcll_slices):
+            s.dclllayer.i2h._commit_state(*olds[i], flips=T)
+            s.dclllayer._ctx = None
+            # DCLLClassification.forward counting rule (ref:724): rows with ignore_burnin or iter >= burnin
+            first = 0 if not train else max(0, int(s.burnin) - int(s.iter) - 1)
+            if first < T:
+                s.clout.extend(clout[first:, i, :])
+            s.iter += T
+            if train:
+                _store_steps(states[i][0], trains[i].adam_i2h.step)
+                if s.dclllayer.output_layer:
+                    _store_steps(states[i][1], trains[i].adam_out.step)
+        return clout
+
+    def learn_window(self, x, labels):
+        """``for t in range(T): self.learn(x[t], labels[t])`` (train.py:249-251) in one call."""
+        return self._run_window(x, labels, True)
+
+    def test_window(self, x):
+        """``for t in range(T): self.test(x[t])`` (test_radio_ml.py:144-145) in one call."""
+        return self._run_window(x, None, False)

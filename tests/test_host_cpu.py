@@ -1,0 +1,139 @@
+"""Host-side logic and C-ABI surface, no GPU needed (no compute call is made)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import NetFixture
+from oracle import refshim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from snn_modulation_classification_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "dcll_b200.h")).read()
+    declared = set(re.findall(r"\b(dcll_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.EXPORTS)
+    so = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(so, name), name
+    assert _lib.lib.dcll_abi_version() == _lib.ABI_VERSION
+    assert _lib.lib.dcll_sizeof_conv_layer() == ctypes.sizeof(_lib.ConvLayer)
+    assert _lib.lib.dcll_sizeof_train_args() == ctypes.sizeof(_lib.TrainArgs)
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    from snn_modulation_classification_b200 import _lib
+    with pytest.raises(ValueError, match="null pointer"):
+        _lib.check(_lib.lib.dcll_iq_encode(None, 4, 8, -1.0, 1.0, -1.0, 1.0, 16, 16, 0, 8, 1, None, None))
+    with pytest.raises(ValueError, match="exceeds"):
+        _lib.check(_lib.lib.dcll_iq_encode(1024, 4, 8, -1.0, 1.0, -1.0, 1.0, 16, 16, 4, 8, 1, 2048, None))
+    d = _lib.ConvLayer()
+    d.B, d.Cin, d.H, d.W, d.Cout, d.KH, d.KW, d.padH, d.padW, d.poolH, d.poolW, d.K = 4, 1, 16, 16, 32, 7, 7, 3, 3, 1, 1, 24
+    assert _lib.lib.dcll_conv_workspace_bytes(ctypes.byref(d)) > 0
+    with pytest.raises(ValueError):
+        _lib.check(_lib.lib.dcll_conv_step_fwd(ctypes.byref(d), None, None, None))
+    d.poolH = 3
+    with pytest.raises(NotImplementedError):
+        _lib.check(_lib.lib.dcll_conv_step_fwd(ctypes.byref(d), 1024, None, None))
+
+
+@pytest.fixture
+def cpu_modules(monkeypatch):
+    """Construction-only use of the host mirror on CPU (kernels are never called)."""
+    from snn_modulation_classification_b200 import networks as N
+    from snn_modulation_classification_b200.dcll import pytorch_libdcll as L
+    monkeypatch.setattr(L, "device", "cpu")
+    monkeypatch.setattr(N, "device", "cpu")
+    return L, N
+
+
+def _build(N, spec, im_dims, B, K, arp, seed=1, train=True):
+    from util_build import make_args
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    kw = dict(loss=torch.nn.SmoothL1Loss, opt=torch.optim.Adam, opt_param={"betas": [0.0, 0.95], "weight_decay": 10.0},
+              learning_rates=[1e-6]) if train else dict(loss=None, opt=None, opt_param={}, learning_rates=None)
+    return N.ConvNetwork(make_args(arp), im_dims, B, N.load_network_spec(spec), K, act=torch.nn.Sigmoid(), burnin=50, **kw)
+
+
+@pytest.mark.parametrize("name", ["radio8_train", "radio8_arp_infer", "mnist_train", "radioref_train"])
+def test_state_dict_keys_and_shapes_match_reference_fixture(cpu_modules, name):
+    L, N = cpu_modules
+    fx = NetFixture(name)
+    net = _build(N, fx.spec_name, fx.im_dims, fx.B, fx.K, fx.arp, train=fx.train)
+    sd = net.state_dict()
+    assert set(sd.keys()) == set(fx.state_dict.keys())
+    for k, v in fx.state_dict.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    net.load_state_dict(fx.state_dict, strict=True)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not refshim.reference_available(), reason="reference not present")
+@pytest.mark.parametrize("spec,im_dims,K,arp", [("radio_ml_conv", (1, 16, 16), 24, 0.0), ("radio_ml_conv", (1, 16, 16), 24, 1.0),
+                                                 ("mnist_conv", (1, 28, 28), 10, 0.0)])
+def test_constructors_consume_rng_like_the_reference(cpu_modules, spec, im_dims, K, arp):
+    """Same seeds -> bit-identical initial parameters and time constants (torch + numpy RNG order:
+    reset_parameters -> nn.Linear inits -> reset_lc_parameters -> randomize_tau: tau_m then tau_s)."""
+    L, N = cpu_modules
+    ref = refshim.build_reference_net(spec, im_dims, 4, K, arp=arp, seed=1)
+    net = _build(N, spec, im_dims, 4, K, arp)
+    net.reset(True)
+    a, b = ref.state_dict(), net.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    # the reference's optimizer groups (train.py:224-225 touches them)
+    for s in net.dcll_slices:
+        assert s.optimizer.param_groups[-1]["lr"] == 1e-6 and s.optimizer.param_groups[-1]["weight_decay"] == 10.0
+    assert net.dcll_slices[-1].optimizer2.param_groups[-1]["lr"] == 1e-4
+    assert not hasattr(net.dcll_slices[0], "optimizer2")
+
+
+def test_load_network_spec_schema(tmp_path, cpu_modules):
+    L, N = cpu_modules
+    p = tmp_path / "net.yaml"
+    p.write_text('conv_layers:\n  - out_channels: 8\n    kernel_size: "(1, 3)"\n    padding: "(0, 1)"\n    pooling: 2\n')
+    convs = N.load_network_spec(str(p))
+    assert convs == [dict(out_channels=8, kernel_size=(1, 3), padding=(0, 1), pooling=2)]
+    assert N.load_network_spec("networks/radio_ml_conv_ref.yaml")[0]["kernel_size"] == (1, 3)
+    assert len(N.load_network_spec("networks/mnist_conv.yaml")) == 3
+    with pytest.raises(FileNotFoundError):
+        N.load_network_spec("networks/nope.yaml")
+
+
+def test_layer_constructor_errors(cpu_modules):
+    L, N = cpu_modules
+    with pytest.raises(ValueError):
+        L.ContinuousConv2D(3, 8, 7, groups=2)                       # ref :316-319
+    with pytest.raises(Exception, match="Non-spiking"):
+        L.Conv2dDCLLlayer(1, 8, wrp=1.0, spiking=False)             # ref :556-558
+    lay = L.Conv2dDCLLlayer(1, 16, kernel_size=7, padding=2, pooling=2, im_dims=(28, 28), target_size=10,
+                            output_layer=True)
+    assert lay.get_flat_size() == 16 * 13 * 13 and tuple(lay.output_shape) == (13, 13)
+    assert lay.i2o.weight.shape == (10, 2704) and not lay.i2o.weight.requires_grad
+    assert lay.output_.weight.requires_grad
+    lay.init_hiddens(3)
+    assert lay.i2h.state.eps0.shape == (3, 1, 28, 28) and lay.i2h.alpha.shape == (1,)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        lay.forward(torch.zeros(3, 1, 28, 28))                      # product path fails loudly without CUDA
+
+
+def test_device_clout_counting_rule_is_host_side(cpu_modules):
+    L, N = cpu_modules
+    c = L.DeviceClout()
+    assert len(c) == 0 and np.array(c).shape[0] == 0
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    import importlib
+    from snn_modulation_classification_b200 import _lib
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libdcll_b200.so"))
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        _lib._load()
