@@ -106,6 +106,16 @@ const char *dcll_last_error(void);
 size_t dcll_sizeof_conv_layer(void);
 size_t dcll_sizeof_train_args(void);
 
+/* -- measurement hooks (bench.py) --------------------------------------------------------------- *
+ * dcll_launch_count: kernels launched by this library since load (or since the last reset).
+ * dcll_profile_enable(every_n): bracket the kernels of every n-th layer-step with CUDA events on the
+ * launching stream (0 disables).  dcll_profile_read synchronises those events and returns, per kernel
+ * class c (0 encode, 1 conv_fwd, 2 readout_fwd, 3 readout_bwd, 4 wgrad, 5 adam, 6 misc) and layer l
+ * (< 8), the summed milliseconds ms[c*8+l] and the number of sampled brackets n[c*8+l]; then clears. */
+int64_t dcll_launch_count(int reset);
+int dcll_profile_enable(int every_n);
+int dcll_profile_read(double *ms, int64_t *n);
+
 /* -- encoder: data/utils.py:43-87 (iq2spiketrain) ------------------------------------------ *
  * x: device float32 [B,2,N]; cells: device int32 [T,B,2] = (cell_Q, cell_I) for samples
  * t_start .. t_start+T-1.  Bit-exact with the reference's torch-CPU arithmetic.              */

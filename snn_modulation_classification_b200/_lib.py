@@ -83,13 +83,35 @@ def _load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
+    lib.dcll_launch_count.argtypes = [C.c_int]
+    lib.dcll_launch_count.restype = C.c_int64
+    lib.dcll_profile_enable.argtypes = [C.c_int]
+    lib.dcll_profile_enable.restype = C.c_int
+    lib.dcll_profile_read.argtypes = [P(C.c_double), P(C.c_int64)]
+    lib.dcll_profile_read.restype = C.c_int
     lib.dcll_conv_workspace_bytes.argtypes = [P(ConvLayer)]
     lib.dcll_conv_workspace_bytes.restype = C.c_size_t
     return lib
 
 
 lib = _load()
-EXPORTS = ["dcll_abi_version", "dcll_last_error", "dcll_sizeof_conv_layer", "dcll_sizeof_train_args", "dcll_iq_encode",
+KERNEL_CLASSES = ["encode", "conv_fwd", "readout_fwd", "readout_bwd", "wgrad", "adam", "misc"]
+
+
+def profile_read():
+    """{(kernel_class, layer): (total_ms, samples)} of the brackets sampled since the last read."""
+    ms = (C.c_double * (len(KERNEL_CLASSES) * 8))()
+    n = (C.c_int64 * (len(KERNEL_CLASSES) * 8))()
+    check(lib.dcll_profile_read(ms, n))
+    out = {}
+    for c, name in enumerate(KERNEL_CLASSES):
+        for l in range(8):
+            if n[c * 8 + l]:
+                out[(name, l)] = (ms[c * 8 + l], n[c * 8 + l])
+    return out
+
+
+EXPORTS = ["dcll_launch_count", "dcll_profile_enable", "dcll_profile_read", "dcll_abi_version", "dcll_last_error", "dcll_sizeof_conv_layer", "dcll_sizeof_train_args", "dcll_iq_encode",
            "dcll_cells_to_frames", "dcll_conv_workspace_bytes", "dcll_conv_sync_weights", "dcll_conv_step_fwd",
            "dcll_conv_core_fwd", "dcll_conv_step_bwd_update", "dcll_conv_apply_update", "dcll_net_window", "dcll_vote",
            "dcll_quantize", "dcll_dequantize"]

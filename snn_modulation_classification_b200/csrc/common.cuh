@@ -28,8 +28,20 @@ void set_error(const char *fmt, ...);
         }                                                                                       \
     } while (0)
 
+// Kernel classes for the launch counter and the optional CUDA-event profile (dcll_profile_*).
+enum KClass { KC_ENCODE = 0, KC_CONV_FWD, KC_READOUT_FWD, KC_READOUT_BWD, KC_WGRAD, KC_ADAM, KC_MISC, KC_COUNT };
+void count_launch(const char *name);
+// RAII: brackets the launches of one kernel class with CUDA events when profiling samples this step.
+struct ProfScope {
+    int slot;
+    cudaStream_t st;
+    ProfScope(int kclass, int layer, cudaStream_t st);
+    ~ProfScope();
+};
+
 #define DCLL_LAUNCH_OK(name)                                                                         \
     do {                                                                                             \
+        ::dcll::count_launch(name);                                                                  \
         cudaError_t _e = cudaGetLastError();                                                         \
         if (_e != cudaSuccess) {                                                                     \
             ::dcll::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));              \

@@ -17,6 +17,38 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+// ---- launch counter + sampled CUDA-event profile ------------------------------------------------
+static int64_t g_launches = 0;
+void count_launch(const char *) { ++g_launches; }
+
+static constexpr int PROF_MAX = 4096, PROF_LAYERS = 8;
+static int g_prof_every = 0;
+static int64_t g_prof_tick = 0;      // layer-steps seen
+static bool g_prof_active = false;   // current layer-step is sampled
+static int g_prof_n = 0;
+static cudaEvent_t g_prof_ev[PROF_MAX][2];
+static int g_prof_key[PROF_MAX];
+static bool g_prof_init = false;
+
+void prof_begin_layer_step() {
+    if (!g_prof_every) { g_prof_active = false; return; }
+    g_prof_active = (g_prof_tick++ % g_prof_every) == 0;
+}
+
+ProfScope::ProfScope(int kclass, int layer, cudaStream_t st_) : slot(-1), st(st_) {
+    if (!g_prof_active || g_prof_n >= PROF_MAX) return;
+    if (!g_prof_init) {
+        for (int i = 0; i < PROF_MAX; ++i) cudaEventCreate(&g_prof_ev[i][0]), cudaEventCreate(&g_prof_ev[i][1]);
+        g_prof_init = true;
+    }
+    slot = g_prof_n++;
+    g_prof_key[slot] = kclass * PROF_LAYERS + (layer < PROF_LAYERS ? layer : PROF_LAYERS - 1);
+    cudaEventRecord(g_prof_ev[slot][0], st);
+}
+ProfScope::~ProfScope() {
+    if (slot >= 0) cudaEventRecord(g_prof_ev[slot][1], st);
+}
+
 WsLayout ws_layout(const dcll_conv_layer *L) {
     Geo g = geo_of(L);
     WsLayout w;
@@ -79,18 +111,33 @@ static int check_layer(const dcll_conv_layer *L, const char *who) {
     return DCLL_OK;
 }
 
+static int g_layer = 0;  // layer index of the step being enqueued (profile key only)
+
 static int step_fwd(dcll_conv_layer *L, const void *x, const float *target, int loss_kind, int32_t *clout, float *loss_out,
                     cudaStream_t st) {
-    int rc = launch_conv_fwd(L, x, st);
+    prof_begin_layer_step();
+    int rc;
+    {
+        ProfScope ps(KC_CONV_FWD, g_layer, st);
+        rc = launch_conv_fwd(L, x, st);
+    }
     if (rc != DCLL_OK) return rc;
     L->cur ^= 1;
+    ProfScope ps(KC_READOUT_FWD, g_layer, st);
     return launch_readout_fwd(L, target, loss_kind, clout, loss_out, st);
 }
 
 static int step_bwd(dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st) {
-    int rc = launch_readout_bwd(L, a, st);
+    int rc;
+    {
+        ProfScope ps(KC_READOUT_BWD, g_layer, st);
+        rc = launch_readout_bwd(L, a, st);
+    }
     if (rc != DCLL_OK) return rc;
-    rc = launch_wgrad(L, a, st);
+    {
+        ProfScope ps(KC_WGRAD, g_layer, st);
+        rc = launch_wgrad(L, a, st);
+    }
     if (rc != DCLL_OK) return rc;
     if (a->apply_update) {
         a->adam_i2h.step += 1;
@@ -178,6 +225,34 @@ __global__ void dequantize_kernel(const int8_t *__restrict__ codes, const float 
 using namespace dcll;
 
 extern "C" __attribute__((visibility("default"))) int dcll_abi_version(void) { return DCLL_ABI_VERSION; }
+
+extern "C" __attribute__((visibility("default"))) int64_t dcll_launch_count(int reset) {
+    int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+extern "C" __attribute__((visibility("default"))) int dcll_profile_enable(int every_n) {
+    DCLL_REQUIRE(every_n >= 0, DCLL_EINVAL, "dcll_profile_enable: every_n must be >= 0");
+    g_prof_every = every_n;
+    g_prof_tick = 0;
+    g_prof_active = false;
+    return DCLL_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dcll_profile_read(double *ms, int64_t *n) {
+    DCLL_REQUIRE(ms && n, DCLL_EINVAL, "dcll_profile_read: null output");
+    for (int i = 0; i < KC_COUNT * PROF_LAYERS; ++i) ms[i] = 0.0, n[i] = 0;
+    for (int i = 0; i < g_prof_n; ++i) {
+        DCLL_CUDA_OK(cudaEventSynchronize(g_prof_ev[i][1]));
+        float t = 0.f;
+        DCLL_CUDA_OK(cudaEventElapsedTime(&t, g_prof_ev[i][0], g_prof_ev[i][1]));
+        ms[g_prof_key[i]] += t;
+        n[g_prof_key[i]] += 1;
+    }
+    g_prof_n = 0;
+    return DCLL_OK;
+}
 extern "C" __attribute__((visibility("default"))) const char *dcll_last_error(void) { return g_err; }
 extern "C" __attribute__((visibility("default"))) size_t dcll_sizeof_conv_layer(void) { return sizeof(dcll_conv_layer); }
 extern "C" __attribute__((visibility("default"))) size_t dcll_sizeof_train_args(void) { return sizeof(dcll_train_args); }
@@ -281,6 +356,7 @@ extern "C" __attribute__((visibility("default"))) int dcll_net_window(dcll_conv_
         const float *tgt = target ? target + (size_t)t * target_t_stride : nullptr;
         for (int l = 0; l < n_layers; ++l) {
             dcll_conv_layer *L = &layers[l];
+            g_layer = l;
             const void *x = l == 0 ? (const void *)((const char *)x0 + (size_t)t * x_stride) : (const void *)layers[l - 1].spikes;
             const int it = iter0[l] + t + 1;                       // DCLLBase.forward :656
             const bool do_train = train_mode && it >= burnin;      // train_dcll :692

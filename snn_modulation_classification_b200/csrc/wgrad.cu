@@ -279,6 +279,7 @@ int launch_wgrad(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st) 
     if (rc != DCLL_OK) return rc;
     AdamScalars sc = adam_scalars(a->adam_i2h, a->adam_i2h.step + 1);
     dcll_adam &o = a->adam_i2h;
+    ProfScope ps(KC_ADAM, 0, st);
     reduce_adam_kernel<<<ceil_div(p.n_tot, 256), 256, 0, st>>>(p.partial, p.S, p.n_tot, p.nW, L->Cout, g.CoutPad,
                                                                L->Cin * L->KH * L->KW, L->weight, L->weight_t, L->bias,
                                                                o.m_w, o.v_w, o.m_b, o.v_b, a->grad_w, a->grad_b,

@@ -129,16 +129,20 @@ class DeviceClout:
     def __getitem__(self, i):
         return self.numpy()[i]
 
-    def vote(self, num_classes=None):
-        """Device-side majority vote (dcll_vote); returns a float numpy array like ref:47."""
-        if self._n == 0:
-            return np.empty(0)
+    def vote_device(self, num_classes=None):
+        """Device-side majority vote (dcll_vote): int32 [B] on the device, no host sync."""
         rows = self.device_rows()
         k = int(num_classes) if num_classes else int(rows.max().item()) + 1
         pred = torch.empty(rows.shape[1], dtype=torch.int32, device=rows.device)
         _lib.check(_lib.lib.dcll_vote(_lib.ptr(rows), rows.shape[0], rows.shape[1], rows.shape[1], k,
                                       _lib.ptr(pred), _lib.current_stream()))
-        return pred.cpu().numpy().astype(np.float64)
+        return pred
+
+    def vote(self, num_classes=None):
+        """Majority vote as a float numpy array like ref:47."""
+        if self._n == 0:
+            return np.empty(0)
+        return self.vote_device(num_classes).cpu().numpy().astype(np.float64)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -182,6 +182,81 @@ class ConvNetwork(torch.nn.Module):
                     _store_steps(states[i][1], trains[i].adam_out.step)
         return clout
 
+    def learn_window_dp(self, x, labels, group=None):
+        """Data-parallel ``learn_window``: every rank holds identical weights and its own shard of the batch
+        (samples are independent in the forward pass, the state and the read-outs; the only coupling is the
+        mean over the batch in the local loss).  Each layer's local gradients (gW, gb and, on the output
+        layer, gWout, gbout) live in one flat bucket that is averaged over ranks with a single NCCL
+        all-reduce per layer per timestep; the collective of layer l overlaps the forward/backward of layers
+        l+1.. and is only waited for right before layer l's next forward, where the identical Adam step is
+        applied on every rank.  Equals the single-process run at the global batch up to summation order."""
+        import torch.distributed as dist
+        n = self.num_layers
+        x_t, x_mode = (x.cells, _lib.X_CELLS) if isinstance(x, SpikeCells) else (_as_cuda_f32(x), _lib.X_DENSE)
+        T, batch = int(x_t.shape[0]), int(x_t.shape[1])
+        win = self._window_buffers(batch)
+        Layers, Trains = _lib.ConvLayer * n, _lib.TrainArgs * n
+        layers, trains = Layers(), Trains()
+        olds, states, buckets, pending = [], [], [], [None] * n
+        target = _as_cuda_f32(labels)
+        if target.dim() == 3:
+            target = target[0].contiguous()
+        for i, s in enumerate(self.dcll_slices):
+            lay = s.dclllayer
+            old, _ = lay._fill_desc(layers[i], batch, x_mode if i == 0 else _lib.X_DENSE, win['outs'][i])
+            olds.append(old)
+            trains[i].loss_kind, trains[i].apply_update = _loss_kind(s.crit), 0
+            trains[i].target = _lib.ptr(target)
+            st = [_fill_adam(trains[i].adam_i2h, s.optimizer, lay.i2h.weight, lay.i2h.bias)]
+            sizes = [lay.i2h.weight.numel(), lay.i2h.bias.numel()]
+            if lay.output_layer:
+                st.append(_fill_adam(trains[i].adam_out, s.optimizer2, lay.output_.weight, lay.output_.bias))
+                sizes += [lay.output_.weight.numel(), lay.output_.bias.numel()]
+            states.append(st)
+            flat = torch.zeros(sum(sizes), device=x_t.device)
+            views = list(flat.split(sizes))
+            trains[i].grad_w, trains[i].grad_b = _lib.ptr(views[0]), _lib.ptr(views[1])
+            if lay.output_layer:
+                trains[i].grad_wout, trains[i].grad_bout = _lib.ptr(views[2]), _lib.ptr(views[3])
+            buckets.append(flat)
+        clout = torch.empty((T, n, batch), dtype=torch.int32, device=x_t.device)
+        stream = _lib.current_stream()
+        step_fwd, step_bwd, apply = _lib.lib.dcll_conv_step_fwd, _lib.lib.dcll_conv_step_bwd_update, \
+            _lib.lib.dcll_conv_apply_update
+        x_stride = x_t[0].numel() * x_t.element_size()
+        x_base = x_t.data_ptr()
+        burnin = int(self.dcll_slices[0].burnin)
+        iters = [int(s.iter) for s in self.dcll_slices]
+
+        def finish(i):
+            if pending[i] is not None:
+                pending[i].wait()
+                _lib.check(apply(ctypes.byref(layers[i]), ctypes.byref(trains[i]), stream))
+                pending[i] = None
+
+        for t in range(T):
+            for i in range(n):
+                finish(i)
+                xin = x_base + t * x_stride if i == 0 else layers[i - 1].spikes
+                _lib.check(step_fwd(ctypes.byref(layers[i]), xin, clout[t, i].data_ptr(), stream))
+                iters[i] += 1
+                if iters[i] >= burnin:
+                    _lib.check(step_bwd(ctypes.byref(layers[i]), ctypes.byref(trains[i]), stream))
+                    pending[i] = dist.all_reduce(buckets[i], op=dist.ReduceOp.AVG, group=group, async_op=True)
+        for i in range(n):
+            finish(i)
+        for i, s in enumerate(self.dcll_slices):
+            s.dclllayer.i2h._commit_state(*olds[i], flips=T)
+            s.dclllayer._ctx = None
+            first = max(0, int(s.burnin) - int(s.iter) - 1)
+            if first < T:
+                s.clout.extend(clout[first:, i, :])
+            s.iter += T
+            _store_steps(states[i][0], trains[i].adam_i2h.step)
+            if s.dclllayer.output_layer:
+                _store_steps(states[i][1], trains[i].adam_out.step)
+        return clout
+
     def learn_window(self, x, labels):
         """``for t in range(T): self.learn(x[t], labels[t])`` (train.py:249-251) in one call."""
         return self._run_window(x, labels, True)
