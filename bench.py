@@ -114,7 +114,7 @@ def cpu_port_sample(wl, T, n_fwd=1, n_train=2, reps=1):
     params = O.random_params(specs, seed=1)
     net = O.OracleNet(specs, params, batch, burnin=0 if train else burnin, backend="autograd")
     x, y = synth(batch, 1)
-    t_enc_n = 8
+    t_enc_n = max(8, 4 + n_fwd + n_train)
     t0 = time.perf_counter()
     cells = O.encode_cells(x.numpy(), res, res, t_start=0, max_duration=t_enc_n)
     frames = torch.from_numpy(O.cells_to_frames(cells, res, res))
@@ -331,7 +331,12 @@ def main():
     ap.add_argument("--timesteps", type=int, default=1024)
     ap.add_argument("--profile-every", type=int, default=31, dest="profile_every")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--burnin", type=int, default=None, help="override the workload's burn-in (profiling runs)")
     a = ap.parse_args()
+    if a.burnin is not None:
+        w = list(WORKLOADS[a.workload])
+        w[5] = a.burnin
+        WORKLOADS[a.workload] = tuple(w)
     if a.impl == "reference":
         run_reference(a)
     else:
