@@ -142,6 +142,29 @@ int dcll_conv_step_bwd_update(dcll_conv_layer *L, dcll_train_args *a, void *stre
 /* Adam on gradients already in a->grad_* (data-parallel path, after the allreduce) */
 int dcll_conv_apply_update(dcll_conv_layer *L, dcll_train_args *a, void *stream);
 
+/* -- dense layer: DenseDCLLlayer (dcll/pytorch_libdcll.py:198-266) over CLLDenseModule (:72-148) or
+ *    CLLDenseRRPModule (:151-195).  Not instantiated by any entry point of the reference; FP32 tiled GEMMs. */
+typedef struct dcll_dense_layer {
+    int32_t B, In, Out, K;
+    int32_t coef_mode;               /* DCLL_COEF_SCALAR or DCLL_COEF_CHANNEL ([In] vectors, random_tau)  */
+    float alpharp, wrp;
+    const float *alpha, *alphas, *tau_m, *tau_s;
+    float *weight, *bias;            /* device [Out,In], [Out]                                            */
+    const float *wo, *bo;            /* device [K,Out], [K]  frozen i2o                                   */
+    float *eps0, *eps1;              /* device [B,In], updated in place (element-wise, no halo)           */
+    float *arp;                      /* device [B,Out] or NULL                                            */
+    float *spikes, *pv, *vmem;       /* device [B,Out] outputs                                            */
+    float *pvoutput;                 /* device [B,K]                                                      */
+    float *g_o, *g_u;                /* device scratch [B,K], [B,Out]                                     */
+    float *grad_w, *grad_b;          /* device [Out,In], [Out]                                            */
+} dcll_dense_layer;
+size_t dcll_sizeof_dense_layer(void);
+/* DenseDCLLlayer.forward :250-255 (x: device [B,In]) */
+int dcll_dense_step_fwd(dcll_dense_layer *L, const float *x, int32_t *clout, void *stream);
+/* local gradient (gW = ((g_o Wo) * s(1-s))^T eps1) + Adam on weight/bias when apply_update;
+ * gradients are always left in grad_w / grad_b. */
+int dcll_dense_step_bwd_update(dcll_dense_layer *L, dcll_train_args *a, void *stream);
+
 /* -- whole window: the T-loop of train.py:249-251 / test_radio_ml.py:144-145 ----------------- *
  * Runs `T` timesteps of ConvNetwork.learn (train != 0) or .test over `n_layers` chained
  * layers.  x0: layer-0 input for all timesteps, dense [T,B,Cin,H,W] or cells [T,B,2].

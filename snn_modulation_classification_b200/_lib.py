@@ -45,6 +45,14 @@ class TrainArgs(C.Structure):
                 ("grad_w", _fp), ("grad_b", _fp), ("grad_wout", _fp), ("grad_bout", _fp), ("loss_out", _fp)]
 
 
+class DenseLayer(C.Structure):
+    _fields_ = [("B", C.c_int32), ("In", C.c_int32), ("Out", C.c_int32), ("K", C.c_int32), ("coef_mode", C.c_int32),
+                ("alpharp", C.c_float), ("wrp", C.c_float),
+                ("alpha", _fp), ("alphas", _fp), ("tau_m", _fp), ("tau_s", _fp), ("weight", _fp), ("bias", _fp),
+                ("wo", _fp), ("bo", _fp), ("eps0", _fp), ("eps1", _fp), ("arp", _fp), ("spikes", _fp), ("pv", _fp),
+                ("vmem", _fp), ("pvoutput", _fp), ("g_o", _fp), ("g_u", _fp), ("grad_w", _fp), ("grad_b", _fp)]
+
+
 class DcllError(RuntimeError):
     pass
 
@@ -61,7 +69,9 @@ def _load():
     lib.dcll_sizeof_train_args.restype = C.c_size_t
     if lib.dcll_abi_version() != ABI_VERSION:
         raise ImportError("libdcll_b200.so has ABI %d, binding expects %d: rebuild" % (lib.dcll_abi_version(), ABI_VERSION))
-    if lib.dcll_sizeof_conv_layer() != C.sizeof(ConvLayer) or lib.dcll_sizeof_train_args() != C.sizeof(TrainArgs):
+    lib.dcll_sizeof_dense_layer.restype = C.c_size_t
+    if lib.dcll_sizeof_conv_layer() != C.sizeof(ConvLayer) or lib.dcll_sizeof_train_args() != C.sizeof(TrainArgs) \
+            or lib.dcll_sizeof_dense_layer() != C.sizeof(DenseLayer):
         raise ImportError("struct layout mismatch between include/dcll_b200.h and _lib.py")
     P = C.POINTER
     sig = {
@@ -75,6 +85,8 @@ def _load():
         "dcll_conv_apply_update": [P(ConvLayer), P(TrainArgs), _fp],
         "dcll_net_window": [P(ConvLayer), P(TrainArgs), C.c_int, _fp, _fp, C.c_int64, C.c_int, C.c_int, C.c_int,
                             P(C.c_int32), _fp, _fp],
+        "dcll_dense_step_fwd": [P(DenseLayer), _fp, _fp, _fp],
+        "dcll_dense_step_bwd_update": [P(DenseLayer), P(TrainArgs), _fp],
         "dcll_vote": [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp],
         "dcll_quantize": [_fp, C.c_int, C.c_int, _fp, _fp, _fp],
         "dcll_dequantize": [_fp, _fp, C.c_int, C.c_int, _fp, _fp],
@@ -114,7 +126,8 @@ def profile_read():
 EXPORTS = ["dcll_launch_count", "dcll_profile_enable", "dcll_profile_read", "dcll_abi_version", "dcll_last_error", "dcll_sizeof_conv_layer", "dcll_sizeof_train_args", "dcll_iq_encode",
            "dcll_cells_to_frames", "dcll_conv_workspace_bytes", "dcll_conv_sync_weights", "dcll_conv_step_fwd",
            "dcll_conv_core_fwd", "dcll_conv_step_bwd_update", "dcll_conv_apply_update", "dcll_net_window", "dcll_vote",
-           "dcll_quantize", "dcll_dequantize"]
+           "dcll_quantize", "dcll_dequantize", "dcll_sizeof_dense_layer", "dcll_dense_step_fwd",
+           "dcll_dense_step_bwd_update"]
 
 
 def check(rc):

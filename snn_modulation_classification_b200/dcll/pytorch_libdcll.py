@@ -580,6 +580,182 @@ class Conv2dDCLLlayer(nn.Module):
         return output, outs['pvoutput'], outs['pv'], outs['pvmem']
 
 
+
+# ------------------------------------------------------------------------------------------------
+# Dense layers  (ref:72-274)
+# ------------------------------------------------------------------------------------------------
+class CLLDenseModule(nn.Module):
+    NeuronState = namedtuple('NeuronState', ['eps0', 'eps1'])
+
+    def __init__(self, in_channels, out_channels, bias=True, alpha=.9, alphas=.85, act=nn.Sigmoid(), spiking=True,
+                 random_tau=False):
+        super(CLLDenseModule, self).__init__()
+        if not bias:
+            raise NotImplementedError('bias=False is not implemented')
+        if not isinstance(act, nn.Sigmoid) or not spiking:
+            raise NotImplementedError('only spiking layers with nn.Sigmoid() are implemented')
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
+        self.bias = nn.Parameter(torch.empty(out_channels))
+        self.reset_parameters()
+        self.act, self.random_tau, self.spiking = act, random_tau, spiking
+        self.alpha = nn.Parameter(torch.Tensor([alpha]), requires_grad=False)          # ref:87-94
+        self.tau_m__dt = nn.Parameter(torch.Tensor([1. / (1 - self.alpha)]), requires_grad=False)
+        self.alphas = nn.Parameter(torch.Tensor([alphas]), requires_grad=False)
+        self.tau_s__dt = nn.Parameter(torch.Tensor([1. / (1 - self.alphas)]), requires_grad=False)
+
+    wrp = 0.0
+    alpharp = 0.65
+
+    def reset_parameters(self):                                         # ref:102-106
+        stdv = 1. / math.sqrt(self.weight.size(1))
+        self.weight.data.uniform_(-stdv * 1e-2, stdv * 1e-2)
+        self.bias.data.uniform_(-stdv, stdv)
+
+    def _zeros(self, batch_size, n, init_value):
+        return torch.zeros(batch_size, n, device=_dev()) + init_value
+
+    def init_state(self, batch_size, init_value=0):                     # ref:108-117 (re-randomises tau every time)
+        self.state = self.NeuronState(eps0=self._zeros(batch_size, self.in_channels, init_value),
+                                      eps1=self._zeros(batch_size, self.in_channels, init_value))
+        if self.random_tau:
+            self.randomize_tau()
+        return self.state
+
+    def randomize_tau(self, low=[5, 5], high=[10, 35]):                 # ref:119-129
+        taum = np.random.uniform(low[1], high[1], size=[self.in_channels]) * 1e-3
+        taus = np.random.uniform(low[0], high[0], size=[self.in_channels]) * 1e-3
+        self.alpha = nn.Parameter(torch.Tensor(1 - 1e-3 / taum).to(_dev()), requires_grad=False)
+        self.tau_m__dt = nn.Parameter(1. / (1 - self.alpha), requires_grad=False)
+        self.alphas = nn.Parameter(torch.Tensor(1 - 1e-3 / taus).to(_dev()), requires_grad=False)
+        self.tau_s__dt = nn.Parameter(1. / (1 - self.alphas), requires_grad=False)
+
+    def _arp(self):
+        return None
+
+    def _step(self, input, wo, bo, clout_row=None):
+        """Trace update + synapse + neuron (+ read-out when wo is given); returns the tensors and the descriptor."""
+        if self.weight.device.type != 'cuda':
+            raise RuntimeError("libdcll_b200 has no CPU path: move the module to a CUDA device (.to('cuda'))")
+        x = _as_cuda_f32(input)
+        if not (x.shape[0] == self.state.eps0.shape[0] == self.state.eps1.shape[0]):     # ref:134-137
+            logger.warning("Batch size changed from {} to {} since last iteration. Reallocating states."
+                           .format(self.state.eps0.shape[0], x.shape[0]))
+            self.init_state(x.shape[0])
+        batch, dev = int(x.shape[0]), x.device
+        d = _lib.DenseLayer()
+        d.B, d.In, d.Out = batch, self.in_channels, self.out_channels
+        d.alpharp, d.wrp = float(self.alpharp), float(self.wrp)
+        ts = [_as_cuda_f32(p.detach()) for p in (self.alpha, self.alphas, self.tau_m__dt, self.tau_s__dt)]
+        if all(t.numel() == 1 for t in ts):
+            d.coef_mode = _lib.COEF_SCALAR
+        else:
+            ts = [t.expand(self.in_channels).contiguous() if t.numel() == 1 else t.reshape(-1) for t in ts]
+            d.coef_mode = _lib.COEF_CHANNEL
+        d.alpha, d.alphas, d.tau_m, d.tau_s = (_lib.ptr(t) for t in ts)
+        d.weight, d.bias = _lib.ptr(self.weight.data), _lib.ptr(self.bias.data)
+        e0, e1 = _as_cuda_f32(self.state.eps0), _as_cuda_f32(self.state.eps1)
+        d.eps0, d.eps1 = _lib.ptr(e0), _lib.ptr(e1)
+        arp = self._arp()
+        if arp is not None:
+            arp = _as_cuda_f32(arp)
+            d.arp = _lib.ptr(arp)
+        k = int(wo.shape[0]) if wo is not None else 1
+        d.K = k
+        outs = dict(spikes=torch.empty((batch, self.out_channels), device=dev),
+                    pv=torch.empty((batch, self.out_channels), device=dev),
+                    vmem=torch.empty((batch, self.out_channels), device=dev),
+                    pvoutput=torch.empty((batch, k), device=dev))
+        if wo is None:      # stand-alone i2h call: a 1-row dummy read-out keeps the entry point uniform
+            wo, bo = torch.zeros((1, self.out_channels), device=dev), torch.zeros(1, device=dev)
+        d.wo, d.bo = _lib.ptr(wo), _lib.ptr(bo)
+        d.spikes, d.pv, d.vmem, d.pvoutput = (_lib.ptr(outs[n]) for n in ('spikes', 'pv', 'vmem', 'pvoutput'))
+        _lib.check(_lib.lib.dcll_dense_step_fwd(ctypes.byref(d), _lib.ptr(x), _lib.ptr(clout_row), _lib.current_stream()))
+        self.state = self.NeuronState(e0, e1) if arp is None else self.NeuronState(e0, e1, arp)
+        return outs, (d, ts, wo, bo, x)
+
+    def forward(self, input):                                           # ref:131-148
+        outs, _ = self._step(input, None, None)
+        return outs['spikes'], outs['pv'], outs['vmem']
+
+
+class CLLDenseRRPModule(CLLDenseModule):
+    NeuronState = namedtuple('NeuronState', ('eps0', 'eps1', 'arp'))
+
+    def __init__(self, in_channels, out_channels, bias=True, alpha=.95, alphas=.9, alpharp=.65, wrp=100,
+                 act=nn.Sigmoid(), spiking=True, random_tau=False):
+        super(CLLDenseRRPModule, self).__init__(in_channels, out_channels, bias, alpha, alphas, act, spiking=spiking,
+                                                random_tau=random_tau)
+        self.wrp = wrp
+        self.alpharp = alpharp
+
+    def init_state(self, batch_size, init_value=0):                     # ref:160-169 (no tau randomisation here)
+        self.state = self.NeuronState(eps0=self._zeros(batch_size, self.in_channels, init_value),
+                                      eps1=self._zeros(batch_size, self.in_channels, init_value),
+                                      arp=self._zeros(batch_size, self.out_channels, init_value))
+        return self.state
+
+    def _arp(self):
+        return self.state.arp
+
+    def forward(self, input):                                           # ref:171-195
+        if not self.spiking:
+            raise Exception('Refractory not allowed in non-spiking mode')
+        return super(CLLDenseRRPModule, self).forward(input)
+
+
+class DenseDCLLlayer(nn.Module):
+    def __init__(self, in_channels, out_channels, target_size=None, bias=True, alpha=.9, alphas=.85, alpharp=.65,
+                 wrp=0., act=nn.Sigmoid(), lc_dropout=False, lc_ampl=.5, spiking=True, random_tau=False,
+                 output_layer=False):
+        if target_size is None:
+            target_size = out_channels
+        super(DenseDCLLlayer, self).__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lc_ampl = lc_ampl
+        self.target_size = target_size
+        self.output_layer = False                                       # ref:222 (hard-coded in the reference)
+        if wrp > 0:
+            self.i2h = CLLDenseRRPModule(in_channels, out_channels, alpha=alpha, alphas=alphas, alpharp=alpharp,
+                                         wrp=wrp, bias=bias, act=act, spiking=spiking, random_tau=random_tau)
+        else:
+            self.i2h = CLLDenseModule(in_channels, out_channels, alpha=alpha, alphas=alphas, bias=bias, act=act,
+                                      spiking=spiking, random_tau=random_tau)
+        self.i2o = nn.Linear(out_channels, target_size, bias=bias)      # ref:229-232, frozen
+        self.i2o.weight.requires_grad = False
+        if bias:
+            self.i2o.bias.requires_grad = False
+        self.input_size = self.out_channels
+        self.reset_lc_parameters()
+        self.lc_dropout = lc_dropout
+        if lc_dropout is not False:
+            raise NotImplementedError('lc_dropout is not implemented')
+        self.dropout = lambda x: x
+        self._ctx = None
+
+    def reset_lc_parameters(self):                                      # ref:244-248
+        stdv = self.lc_ampl / math.sqrt(self.i2o.weight.size(1))
+        self.i2o.weight.data.uniform_(-stdv, stdv)
+        if self.i2o.bias is not None:
+            self.i2o.bias.data.uniform_(-stdv, stdv)
+
+    def forward(self, input, clout_row=None):                           # ref:250-255
+        x = _as_cuda_f32(input).reshape(-1, self.in_channels)
+        outs, ctx = self.i2h._step(x, self.i2o.weight.data, self.i2o.bias.data, clout_row)
+        self._ctx = (ctx, outs)
+        return outs['spikes'], outs['pvoutput'], outs['pv'], outs['vmem']
+
+    def init_hiddens(self, batch_size, init_value=0):                   # ref:257-259
+        self.i2h.init_state(batch_size, init_value=init_value)
+        return self
+
+    def reset_tracks(self, mask=None):                                  # ref:261-266 (the mask=None branch reads a
+        if mask is None:                                                #  non-existent field in the reference; fixed)
+            self.init_hiddens(self.i2h.state.eps0.shape[0])
+            return
+        for field in self.i2h.state:
+            field[mask] = 0.
+
 # ------------------------------------------------------------------------------------------------
 # optimiser / loss adapters
 # ------------------------------------------------------------------------------------------------
@@ -692,6 +868,8 @@ class DCLLBase(nn.Module):
     def _bwd_update(self, target, do_train):
         """Local gradient + optimiser step(s) for the forward pass that just ran (ref:693-714)."""
         lay = self.dclllayer
+        if isinstance(lay, DenseDCLLlayer):
+            return self._bwd_update_dense(target, do_train)
         desc, outs, _x = lay._ctx
         targ = _as_cuda_f32(target)
         args = _lib.TrainArgs()
@@ -742,6 +920,47 @@ class DCLLBase(nn.Module):
             self.optimizer.step()                                       # ref:712
             if lay.output_layer:
                 self.optimizer2.step()                                  # ref:714
+        del keep
+        return loss_t
+
+    def _bwd_update_dense(self, target, do_train):
+        lay = self.dclllayer
+        (d, _ts, _wo, _bo, _x), outs = lay._ctx
+        i2h = lay.i2h
+        targ = _as_cuda_f32(target)
+        dev = targ.device
+        args = _lib.TrainArgs()
+        kind = _loss_kind(self.crit)
+        args.loss_kind = kind
+        keep = [targ]
+        if kind == _lib.LOSS_EXTERNAL:
+            pvo = outs['pvoutput'].detach().clone().requires_grad_(True)
+            loss = self.crit(pvo, targ)
+            loss.backward()
+            keep.append(pvo.grad)
+            args.g_o_ext = _lib.ptr(pvo.grad.contiguous())
+            loss_t = loss.detach().reshape(1)
+        else:
+            args.target = _lib.ptr(targ)
+            loss_t = self.crit(outs['pvoutput'], targ).detach().reshape(1)
+        for p in (i2h.weight, i2h.bias):
+            if p.grad is None or p.grad.shape != p.shape or not p.grad.is_contiguous():
+                p.grad = torch.zeros_like(p)
+        g_o = torch.empty((d.B, d.K), device=dev)
+        g_u = torch.empty((d.B, d.Out), device=dev)
+        d.g_o, d.g_u = _lib.ptr(g_o), _lib.ptr(g_u)
+        d.grad_w, d.grad_b = _lib.ptr(i2h.weight.grad), _lib.ptr(i2h.bias.grad)
+        fused = do_train and _is_plain_adam(self.optimizer)
+        states = None
+        if fused:
+            args.apply_update = 1
+            states = _fill_adam(args.adam_i2h, self.optimizer, i2h.weight, i2h.bias)
+        _lib.check(_lib.lib.dcll_dense_step_bwd_update(ctypes.byref(d), ctypes.byref(args), _lib.current_stream()))
+        if fused:
+            _store_steps(states, args.adam_i2h.step)
+        elif do_train:
+            self.optimizer.step()
+        lay._g_u = g_u
         del keep
         return loss_t
 

@@ -52,6 +52,29 @@ def load_network_spec(yaml_path):
     return convs
 
 
+def grad_bucket(lay, dev):
+    """One flat float32 bucket per layer holding (gW, gb[, gWout, gbout]) back to back: the unit of the
+    data-parallel all-reduce (6.4 KB for conv0, 201 KB for conv1/2, + 24*F+24 floats for
+    output_).  Returns (flat, views)."""
+    sizes = [lay.i2h.weight.numel(), lay.i2h.bias.numel()]
+    if lay.output_layer:
+        sizes += [lay.output_.weight.numel(), lay.output_.bias.numel()]
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+    return flat, list(flat.split(sizes))
+
+
+def allreduce_mean(flat, group=None, async_op=False):
+    """Average a gradient bucket over the ranks.  Every rank normalises its local loss by its own B_local*K
+    (mean reduction), shards are equal, so the mean of the per-rank gradients is the global-batch gradient.
+    NCCL averages in the collective; other backends (gloo in the CPU tests) sum and divide."""
+    import torch.distributed as dist
+    if dist.get_backend(group) == 'nccl':
+        return dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+    work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=False)
+    flat.div_(dist.get_world_size(group))
+    return work
+
+
 class ConvNetwork(torch.nn.Module):
     def __init__(self, args, im_dims, batch_size, convs, target_size, act, loss, opt, opt_param, learning_rates,
                  DCLLSlice=DCLLClassification, burnin=50):
@@ -208,13 +231,10 @@ class ConvNetwork(torch.nn.Module):
             trains[i].loss_kind, trains[i].apply_update = _loss_kind(s.crit), 0
             trains[i].target = _lib.ptr(target)
             st = [_fill_adam(trains[i].adam_i2h, s.optimizer, lay.i2h.weight, lay.i2h.bias)]
-            sizes = [lay.i2h.weight.numel(), lay.i2h.bias.numel()]
             if lay.output_layer:
                 st.append(_fill_adam(trains[i].adam_out, s.optimizer2, lay.output_.weight, lay.output_.bias))
-                sizes += [lay.output_.weight.numel(), lay.output_.bias.numel()]
             states.append(st)
-            flat = torch.zeros(sum(sizes), device=x_t.device)
-            views = list(flat.split(sizes))
+            flat, views = grad_bucket(lay, x_t.device)
             trains[i].grad_w, trains[i].grad_b = _lib.ptr(views[0]), _lib.ptr(views[1])
             if lay.output_layer:
                 trains[i].grad_wout, trains[i].grad_bout = _lib.ptr(views[2]), _lib.ptr(views[3])
@@ -242,7 +262,7 @@ class ConvNetwork(torch.nn.Module):
                 iters[i] += 1
                 if iters[i] >= burnin:
                     _lib.check(step_bwd(ctypes.byref(layers[i]), ctypes.byref(trains[i]), stream))
-                    pending[i] = dist.all_reduce(buckets[i], op=dist.ReduceOp.AVG, group=group, async_op=True)
+                    pending[i] = allreduce_mean(buckets[i], group=group, async_op=True)
         for i in range(n):
             finish(i)
         for i, s in enumerate(self.dcll_slices):

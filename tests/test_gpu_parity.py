@@ -356,3 +356,55 @@ def test_unsupported_shapes_fail_loudly():
         lay.forward(torch.zeros(2, 1, 16, 16, device="cuda"))
     with pytest.raises(ValueError):
         Conv2dDCLLlayer(3, 8, kernel_size=7, im_dims=(16, 16)).i2h.__class__(3, 8, 7, groups=2)
+
+
+# ------------------------------------------------------------------------------------------------
+# dense layers
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("wrp,random_tau", [(0.0, False), (0.0, True), (2.0, True)])
+def test_dense_layer_vs_oracle(wrp, random_tau):
+    from snn_modulation_classification_b200.dcll import pytorch_libdcll as L
+    torch.manual_seed(0)
+    np.random.seed(0)
+    B, In, Out, K, lr = 9, 70, 45, 10, 1e-3
+    lay = L.DenseDCLLlayer(In, Out, target_size=K, wrp=wrp, random_tau=random_tau).to("cuda").init_hiddens(B)
+    sl = L.DCLLClassification(dclllayer=lay, batch_size=B, loss=torch.nn.SmoothL1Loss, optimizer=torch.optim.Adam,
+                              kwargs_optimizer={"lr": lr, "betas": [0.0, 0.95], "weight_decay": 10.0}, burnin=2)
+    m = lay.i2h
+    c = lambda t: t.detach().cpu().clone()
+    p = O.ConvParams(c(m.weight), c(m.bias), c(m.alpha), c(m.alphas), c(m.tau_m__dt), c(m.tau_s__dt), c(lay.i2o.weight),
+                     c(lay.i2o.bias))
+    st = O.ConvState(torch.zeros(B, In), torch.zeros(B, In), torch.zeros(B, Out) if wrp > 0 else None)
+    slots = dict(w=O.AdamSlot(), b=O.AdamSlot())
+    g = torch.Generator().manual_seed(1)
+    y = O.to_one_hot(torch.randint(0, K, (B,), generator=g), K)
+    for t in range(6):
+        x = (torch.rand(B, In, generator=g) < 0.3).float()
+        # teacher forcing of the weights (training is chaotic)
+        with torch.no_grad():
+            m.weight.copy_(p.weight)
+            m.bias.copy_(p.bias)
+        out, pvo, pv, vmem, _ = sl.train_dcll(x.cuda(), y.cuda(), regularize=False)
+        fo = O.dense_step_fwd(p, st, x, wrp=wrp)
+        st = fo.state
+        assert torch.equal(m.state.eps0.cpu(), st.eps0) and torch.equal(m.state.eps1.cpu(), st.eps1)
+        assert rel_err(vmem, fo.vmem) <= MEM_TOL and rel_err(pvo, fo.pvoutput) <= MEM_TOL
+        assert float((out.cpu() != fo.spikes).float().mean()) <= 1e-3
+        if wrp > 0:
+            assert float((m.state.arp.cpu() - st.arp).abs().gt(1e-5).float().mean()) <= 1e-3
+        if t + 1 >= 2:
+            g_o, g_u, gW, gb = O.dense_local_grads(p, fo, y)
+            assert rel_err(m.weight.grad, gW) <= 2e-5 and rel_err(m.bias.grad, gb) <= 2e-5
+            kw = dict(lr=lr, beta1=0.0, beta2=0.95, weight_decay=10.0)
+            O.adam_update(p.weight, gW, slots["w"], **kw)
+            O.adam_update(p.bias, gb, slots["b"], **kw)
+            # moments follow the oracle's (same gradients up to rounding)
+            stt = sl.optimizer.state[m.weight]
+            assert float(stt["step"]) == slots["w"].step
+            assert float((m.weight.detach().cpu() - p.weight).abs().max()) <= 5e-2 * lr
+            stt["exp_avg_sq"].copy_(slots["w"].exp_avg_sq)
+            sl.optimizer.state[m.bias]["exp_avg_sq"].copy_(slots["b"].exp_avg_sq)
+    assert len(sl.clout) == 5
+    # stand-alone i2h call (ref :131-148)
+    o2, pv2, vm2 = m.forward(torch.zeros(B, In, device="cuda"))
+    assert o2.shape == (B, Out) and vm2.shape == (B, Out)

@@ -26,7 +26,8 @@ def test_cuda_codes_bit_exact(shape):
     g = torch.Generator().manual_seed(3)
     w = (torch.rand(shape, generator=g) * 2 - 1) * 2e-6
     w[1] = 0
-    w.view(shape[0], -1)[2, :4] = torch.tensor([0.5, 1.5, 2.5, -0.5]) * (w[2].abs().max() / 127)   # ties -> even
+    if w[0].numel() >= 8:
+        w.view(shape[0], -1)[2, :4] = torch.tensor([0.5, 1.5, 2.5, -0.5]) * (w[2].abs().max() / 127)   # ties -> even
     codes, scales = quant.quantize(w.cuda())
     q, s = Q.quantize(w.numpy())
     assert np.array_equal(codes.cpu().numpy(), q)
