@@ -207,6 +207,8 @@ def run_b200(a):
     spec, res, batch, train, arp, burnin = WORKLOADS[a.workload]
     T = a.timesteps
     net = build_net(a.workload)
+    net.set_precision(a.precision)
+    tc = any(sl.dclllayer.i2h.tensor_core_ok() for sl in net.dcll_slices)
     if world > 1:                                   # identical replicas: broadcast rank 0's parameters
         for p in net.state_dict().values():
             dist.broadcast(p, 0)
@@ -285,21 +287,28 @@ def run_b200(a):
     achieved = conv_flops / (avg_ms * 1e-3) / 1e12 if avg_ms else None
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    roofline = {"kernel": "conv_fwd_kernel<7,7,...> (layer 1: 32->32 ch, FP32 FMA path)", "bound": "tensor",
+    roofline = {"kernel": ("conv_fwd_tc_kernel<7,7,32,32> (layer 1: 32->32 ch, tcgen05 split-bf16 x3, TMEM accumulators)" if tc
+                           else "conv_fwd_kernel<7,7,...> (layer 1: 32->32 ch, FP32 FMA path)"), "bound": "tensor",
                 "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tensor"] if achieved else None, "traffic": None,
                 "peak_source": "%s bf16 dense sustained (MEASURED_PEAKS.json)" % pk["src"],
                 "avg_launch_ms": avg_ms, "launches_sampled": c_n, "algorithmic_flops_per_launch": conv_flops,
                 "fp32_fma_peak_tflops_at_clock": fp32_peak, "frac_of_fp32_fma_peak": achieved / fp32_peak if achieved else None,
-                "note": "FP32-exact parity mode runs on the CUDA-core FMA pipe; the tcgen05 split-bf16 mode is the next round's work"}
+                "executed_tensor_flops_per_launch": conv_flops * (3 if tc else 0),
+                "frac_executed": (3 * achieved / pk["tensor"]) if (achieved and tc) else None,
+                "note": ("achieved counts ALGORITHMIC conv FLOPs; the split-bf16 mode executes 3 bf16 MMAs per product "
+                         "(frac_executed = tensor-pipe share actually used). wgrad still runs on the FP32 FMA pipe." if tc else
+                         "FP32-exact parity mode runs on the CUDA-core FMA pipe")}
     per_class = {}
     for (name, layer), (tms, n) in sorted(prof.items()):
         per_class["%s[l%d]" % (name, layer)] = {"avg_ms": tms / n, "samples": n}
 
     out = {"metric": "RadioML IQ windows/sec (DCLL %s)" % ("train" if train else "infer"), "value": value,
            "unit": "windows/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": a.workload, "network": spec + ".yaml", "timesteps": T, "batch_per_gpu": batch,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "bf16x3 (split-bf16 operands on tcgen05, fp32 accumulate; traces/neuron/update fp32)" if tc else "f32",
+           "data": "synthetic",
+           "config": {"workload": a.workload, "precision": a.precision, "network": spec + ".yaml", "timesteps": T, "batch_per_gpu": batch,
                       "global_batch": batch * world, "resolution": "%dx%d" % (res, res), "arp": arp, "burnin": burnin,
                       "parallelism": "dp%d (batch-sharded, NCCL allreduce of local-layer grads per timestep)" % world
                       if world > 1 else "single GPU",
@@ -331,6 +340,8 @@ def main():
     ap.add_argument("--timesteps", type=int, default=1024)
     ap.add_argument("--profile-every", type=int, default=31, dest="profile_every")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3"],
+                    help="fp32: FP32-exact parity mode on the FMA pipe; bf16x3: tcgen05 split-bf16 (headline mode)")
     ap.add_argument("--burnin", type=int, default=None, help="override the workload's burn-in (profiling runs)")
     a = ap.parse_args()
     if a.burnin is not None:

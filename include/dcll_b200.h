@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DCLL_ABI_VERSION 3
+#define DCLL_ABI_VERSION 4
 
 enum { DCLL_OK = 0, DCLL_EINVAL = -1, DCLL_ECUDA = -2, DCLL_EUNSUPPORTED = -3 };
 
@@ -68,6 +68,9 @@ typedef struct dcll_conv_layer {
     float *weight;                   /* device [Cout,Cin,KH,KW]  (the nn.Parameter)          */
     float *weight_t;                 /* device [Cin,KH*KW,CoutPad] kernel-side copy,
                                         CoutPad = 32*ceil(Cout/32); dcll_conv_sync_weights   */
+    void *weight_mma;                /* device bf16 [KH*KW][2][Cin/8][Cout][8]: {hi,lo} split weights in the
+                                        tcgen05 B-operand layout; required when precision is
+                                        DCLL_PREC_BF16X3, refreshed together with weight_t       */
     float *bias;                     /* device [Cout]                                        */
     const float *wo, *bo;            /* device [K,F], [K]   frozen local read-out i2o        */
     float *wout, *bout;              /* device [K,F], [K]   output_ or NULL                  */

@@ -83,6 +83,9 @@ WsLayout ws_layout(const dcll_conv_layer *L);
 
 // Launchers implemented in the individual .cu files (all asynchronous on `st`).
 int launch_conv_fwd(const dcll_conv_layer *L, const void *x, cudaStream_t st);
+int launch_conv_fwd_tc(const dcll_conv_layer *L, const void *x, cudaStream_t st);   // tcgen05, split-bf16 x3
+int launch_weight_mma(const dcll_conv_layer *L, const float *w, cudaStream_t st);
+bool tc_supported(const dcll_conv_layer *L);
 int launch_readout_fwd(const dcll_conv_layer *L, const float *target, int loss_kind, int32_t *clout,
                        float *loss_out, cudaStream_t st);
 int launch_loss_grad(const dcll_conv_layer *L, const float *target, int loss_kind, float *loss_out, cudaStream_t st);

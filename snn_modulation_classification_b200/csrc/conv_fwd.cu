@@ -109,31 +109,60 @@ __global__ void __launch_bounds__(TH *SEGS * 4, 512 / (TH * SEGS * 4)) conv_fwd_
             }
         }
         // ---- trace recurrences on the tile + halo (dcll/pytorch_libdcll.py:415-416), one rounding per
-        //      reference operation so that the traces are bit-identical to the reference's
+        //      reference operation so that the traces are bit-identical to the reference's.  Elements are
+        //      processed in batches of U with all loads issued before the first store: a store to the
+        //      ping-pong half would otherwise fence the next element's loads (one exposed latency each).
         {
+            constexpr int U = 4;
+            const float *__restrict__ ge0 = p.e0_old;
+            const float *__restrict__ ge1 = p.e1_old;
+            const float *__restrict__ gx = p.x;
+            float *__restrict__ ne0 = p.e0_new;
+            float *__restrict__ ne1 = p.e1_new;
             const int n_el = cin_here * HALO_H * HALO_W;
-            for (int idx = tid; idx < n_el; idx += NT) {
-                int ci_l = idx / (HALO_H * HALO_W);
-                int rem = idx - ci_l * (HALO_H * HALO_W);
-                int r = rem / HALO_W;
-                int c = rem - r * HALO_W;
-                int gh = h0 - p.padH + r, gw = w0 - p.padW + c;
-                int ci = ci0 + ci_l;
-                float n1 = 0.f;
-                if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {
-                    size_t off = ((size_t)(b * p.Cin + ci) * p.H + gh) * p.W + gw;
-                    float e0 = __ldg(p.e0_old + off), e1 = __ldg(p.e1_old + off);
-                    float xin = p.cells ? ((gh == cq && gw == cI) ? 1.f : 0.f) : __ldg(p.x + off);
-                    int k = p.coef_mode == DCLL_COEF_SCALAR ? 0
-                                                            : (p.coef_mode == DCLL_COEF_CHANNEL ? ci : (ci * p.H + gh) * p.W + gw);
-                    float n0 = __fadd_rn(__fmul_rn(xin, __ldg(p.tau_s + k)), __fmul_rn(__ldg(p.alphas + k), e0));
-                    n1 = __fadd_rn(__fmul_rn(__ldg(p.alpha + k), e1), __fmul_rn(n0, __ldg(p.tau_m + k)));
-                    if (writer && gh >= h0 && gh < own_h_end && gw >= w0 && gw < own_w_end) {
-                        p.e0_new[off] = n0;
-                        p.e1_new[off] = n1;
+            for (int idx0 = tid; idx0 < n_el; idx0 += U * NT) {
+                float e0[U], e1[U], xin[U], cts[U], cas[U], cal[U], ctm[U];
+                size_t off[U];
+                int sidx[U];
+                bool inimg[U], own[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int idx = idx0 + u * NT;
+                    inimg[u] = false, own[u] = false, sidx[u] = -1, off[u] = 0;
+                    e0[u] = e1[u] = xin[u] = cts[u] = cas[u] = cal[u] = ctm[u] = 0.f;
+                    if (idx < n_el) {
+                        int ci_l = idx / (HALO_H * HALO_W);
+                        int rem = idx - ci_l * (HALO_H * HALO_W);
+                        int r = rem / HALO_W;
+                        int c = rem - r * HALO_W;
+                        int gh = h0 - p.padH + r, gw = w0 - p.padW + c;
+                        int ci = ci0 + ci_l;
+                        sidx[u] = ci_l * XS_PLANE + r * PITCH + c;
+                        if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {
+                            inimg[u] = true;
+                            own[u] = writer && gh >= h0 && gh < own_h_end && gw >= w0 && gw < own_w_end;
+                            off[u] = ((size_t)(b * p.Cin + ci) * p.H + gh) * p.W + gw;
+                            e0[u] = __ldg(ge0 + off[u]);
+                            e1[u] = __ldg(ge1 + off[u]);
+                            xin[u] = p.cells ? ((gh == cq && gw == cI) ? 1.f : 0.f) : __ldg(gx + off[u]);
+                            int k = p.coef_mode == DCLL_COEF_SCALAR ? 0
+                                                                    : (p.coef_mode == DCLL_COEF_CHANNEL ? ci : (ci * p.H + gh) * p.W + gw);
+                            cts[u] = __ldg(p.tau_s + k), cas[u] = __ldg(p.alphas + k);
+                            cal[u] = __ldg(p.alpha + k), ctm[u] = __ldg(p.tau_m + k);
+                        }
                     }
                 }
-                xs[ci_l * XS_PLANE + r * PITCH + c] = n1;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (sidx[u] < 0) continue;
+                    float n1 = 0.f;
+                    if (inimg[u]) {
+                        float n0 = __fadd_rn(__fmul_rn(xin[u], cts[u]), __fmul_rn(cas[u], e0[u]));
+                        n1 = __fadd_rn(__fmul_rn(cal[u], e1[u]), __fmul_rn(n0, ctm[u]));
+                        if (own[u]) ne0[off[u]] = n0, ne1[off[u]] = n1;
+                    }
+                    xs[sidx[u]] = n1;
+                }
             }
         }
         cp_async_wait_all();
@@ -333,6 +362,7 @@ static int launch_pool(FwdP &p, int B, int PH, int PW, cudaStream_t st) {
 }
 
 int launch_conv_fwd(const dcll_conv_layer *L, const void *x, cudaStream_t st) {
+    if (L->precision == DCLL_PREC_BF16X3) return launch_conv_fwd_tc(L, x, st);
     Geo g = geo_of(L);
     FwdP p;
     p.x = L->x_mode == DCLL_X_DENSE ? (const float *)x : nullptr;
@@ -369,5 +399,6 @@ extern "C" __attribute__((visibility("default"))) int dcll_conv_sync_weights(con
     weight_transpose_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(L->weight, L->weight_t, L->Cout,
                                                                                 g.CoutPad, cinkk);
     DCLL_LAUNCH_OK("weight_transpose_kernel");
+    if (L->weight_mma) return launch_weight_mma(L, L->weight, (cudaStream_t)stream);
     return DCLL_OK;
 }

@@ -285,6 +285,7 @@ int launch_wgrad(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st) 
                                                                o.m_w, o.v_w, o.m_b, o.v_b, a->grad_w, a->grad_b,
                                                                a->apply_update, sc);
     DCLL_LAUNCH_OK("reduce_adam_kernel");
+    if (L->weight_mma && a->apply_update) return launch_weight_mma(L, L->weight, st);
     return DCLL_OK;
 }
 

@@ -250,6 +250,8 @@ class ContinuousConv2D(nn.Module):
         self._wt_key = None
         self._spare = None         # the other half of the ping-pong state
         self.quantized = False     # see quant.py
+        self.precision = 'fp32'    # 'fp32' (parity mode) or 'bf16x3' (tcgen05 tensor cores, where instantiated)
+        self._wmma = None          # bf16 {hi,lo} weights in the tcgen05 B-operand layout
 
     # ref:359-366
     def reset_parameters(self):
@@ -324,12 +326,25 @@ class ContinuousConv2D(nn.Module):
             self._wt = torch.empty(n, dtype=torch.float32, device=w.device)
             self._wt_key = None
         desc.weight_t = _lib.ptr(self._wt)
+        if self.tensor_core_ok():
+            n_mma = 2 * self.weight.numel()
+            if self._wmma is None or self._wmma.numel() != n_mma or self._wmma.device != w.device:
+                self._wmma = torch.empty(n_mma, dtype=torch.bfloat16, device=w.device)
+                self._wt_key = None
+            desc.weight_mma = _lib.ptr(self._wmma)
         if self._wt_key != key or self.quantized:
             src = self.effective_weight().contiguous()
             desc.weight = _lib.ptr(src)
             _lib.check(_lib.lib.dcll_conv_sync_weights(ctypes.byref(desc), _lib.current_stream()))
             desc.weight = _lib.ptr(w.data)
             self._wt_key = key
+
+    def tensor_core_ok(self):
+        """True when this core runs on the tcgen05 split-bf16 kernel (precision 'bf16x3' and an instantiated
+        shape: 7x7, 32 -> 32 channels).  Other shapes (e.g. layer 0 with a single input channel, K = 49) stay on
+        the FP32 FMA kernel by design."""
+        return (self.precision == 'bf16x3' and self.kernel_size == (7, 7) and self.in_channels == 32
+                and self.out_channels == 32)
 
     def _fill_core(self, desc, batch, height, width, x_mode):
         """Geometry, parameters and state pointers of the i2h core."""
@@ -342,7 +357,7 @@ class ContinuousConv2D(nn.Module):
         desc.Cout, desc.KH, desc.KW = self.out_channels, self.kernel_size[0], self.kernel_size[1]
         desc.padH, desc.padW = self.padding
         desc.x_mode = x_mode
-        desc.precision = _lib.PREC_FP32
+        desc.precision = _lib.PREC_BF16X3 if self.tensor_core_ok() else _lib.PREC_FP32
         desc.alpharp, desc.wrp = float(self.alpharp), float(self.wrp)
         mode, ts = self._coef.get(self, self.in_channels, height, width)
         desc.coef_mode = mode

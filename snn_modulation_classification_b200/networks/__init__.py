@@ -101,6 +101,18 @@ class ConvNetwork(torch.nn.Module):
                                               burnin=burnin))
         self._win = None
 
+    def set_precision(self, mode):
+        """'fp32': FP32-exact parity mode (CUDA-core FMA).  'bf16x3': convolutions of the layers with an
+        instantiated tensor-core shape run on tcgen05 with split-bf16 operands (3 MMAs, FP32 accumulation in TMEM);
+        pooled layers fall back to FP32 per layer."""
+        if mode not in ('fp32', 'bf16x3'):
+            raise ValueError("precision must be 'fp32' or 'bf16x3'")
+        for s in self.dcll_slices:
+            lay = s.dclllayer
+            lay.i2h.precision = mode if max(lay.pooling) == 1 else 'fp32'
+            lay.i2h._wt_key = None
+        return self
+
     # -- reference per-timestep API -------------------------------------------------------------
     def learn(self, x, labels):                                         # ref:175-180
         spikes = x

@@ -1,0 +1,33 @@
+"""Debug/parity probe of the bf16x3 tensor-core conv against the oracle (teacher-forced, per layer)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, torch
+from oracle import dcll_oracle as O
+from util_build import build_pair, force_state, rel_err
+
+def run(im, B, arp, steps=4, mode='bf16x3'):
+    K = 24
+    net, onet = build_pair("radio_ml_conv", (1,)+im, B, K, arp=arp, train=False)
+    net.set_precision(mode)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(steps, B, 1, *im, generator=g) < 0.1).float()
+    net.reset(); onet.reset()
+    for t in range(steps):
+        force_state(net, onet)
+        onet.test(x[t])
+        for i, s in enumerate(net.dcll_slices):
+            inp = x[t].cuda() if i == 0 else onet.last[i-1].output.cuda()
+            out, pvo, pv, pvmem = s.forward(inp, ignore_burnin=True)
+            fo = onet.last[i]
+            st = s.dclllayer.i2h.state
+            eq = torch.equal(st.eps1.cpu(), fo.state.eps1) and torch.equal(st.eps0.cpu(), fo.state.eps0)
+            flips = float((s.dclllayer._ctx[1]['spikes'].cpu() != fo.spikes).float().mean())
+            print("im=%s B=%d arp=%g t=%d L%d tc=%s traces_exact=%s pvmem_rel=%.2e flips=%.2e pvo_rel=%.2e" % (
+                im, B, arp, t, i, s.dclllayer.i2h.tensor_core_ok(), eq, rel_err(pvmem, fo.pvmem), flips, rel_err(pvo, fo.pvoutput)))
+    torch.cuda.synchronize()
+
+if __name__ == "__main__":
+    run((16, 16), 4, 0.0)
+    run((40, 24), 3, 1.0)
+    run((128, 128), 2, 0.0, steps=2)
