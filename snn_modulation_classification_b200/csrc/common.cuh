@@ -92,6 +92,9 @@ int launch_loss_grad(const dcll_conv_layer *L, const float *target, int loss_kin
 int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st);
 int launch_wgrad(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st);
 int wgrad_splits(const dcll_conv_layer *L);
+bool wgrad_tc_supported(const dcll_conv_layer *L);
+int wgrad_tc_splits(const dcll_conv_layer *L);
+int launch_wgrad_tc(const dcll_conv_layer *L, float *partial, int S, cudaStream_t st);
 struct AdamScalars;
 int launch_adam_flat(float *w, const float *g, float *m, float *v, size_t n, const AdamScalars &sc, cudaStream_t st);
 

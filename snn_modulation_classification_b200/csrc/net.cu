@@ -53,7 +53,7 @@ WsLayout ws_layout(const dcll_conv_layer *L) {
     Geo g = geo_of(L);
     WsLayout w;
     w.n_ro = max(1, min(ceil_div(g.F, 32), 148));
-    w.n_split = wgrad_splits(L);
+    w.n_split = max(wgrad_splits(L), wgrad_tc_splits(L));   // room for either weight-gradient kernel
     size_t off = 0;
     w.off_ro_part = off;
     off = align_up(off + sizeof(float) * (size_t)w.n_ro * L->B * g.Ktot, 256);

@@ -269,13 +269,19 @@ int launch_wgrad(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st) 
     p.B = L->B, p.Cin = L->Cin, p.H = L->H, p.W = L->W, p.Cout = L->Cout, p.padH = L->padH, p.padW = L->padW;
     p.Hc = g.Hc, p.Wc = g.Wc, p.Hp = g.Hp, p.Wp = g.Wp;
     p.tiles_h = ceil_div(g.Hc, 16), p.tiles_w = ceil_div(g.Wc, 16);
-    p.n_units = wgrad_units(L), p.S = ws.n_split, p.nW = g.nW, p.n_tot = g.nW + L->Cout;
+    p.n_units = wgrad_units(L), p.nW = g.nW, p.n_tot = g.nW + L->Cout;
     int rc;
-    if (L->KH == 7 && L->KW == 7) rc = launch_wg<7, 7>(p, L, st);
-    else if (L->KH == 5 && L->KW == 5) rc = launch_wg<5, 5>(p, L, st);
-    else if (L->KH == 3 && L->KW == 3) rc = launch_wg<3, 3>(p, L, st);
-    else if (L->KH == 1 && L->KW == 3) rc = launch_wg<1, 3>(p, L, st);
-    else { set_error("kernel_size (%d,%d) has no sm_100a instantiation", L->KH, L->KW); return DCLL_EUNSUPPORTED; }
+    if (wgrad_tc_supported(L)) {
+        p.S = wgrad_tc_splits(L);
+        rc = launch_wgrad_tc(L, p.partial, p.S, st);
+    } else {
+        p.S = wgrad_splits(L);
+        if (L->KH == 7 && L->KW == 7) rc = launch_wg<7, 7>(p, L, st);
+        else if (L->KH == 5 && L->KW == 5) rc = launch_wg<5, 5>(p, L, st);
+        else if (L->KH == 3 && L->KW == 3) rc = launch_wg<3, 3>(p, L, st);
+        else if (L->KH == 1 && L->KW == 3) rc = launch_wg<1, 3>(p, L, st);
+        else { set_error("kernel_size (%d,%d) has no sm_100a instantiation", L->KH, L->KW); return DCLL_EUNSUPPORTED; }
+    }
     if (rc != DCLL_OK) return rc;
     AdamScalars sc = adam_scalars(a->adam_i2h, a->adam_i2h.step + 1);
     dcll_adam &o = a->adam_i2h;

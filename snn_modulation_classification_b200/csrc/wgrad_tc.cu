@@ -1,0 +1,305 @@
+// Local weight gradient of a Conv2dDCLLlayer on tcgen05 (split-bf16 x3), 7x7 kernels, 32 -> 32 channels.
+//
+//     gW[co,ci,kh,kw] = sum_{b,h,w} g_u[b,co,h,w] * eps1[b,ci,h+kh-pad,w+kw-pad]           (see wgrad.cu)
+//
+// As a GEMM the reduction (K) runs over positions and the output is tiny, so ALL of gW stays resident in tensor memory
+// while a persistent CTA streams its share of the positions through shared memory:
+//
+//   D_{g,kw}[(dy,ci), co] += sum_{16 columns} X[row+4g+dy][col+kw][ci] * G[row][col][co]       g in {0,1}, dy in 0..3
+//
+// * M = 128 = 4 kernel rows x 32 input channels.  With the eps1 halo tile staged as [halo row][ci/8][halo col][8 ci]
+//   (row pitch = 4 x channel-group pitch) the M index (dy, ci/8) has ONE uniform stride, so a single MN-major
+//   no-swizzle descriptor addresses four kernel rows at once; the kernel column kw is a 16-byte start-address shift.
+// * N = 32 output channels, K = 16 consecutive columns of one output row per MMA; G staged as [co/8][row][col][8 co].
+// * 2 x 7 accumulators of 128 x 32 fp32 = 448 of the 512 TMEM columns (the 8th kernel row of group 1 is padding).
+// * bf16 hi/lo split of both operands, three MMAs per product (hi*hi + lo*hi + hi*lo), FP32 accumulation.
+// Partials (one per CTA) are reduced in fixed order by reduce_adam_kernel, exactly like the FP32 path.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace dcll {
+
+namespace wtc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+}  // namespace wtc
+
+struct WgTcP {
+    const float *g_u;   // [B,32,Hc,Wc]
+    const float *eps1;  // [B,32,H,W] (state after the forward step)
+    float *partial;     // [S][nW + Cout]
+    int B, H, W, padH, padW, Hc, Wc;
+    int tiles_h, tiles_w, n_units, n_tot, nW;
+};
+
+struct WgTcGeo {
+    static constexpr int KH = 7, KW = 7, CIN = 32, COUT = 32;
+    static constexpr int TH = 16, TW = 32;
+    static constexpr int XROWS = TH + 8 - 1;                 // 4 + 4 kernel rows (the 8th is padding)
+    static constexpr int XCOLS = TW + KW - 1;                // 38
+    static constexpr int X_CP = XCOLS * 16;                  // channel-group pitch (bytes)
+    static constexpr int X_RP = 4 * X_CP;                    // halo-row pitch
+    static constexpr int X_PART = XROWS * X_RP;              // one of {hi,lo}
+    static constexpr int G_ROW = TW * 16, G_PLANE = TH * G_ROW, G_PART = 4 * G_PLANE;
+    static constexpr int X_BYTES = 2 * X_PART, G_BYTES = 2 * G_PART;
+    static constexpr int SMEM = X_BYTES + G_BYTES + 128 + 16 * 8 * 4;
+    static constexpr int NT = 512;
+};
+
+__global__ void __launch_bounds__(WgTcGeo::NT, 1) wgrad_tc_kernel(const WgTcP p) {
+    using G = WgTcGeo;
+    using namespace wtc;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *sX = smem;
+    unsigned char *sG = smem + G::X_BYTES;
+    uint64_t *mma_done = reinterpret_cast<uint64_t *>(smem + G::X_BYTES + G::G_BYTES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mma_done + 2);
+    float *bias_red = reinterpret_cast<float *>(smem + G::X_BYTES + G::G_BYTES + 128);   // [16 warps][8]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(mma_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const float *__restrict__ gg = p.g_u;
+    const float *__restrict__ ge = p.eps1;
+    const int cgw = warp & 3;                 // channel group (of eps1 and of g_u) this warp stages
+    const int sub = warp >> 2;                // 4 warps share the positions of a group
+    float gsum[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gsum[k] = 0.f;
+
+    const int tiles = p.tiles_h * p.tiles_w;
+    const size_t xcs = (size_t)p.H * p.W, gcs = (size_t)p.Hc * p.Wc;
+    uint32_t first = 1, phase = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const int b = u / tiles;
+        const int tile = u - b * tiles;
+        const int th_i = tile / p.tiles_w, tw_i = tile - th_i * p.tiles_w;
+        const int h0 = th_i * G::TH, w0 = tw_i * G::TW;
+        const int rows = min(G::TH, p.Hc - h0);                       // output rows of this tile inside the image
+        const int chunks = min(2, (p.Wc - w0 + 15) / 16);             // 16-column K chunks with at least one valid column
+        // the previous unit's MMAs must have finished reading shared memory
+        if (!first) {
+            mbar_wait(mma_done, phase);
+            phase ^= 1;
+            tc_fence_after();
+        }
+        // ---- stage eps1 halo tile: [row][cg][col][8 ci], bf16 hi | lo
+        for (int it = sub * 32 + lane; it < G::XROWS * G::XCOLS; it += 128) {
+            const int r = it / G::XCOLS, c = it - r * G::XCOLS;
+            const int gh = h0 - p.padH + r, gw = w0 - p.padW + c;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = 0.f;
+            if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {
+                const size_t off = ((size_t)(b * G::CIN + cgw * 8) * p.H + gh) * p.W + gw;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = __ldg(ge + off + k * xcs);
+            }
+            __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                hi[k] = __float2bfloat16_rn(v[k]);
+                lo[k] = __float2bfloat16_rn(v[k] - __bfloat162float(hi[k]));
+            }
+            unsigned char *dst = sX + r * G::X_RP + cgw * G::X_CP + c * 16;
+            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
+            *reinterpret_cast<uint4 *>(dst + G::X_PART) = *reinterpret_cast<const uint4 *>(lo);
+        }
+        // ---- stage g_u tile: [cog][row][col][8 co], bf16 hi | lo (zero outside the image)
+        for (int it = sub * 32 + lane; it < G::TH * G::TW; it += 128) {
+            const int r = it / G::TW, c = it - r * G::TW;
+            const int oh = h0 + r, ow = w0 + c;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = 0.f;
+            if (oh < p.Hc && ow < p.Wc) {
+                const size_t off = ((size_t)(b * G::COUT + cgw * 8) * p.Hc + oh) * p.Wc + ow;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = __ldg(gg + off + k * gcs);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) gsum[k] += v[k];
+            }
+            __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                hi[k] = __float2bfloat16_rn(v[k]);
+                lo[k] = __float2bfloat16_rn(v[k] - __bfloat162float(hi[k]));
+            }
+            unsigned char *dst = sG + cgw * G::G_PLANE + r * G::G_ROW + c * 16;
+            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
+            *reinterpret_cast<uint4 *>(dst + G::G_PART) = *reinterpret_cast<const uint4 *>(lo);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        // ---- MMA issue: warp 0 converged, one elected lane
+        if (warp == 0) {
+            // a_major = b_major = MN (bits 15,16), bf16 x bf16 -> f32, N = 32, M = 128
+            constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(G::COUT >> 3) << 17) |
+                                       ((uint32_t)(128 >> 4) << 24);
+            constexpr uint32_t A_HI = (G::X_CP >> 4) | (1u << 14);         // SBO: next 8 rows of M = next (dy, cg) group
+            constexpr uint32_t B_HI = (G::G_PLANE >> 4) | (1u << 14);      // SBO: next 8 output channels
+            constexpr uint32_t LBO = (128u >> 4) << 16;                    // next 8 positions (K)
+            const uint32_t a_base = (smem_u32(sX) >> 4) | LBO;
+            const uint32_t b_base = (smem_u32(sG) >> 4) | LBO;
+            uint32_t elected;
+            asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(elected));
+            tc_fence_after();
+            if (elected) {
+                for (int r = 0; r < rows; ++r) {
+                    for (int ch = 0; ch < chunks; ++ch) {
+                        const uint32_t b_lo0 = b_base + (r * G::TW + ch * 16);
+                        const uint64_t b_hi = ((uint64_t)B_HI << 32) | b_lo0;
+                        const uint64_t b_lo = ((uint64_t)B_HI << 32) | (b_lo0 + (G::G_PART >> 4));
+                        const uint32_t acc = (first && r == 0 && ch == 0) ? 0u : 1u;
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+#pragma unroll
+                            for (int kw = 0; kw < G::KW; ++kw) {
+                                const uint32_t a_lo0 = a_base + (((r + 4 * g) * G::X_RP) >> 4) + ch * 16 + kw;
+                                const uint64_t a_hi = ((uint64_t)A_HI << 32) | a_lo0;
+                                const uint64_t a_lo = ((uint64_t)A_HI << 32) | (a_lo0 + (G::X_PART >> 4));
+                                const uint32_t d = tmem_base + (g * G::KW + kw) * G::COUT;
+                                tc_mma_bf16(d, a_hi, b_hi, IDESC, acc);
+                                tc_mma_bf16(d, a_lo, b_hi, IDESC, 1);
+                                tc_mma_bf16(d, a_hi, b_lo, IDESC, 1);
+                            }
+                        }
+                    }
+                }
+                tc_commit(mma_done);
+            }
+            __syncwarp();
+        }
+        first = 0;
+    }
+    // ---- all of this CTA's units are in flight: wait for the last commit, then drain TMEM into the partial
+    float *out = p.partial + (size_t)blockIdx.x * p.n_tot;
+    if (!first) {
+        mbar_wait(mma_done, phase);
+        tc_fence_after();
+        if (warp < 4 || (warp >= 8 && warp < 12)) {                      // two warps per TMEM lane quarter
+            const int q = warp & 3;
+            const int m = q * 32 + lane;                                 // (dy, ci)
+            const int dy = m >> 5, ci = m & 31;
+            for (int a = (warp >> 3); a < 2 * G::KW; a += 2) {
+                const int g = a / G::KW, kw = a - g * G::KW;
+                const int kh = 4 * g + dy;
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::COUT, v);
+                if (kh < G::KH) {
+#pragma unroll
+                    for (int co = 0; co < 32; ++co)
+                        out[((size_t)(co * G::CIN + ci) * G::KH + kh) * G::KW + kw] = __uint_as_float(v[co]);
+                }
+            }
+        }
+    } else {
+        for (int i = tid; i < p.nW; i += G::NT) out[i] = 0.f;
+    }
+    // ---- bias gradient: sum of g_u over this CTA's positions (fixed-order in-CTA reduction)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float s = gsum[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) bias_red[warp * 8 + k] = s;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) {
+        const int cog = tid >> 3, k = tid & 7;                            // warps with (warp & 3) == cog staged this group
+        float s = 0.f;
+        for (int w = cog; w < 16; w += 4) s += bias_red[w * 8 + k];
+        out[p.nW + tid] = s;
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+bool wgrad_tc_supported(const dcll_conv_layer *L) {
+    return L->precision == DCLL_PREC_BF16X3 && L->KH == 7 && L->KW == 7 && L->Cin == 32 && L->Cout == 32 && L->poolH == 1 &&
+           L->poolW == 1;
+}
+
+int wgrad_tc_splits(const dcll_conv_layer *L) {
+    Geo g = geo_of(L);
+    int n_units = L->B * ceil_div(g.Hc, 16) * ceil_div(g.Wc, 32);
+    return n_units < 148 ? n_units : 148;
+}
+
+int launch_wgrad_tc(const dcll_conv_layer *L, float *partial, int S, cudaStream_t st) {
+    Geo g = geo_of(L);
+    WgTcP p;
+    p.g_u = L->g_u, p.eps1 = L->eps1[L->cur & 1], p.partial = partial;
+    p.B = L->B, p.H = L->H, p.W = L->W, p.padH = L->padH, p.padW = L->padW, p.Hc = g.Hc, p.Wc = g.Wc;
+    p.tiles_h = ceil_div(g.Hc, 16), p.tiles_w = ceil_div(g.Wc, 32);
+    p.n_units = L->B * p.tiles_h * p.tiles_w;
+    p.nW = g.nW, p.n_tot = g.nW + L->Cout;
+    static bool configured = false;
+    if (!configured) {
+        DCLL_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgTcGeo::SMEM));
+        configured = true;
+    }
+    wgrad_tc_kernel<<<S, WgTcGeo::NT, WgTcGeo::SMEM, st>>>(p);
+    DCLL_LAUNCH_OK("wgrad_tc_kernel");
+    return DCLL_OK;
+}
+
+}  // namespace dcll
