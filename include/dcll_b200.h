@@ -68,7 +68,7 @@ typedef struct dcll_conv_layer {
     float *weight;                   /* device [Cout,Cin,KH,KW]  (the nn.Parameter)          */
     float *weight_t;                 /* device [Cin,KH*KW,CoutPad] kernel-side copy,
                                         CoutPad = 32*ceil(Cout/32); dcll_conv_sync_weights   */
-    void *weight_mma;                /* device bf16 [KH*KW][2][Cin/8][Cout][8]: {hi,lo} split weights in the
+    void *weight_mma;                /* device bf16 [KH*KW][Cin/8][2][Cout][8]: {hi,lo} split weights in the
                                         tcgen05 B-operand layout; required when precision is
                                         DCLL_PREC_BF16X3, refreshed together with weight_t       */
     float *bias;                     /* device [Cout]                                        */

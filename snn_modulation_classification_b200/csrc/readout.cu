@@ -23,7 +23,7 @@ constexpr int RO_PITCH = RO_BK + 4;
 
 // partial[blk][b][kt] = sum over this CTA's feature tiles of pv[b,f] * Wcat[kt,f],  Wcat = [wo ; wout]
 template <int KJ>
-__global__ void __launch_bounds__(256) readout_fwd_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
+__global__ void __launch_bounds__(256, 4) readout_fwd_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
                                                           const float *__restrict__ wout, int B, int F, int K, int Ktot,
                                                           float *__restrict__ partial) {
     __shared__ __align__(16) float pvs[RO_BM * RO_PITCH];

@@ -13,6 +13,8 @@
 // * N = 32 output channels, K = 16 consecutive columns of one output row per MMA; G staged as [co/8][row][col][8 co].
 // * 2 x 7 accumulators of 128 x 32 fp32 = 448 of the 512 TMEM columns (the 8th kernel row of group 1 is padding).
 // * bf16 hi/lo split of both operands, three MMAs per product (hi*hi + lo*hi + hi*lo), FP32 accumulation.
+// * Persistent and warp-specialised: 12 loader warps fill one half of a double buffer with the next (eps1, g_u) tile while
+//   one elected lane issues the 672 MMAs of the current tile; mbarriers (full: loader arrivals, empty: tcgen05.commit).
 // Partials (one per CTA) are reduced in fixed order by reduce_adam_kernel, exactly like the FP32 path.
 #include <cuda_bf16.h>
 
@@ -79,31 +81,39 @@ struct WgTcP {
 
 struct WgTcGeo {
     static constexpr int KH = 7, KW = 7, CIN = 32, COUT = 32;
-    static constexpr int TH = 16, TW = 32;
+    static constexpr int TH = 16, TW = 16;                   // one 16-column K chunk per output row
     static constexpr int XROWS = TH + 8 - 1;                 // 4 + 4 kernel rows (the 8th is padding)
-    static constexpr int XCOLS = TW + KW - 1;                // 38
+    static constexpr int XCOLS = TW + KW - 1;                // 22
     static constexpr int X_CP = XCOLS * 16;                  // channel-group pitch (bytes)
     static constexpr int X_RP = 4 * X_CP;                    // halo-row pitch
     static constexpr int X_PART = XROWS * X_RP;              // one of {hi,lo}
     static constexpr int G_ROW = TW * 16, G_PLANE = TH * G_ROW, G_PART = 4 * G_PLANE;
     static constexpr int X_BYTES = 2 * X_PART, G_BYTES = 2 * G_PART;
-    static constexpr int SMEM = X_BYTES + G_BYTES + 128 + 16 * 8 * 4;
+    static constexpr int BUF = X_BYTES + G_BYTES;            // one pipeline stage
     static constexpr int NT = 512;
+    static constexpr int LOADER_WARPS = 12;                  // warps 4..15
+    static constexpr int SMEM = 2 * BUF + 128 + 16 * 8 * 4;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(wtc::smem_u32(bar)) : "memory");
+}
+
+// Persistent, warp-specialised: warps 4..15 stage (eps1, g_u) tiles of unit i+1 into the free half of a double buffer
+// while the elected lane of warp 0 issues the MMAs of unit i; tcgen05.commit hands buffers back to the loaders.
 __global__ void __launch_bounds__(WgTcGeo::NT, 1) wgrad_tc_kernel(const WgTcP p) {
     using G = WgTcGeo;
     using namespace wtc;
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *sX = smem;
-    unsigned char *sG = smem + G::X_BYTES;
-    uint64_t *mma_done = reinterpret_cast<uint64_t *>(smem + G::X_BYTES + G::G_BYTES);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mma_done + 2);
-    float *bias_red = reinterpret_cast<float *>(smem + G::X_BYTES + G::G_BYTES + 128);   // [16 warps][8]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * G::BUF);
+    uint64_t *full = bars, *empty = bars + 2, *done = bars + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
+    float *bias_red = reinterpret_cast<float *>(smem + 2 * G::BUF + 128);   // [16 warps][8]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        mbar_init(mma_done, 1);
+        for (int i = 0; i < 2; ++i) mbar_init(full + i, G::LOADER_WARPS), mbar_init(empty + i, 1);
+        mbar_init(done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -115,142 +125,155 @@ __global__ void __launch_bounds__(WgTcGeo::NT, 1) wgrad_tc_kernel(const WgTcP p)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const float *__restrict__ gg = p.g_u;
-    const float *__restrict__ ge = p.eps1;
-    const int cgw = warp & 3;                 // channel group (of eps1 and of g_u) this warp stages
-    const int sub = warp >> 2;                // 4 warps share the positions of a group
+    const int tiles = p.tiles_h * p.tiles_w;
     float gsum[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) gsum[k] = 0.f;
 
-    const int tiles = p.tiles_h * p.tiles_w;
-    const size_t xcs = (size_t)p.H * p.W, gcs = (size_t)p.Hc * p.Wc;
-    uint32_t first = 1, phase = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-        const int b = u / tiles;
-        const int tile = u - b * tiles;
-        const int th_i = tile / p.tiles_w, tw_i = tile - th_i * p.tiles_w;
-        const int h0 = th_i * G::TH, w0 = tw_i * G::TW;
-        const int rows = min(G::TH, p.Hc - h0);                       // output rows of this tile inside the image
-        const int chunks = min(2, (p.Wc - w0 + 15) / 16);             // 16-column K chunks with at least one valid column
-        // the previous unit's MMAs must have finished reading shared memory
-        if (!first) {
-            mbar_wait(mma_done, phase);
-            phase ^= 1;
-            tc_fence_after();
+    if (warp >= 4) {
+        // ================= loaders =================
+        const float *__restrict__ gg = p.g_u;
+        const float *__restrict__ ge = p.eps1;
+        const int cgw = warp & 3;                 // channel group (of eps1 and of g_u) this warp stages
+        const int l96 = ((warp >> 2) - 1) * 32 + lane;   // 0..95 within the group
+        const size_t xcs = (size_t)p.H * p.W, gcs = (size_t)p.Hc * p.Wc;
+        int i = 0;
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+            const int buf = i & 1;
+            unsigned char *sX = smem + buf * G::BUF, *sG = sX + G::X_BYTES;
+            const int b = u / tiles;
+            const int tile = u - b * tiles;
+            const int th_i = tile / p.tiles_w, tw_i = tile - th_i * p.tiles_w;
+            const int h0 = th_i * G::TH, w0 = tw_i * G::TW;
+            if (i >= 2) mbar_wait(empty + buf, ((i >> 1) - 1) & 1);   // MMAs of unit i-2 have finished reading this half
+            // ---- eps1 halo tile: [row][cg][col][8 ci], bf16 hi | lo; two positions per iteration (16 loads in flight)
+            for (int it = l96; it < G::XROWS * G::XCOLS; it += 2 * 96) {
+                float v[2][8];
+                int r_[2], c_[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int itt = it + h * 96;
+                    r_[h] = itt / G::XCOLS, c_[h] = itt - r_[h] * G::XCOLS;
+                    const int gh = h0 - p.padH + r_[h], gw = w0 - p.padW + c_[h];
+                    const bool ok = itt < G::XROWS * G::XCOLS && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W;
+                    const size_t off = ok ? ((size_t)(b * G::CIN + cgw * 8) * p.H + gh) * p.W + gw : 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[h][k] = ok ? __ldg(ge + off + k * xcs) : 0.f;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (it + h * 96 >= G::XROWS * G::XCOLS) continue;
+                    __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        hi[k] = __float2bfloat16_rn(v[h][k]);
+                        lo[k] = __float2bfloat16_rn(v[h][k] - __bfloat162float(hi[k]));
+                    }
+                    unsigned char *dst = sX + r_[h] * G::X_RP + cgw * G::X_CP + c_[h] * 16;
+                    *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
+                    *reinterpret_cast<uint4 *>(dst + G::X_PART) = *reinterpret_cast<const uint4 *>(lo);
+                }
+            }
+            // ---- g_u tile: [cog][row][col][8 co], bf16 hi | lo (zero outside the image)
+            for (int it = l96; it < G::TH * G::TW; it += 2 * 96) {
+                float v[2][8];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int itt = it + h * 96;
+                    const int r = itt / G::TW, c = itt - r * G::TW;
+                    const int oh = h0 + r, ow = w0 + c;
+                    const bool ok = itt < G::TH * G::TW && oh < p.Hc && ow < p.Wc;
+                    const size_t off = ok ? ((size_t)(b * G::COUT + cgw * 8) * p.Hc + oh) * p.Wc + ow : 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[h][k] = ok ? __ldg(gg + off + k * gcs) : 0.f;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int itt = it + h * 96;
+                    if (itt >= G::TH * G::TW) continue;
+                    const int r = itt / G::TW, c = itt - r * G::TW;
+                    __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        gsum[k] += v[h][k];
+                        hi[k] = __float2bfloat16_rn(v[h][k]);
+                        lo[k] = __float2bfloat16_rn(v[h][k] - __bfloat162float(hi[k]));
+                    }
+                    unsigned char *dst = sG + cgw * G::G_PLANE + r * G::G_ROW + c * 16;
+                    *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
+                    *reinterpret_cast<uint4 *>(dst + G::G_PART) = *reinterpret_cast<const uint4 *>(lo);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's smem writes -> async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full + buf);
         }
-        // ---- stage eps1 halo tile: [row][cg][col][8 ci], bf16 hi | lo
-        for (int it = sub * 32 + lane; it < G::XROWS * G::XCOLS; it += 128) {
-            const int r = it / G::XCOLS, c = it - r * G::XCOLS;
-            const int gh = h0 - p.padH + r, gw = w0 - p.padW + c;
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = 0.f;
-            if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {
-                const size_t off = ((size_t)(b * G::CIN + cgw * 8) * p.H + gh) * p.W + gw;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = __ldg(ge + off + k * xcs);
-            }
-            __align__(16) __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                hi[k] = __float2bfloat16_rn(v[k]);
-                lo[k] = __float2bfloat16_rn(v[k] - __bfloat162float(hi[k]));
-            }
-            unsigned char *dst = sX + r * G::X_RP + cgw * G::X_CP + c * 16;
-            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
-            *reinterpret_cast<uint4 *>(dst + G::X_PART) = *reinterpret_cast<const uint4 *>(lo);
-        }
-        // ---- stage g_u tile: [cog][row][col][8 co], bf16 hi | lo (zero outside the image)
-        for (int it = sub * 32 + lane; it < G::TH * G::TW; it += 128) {
-            const int r = it / G::TW, c = it - r * G::TW;
-            const int oh = h0 + r, ow = w0 + c;
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = 0.f;
-            if (oh < p.Hc && ow < p.Wc) {
-                const size_t off = ((size_t)(b * G::COUT + cgw * 8) * p.Hc + oh) * p.Wc + ow;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = __ldg(gg + off + k * gcs);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) gsum[k] += v[k];
-            }
-            __align__(16) __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                hi[k] = __float2bfloat16_rn(v[k]);
-                lo[k] = __float2bfloat16_rn(v[k] - __bfloat162float(hi[k]));
-            }
-            unsigned char *dst = sG + cgw * G::G_PLANE + r * G::G_ROW + c * 16;
-            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
-            *reinterpret_cast<uint4 *>(dst + G::G_PART) = *reinterpret_cast<const uint4 *>(lo);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        // ---- MMA issue: warp 0 converged, one elected lane
-        if (warp == 0) {
-            // a_major = b_major = MN (bits 15,16), bf16 x bf16 -> f32, N = 32, M = 128
-            constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(G::COUT >> 3) << 17) |
-                                       ((uint32_t)(128 >> 4) << 24);
-            constexpr uint32_t A_HI = (G::X_CP >> 4) | (1u << 14);         // SBO: next 8 rows of M = next (dy, cg) group
-            constexpr uint32_t B_HI = (G::G_PLANE >> 4) | (1u << 14);      // SBO: next 8 output channels
-            constexpr uint32_t LBO = (128u >> 4) << 16;                    // next 8 positions (K)
-            const uint32_t a_base = (smem_u32(sX) >> 4) | LBO;
-            const uint32_t b_base = (smem_u32(sG) >> 4) | LBO;
-            uint32_t elected;
-            asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(elected));
+    } else if (warp == 0) {
+        // ================= MMA issuer =================
+        // a_major = b_major = MN (bits 15,16), bf16 x bf16 -> f32, N = 32, M = 128
+        constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(G::COUT >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t A_HI = (G::X_CP >> 4) | (1u << 14);         // SBO: next 8 rows of M = next (dy, cg) group
+        constexpr uint32_t B_HI = (G::G_PLANE >> 4) | (1u << 14);      // SBO: next 8 output channels
+        constexpr uint32_t LBO = (128u >> 4) << 16;                    // next 8 positions (K)
+        uint32_t elected;
+        asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(elected));
+        int i = 0;
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+            const int buf = i & 1;
+            const int tile = u % tiles;
+            const int h0 = (tile / p.tiles_w) * G::TH;
+            const int rows = min(G::TH, p.Hc - h0);
+            const uint32_t a_base = (smem_u32(smem + buf * G::BUF) >> 4) | LBO;
+            const uint32_t b_base = (smem_u32(smem + buf * G::BUF + G::X_BYTES) >> 4) | LBO;
+            mbar_wait(full + buf, (i >> 1) & 1);
             tc_fence_after();
             if (elected) {
                 for (int r = 0; r < rows; ++r) {
-                    for (int ch = 0; ch < chunks; ++ch) {
-                        const uint32_t b_lo0 = b_base + (r * G::TW + ch * 16);
-                        const uint64_t b_hi = ((uint64_t)B_HI << 32) | b_lo0;
-                        const uint64_t b_lo = ((uint64_t)B_HI << 32) | (b_lo0 + (G::G_PART >> 4));
-                        const uint32_t acc = (first && r == 0 && ch == 0) ? 0u : 1u;
+                    const uint32_t b_lo0 = b_base + r * G::TW;
+                    const uint64_t b_hi = ((uint64_t)B_HI << 32) | b_lo0;
+                    const uint64_t b_lo = ((uint64_t)B_HI << 32) | (b_lo0 + (G::G_PART >> 4));
+                    const uint32_t acc = (i == 0 && r == 0) ? 0u : 1u;
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
+                    for (int g = 0; g < 2; ++g) {
 #pragma unroll
-                            for (int kw = 0; kw < G::KW; ++kw) {
-                                const uint32_t a_lo0 = a_base + (((r + 4 * g) * G::X_RP) >> 4) + ch * 16 + kw;
-                                const uint64_t a_hi = ((uint64_t)A_HI << 32) | a_lo0;
-                                const uint64_t a_lo = ((uint64_t)A_HI << 32) | (a_lo0 + (G::X_PART >> 4));
-                                const uint32_t d = tmem_base + (g * G::KW + kw) * G::COUT;
-                                tc_mma_bf16(d, a_hi, b_hi, IDESC, acc);
-                                tc_mma_bf16(d, a_lo, b_hi, IDESC, 1);
-                                tc_mma_bf16(d, a_hi, b_lo, IDESC, 1);
-                            }
+                        for (int kw = 0; kw < G::KW; ++kw) {
+                            const uint32_t a_lo0 = a_base + (((r + 4 * g) * G::X_RP) >> 4) + kw;
+                            const uint64_t a_hi = ((uint64_t)A_HI << 32) | a_lo0;
+                            const uint64_t a_lo = ((uint64_t)A_HI << 32) | (a_lo0 + (G::X_PART >> 4));
+                            const uint32_t d = tmem_base + (g * G::KW + kw) * G::COUT;
+                            tc_mma_bf16(d, a_hi, b_hi, IDESC, acc);
+                            tc_mma_bf16(d, a_lo, b_hi, IDESC, 1);
+                            tc_mma_bf16(d, a_hi, b_lo, IDESC, 1);
                         }
                     }
                 }
-                tc_commit(mma_done);
+                tc_commit(empty + buf);
             }
             __syncwarp();
         }
-        first = 0;
+        if (elected) tc_commit(done);
+        __syncwarp();
     }
-    // ---- all of this CTA's units are in flight: wait for the last commit, then drain TMEM into the partial
+    // ---- drain: every MMA of this CTA has completed when `done` flips
     float *out = p.partial + (size_t)blockIdx.x * p.n_tot;
-    if (!first) {
-        mbar_wait(mma_done, phase);
-        tc_fence_after();
-        if (warp < 4 || (warp >= 8 && warp < 12)) {                      // two warps per TMEM lane quarter
-            const int q = warp & 3;
-            const int m = q * 32 + lane;                                 // (dy, ci)
-            const int dy = m >> 5, ci = m & 31;
-            for (int a = (warp >> 3); a < 2 * G::KW; a += 2) {
-                const int g = a / G::KW, kw = a - g * G::KW;
-                const int kh = 4 * g + dy;
-                uint32_t v[32];
-                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::COUT, v);
-                if (kh < G::KH) {
+    mbar_wait(done, 0);
+    tc_fence_after();
+    {
+        const int q = warp & 3;                                          // TMEM lane quarter of this warp
+        const int m = q * 32 + lane;                                     // (dy, ci)
+        const int dy = m >> 5, ci = m & 31;
+        for (int a = (warp >> 2); a < 2 * G::KW; a += 4) {
+            const int g = a / G::KW, kw = a - g * G::KW;
+            const int kh = 4 * g + dy;
+            uint32_t v[32];
+            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::COUT, v);
+            if (kh < G::KH) {
 #pragma unroll
-                    for (int co = 0; co < 32; ++co)
-                        out[((size_t)(co * G::CIN + ci) * G::KH + kh) * G::KW + kw] = __uint_as_float(v[co]);
-                }
+                for (int co = 0; co < 32; ++co)
+                    out[((size_t)(co * G::CIN + ci) * G::KH + kh) * G::KW + kw] = __uint_as_float(v[co]);
             }
         }
-    } else {
-        for (int i = tid; i < p.nW; i += G::NT) out[i] = 0.f;
     }
     // ---- bias gradient: sum of g_u over this CTA's positions (fixed-order in-CTA reduction)
 #pragma unroll
@@ -263,9 +286,9 @@ __global__ void __launch_bounds__(WgTcGeo::NT, 1) wgrad_tc_kernel(const WgTcP p)
     tc_fence_before();
     __syncthreads();
     if (tid < 32) {
-        const int cog = tid >> 3, k = tid & 7;                            // warps with (warp & 3) == cog staged this group
+        const int cog = tid >> 3, k = tid & 7;                            // loader warps with (warp & 3) == cog staged this group
         float s = 0.f;
-        for (int w = cog; w < 16; w += 4) s += bias_red[w * 8 + k];
+        for (int w = 4 + cog; w < 16; w += 4) s += bias_red[w * 8 + k];
         out[p.nW + tid] = s;
     }
     if (warp == 2) {
@@ -280,7 +303,7 @@ bool wgrad_tc_supported(const dcll_conv_layer *L) {
 
 int wgrad_tc_splits(const dcll_conv_layer *L) {
     Geo g = geo_of(L);
-    int n_units = L->B * ceil_div(g.Hc, 16) * ceil_div(g.Wc, 32);
+    int n_units = L->B * ceil_div(g.Hc, 16) * ceil_div(g.Wc, 16);
     return n_units < 148 ? n_units : 148;
 }
 
@@ -289,7 +312,7 @@ int launch_wgrad_tc(const dcll_conv_layer *L, float *partial, int S, cudaStream_
     WgTcP p;
     p.g_u = L->g_u, p.eps1 = L->eps1[L->cur & 1], p.partial = partial;
     p.B = L->B, p.H = L->H, p.W = L->W, p.padH = L->padH, p.padW = L->padW, p.Hc = g.Hc, p.Wc = g.Wc;
-    p.tiles_h = ceil_div(g.Hc, 16), p.tiles_w = ceil_div(g.Wc, 32);
+    p.tiles_h = ceil_div(g.Hc, 16), p.tiles_w = ceil_div(g.Wc, 16);
     p.n_units = L->B * p.tiles_h * p.tiles_w;
     p.nW = g.nW, p.n_tot = g.nW + L->Cout;
     static bool configured = false;
