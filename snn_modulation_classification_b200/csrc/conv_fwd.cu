@@ -362,7 +362,8 @@ static int launch_pool(FwdP &p, int B, int PH, int PW, cudaStream_t st) {
 }
 
 int launch_conv_fwd(const dcll_conv_layer *L, const void *x, cudaStream_t st) {
-    if (L->precision == DCLL_PREC_BF16X3) return launch_conv_fwd_tc(L, x, st);
+    // "bf16x3" = tensor cores wherever a shape is instantiated; the rest (e.g. layer 0, K = 49) stays on the FMA pipe
+    if (L->precision == DCLL_PREC_BF16X3 && tc_supported(L)) return launch_conv_fwd_tc(L, x, st);
     Geo g = geo_of(L);
     FwdP p;
     p.x = L->x_mode == DCLL_X_DENSE ? (const float *)x : nullptr;

@@ -97,8 +97,8 @@ static int check_layer(const dcll_conv_layer *L, const char *who) {
                  g.Hc, g.Wc, L->poolH, L->poolW);
     DCLL_REQUIRE(L->precision == DCLL_PREC_FP32 || L->precision == DCLL_PREC_BF16X3, DCLL_EINVAL, "%s: unknown precision mode %d",
                  who, L->precision);
-    DCLL_REQUIRE(L->precision != DCLL_PREC_BF16X3 || (tc_supported(L) && L->weight_mma), DCLL_EUNSUPPORTED,
-                 "%s: the bf16x3 tensor-core conv is instantiated for 7x7, 32->32 channels, pooling 1 (and needs weight_mma)", who);
+    DCLL_REQUIRE(L->precision != DCLL_PREC_BF16X3 || !tc_supported(L) || L->weight_mma, DCLL_EINVAL,
+                 "%s: the bf16x3 tensor-core conv needs weight_mma", who);
     DCLL_REQUIRE(L->alpha && L->alphas && L->tau_m && L->tau_s && L->weight && L->weight_t && L->bias && L->wo && L->bo,
                  DCLL_EINVAL, "%s: null parameter pointer", who);
     DCLL_REQUIRE(!L->output_layer || (L->wout && L->bout && L->output), DCLL_EINVAL, "%s: output layer without output_", who);

@@ -6,7 +6,7 @@
 //   :694-697  SmoothL1Loss(pvoutput, target) [+ (output, target)]   -> readout_finish_kernel (gradient only)
 //   :724-728  clout.append(argmax)                                  -> readout_finish_kernel (device side)
 //   :704      autograd: d loss / d membrane through i2o, pool, sigmoid -> readout_bwd_kernel
-//             d loss / d output_.{weight,bias} + optimizer2.step()  -> wout_grad_adam_kernel
+//             d loss / d output_.{weight,bias} + optimizer2.step()  -> readout_bwd_kernel<.,true> (fused)
 //
 // The read-out is a skinny GEMM [B,F] x [F,Ktot] whose frozen matrix (4*K*F bytes, 50 MB per layer at
 // 128x128) must be amortised over the batch, so it is a separate HBM-bound pass over pv rather than an
@@ -139,93 +139,87 @@ __global__ void __launch_bounds__(256) readout_finish_kernel(const float *__rest
 }
 
 // g_u[b,f] = (sum_k g_o[b,k] Wo[k,f]) * (1 - pv) * pv      (gradient w.r.t. the membrane at the pool argmax)
-// Thread = one feature column of Wo held in registers, swept over a slice of the batch.
-template <int KMAX>
+// Thread = one feature column of Wo held in registers, swept over a slice of the batch (4 samples in flight).
+// WOUT variant (output layer, whole batch per CTA): the same sweep also accumulates
+//   gWout[k,f] = sum_b g_o2[b,k] pv[b,f]   and applies optimizer2.step() (Adam, lr 1e-4, torch defaults;
+//   dcll/pytorch_libdcll.py:636-638,713-714) thread-locally, so pv is read once for both purposes.
+template <int KMAX, bool WOUT>
 __global__ void __launch_bounds__(256) readout_bwd_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
-                                                          const float *__restrict__ g_o, int B, int F, int K, int b_per_blk,
-                                                          float *__restrict__ g_u) {
+                                                          const float *__restrict__ g_o, const float *__restrict__ g_o2, int B,
+                                                          int F, int K, int b_per_blk, float *__restrict__ g_u,
+                                                          float *__restrict__ wout, float *__restrict__ bout,
+                                                          float *__restrict__ m_w, float *__restrict__ v_w,
+                                                          float *__restrict__ m_b, float *__restrict__ v_b,
+                                                          float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
+                                                          AdamScalars sc) {
     __shared__ float gs[64][KMAX];
+    __shared__ float gs2[WOUT ? 64 : 1][KMAX];
     const int tid = threadIdx.x;
     const int f = blockIdx.x * 256 + tid;
-    float w[KMAX];
+    const bool fok = f < F;
+    float w[KMAX], acc[WOUT ? KMAX : 1];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) w[k] = (k < K && f < F) ? __ldg(wo + (size_t)k * F + f) : 0.f;
+    for (int k = 0; k < KMAX; ++k) w[k] = (k < K && fok) ? __ldg(wo + (size_t)k * F + f) : 0.f;
+    if (WOUT) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
+    }
+    float bsum = 0.f;
     const int b_begin = blockIdx.y * b_per_blk, b_end = min(B, b_begin + b_per_blk);
     for (int b0 = b_begin; b0 < b_end; b0 += 64) {
         const int nb = min(64, b_end - b0);
         __syncthreads();
         for (int i = tid; i < 64 * KMAX; i += 256) {
             int bb = i / KMAX, k = i - bb * KMAX;
-            gs[bb][k] = (bb < nb && k < K) ? g_o[(size_t)(b0 + bb) * K + k] : 0.f;
+            const bool ok = bb < nb && k < K;
+            gs[bb][k] = ok ? g_o[(size_t)(b0 + bb) * K + k] : 0.f;
+            if (WOUT) gs2[bb][k] = ok ? g_o2[(size_t)(b0 + bb) * K + k] : 0.f;
         }
         __syncthreads();
-        if (f < F) {
-            for (int bb = 0; bb < nb; ++bb) {
-                float s = 0.f;
+        if (fok) {
+            for (int bb = 0; bb < nb; bb += 4) {
+                float pvv[4];
 #pragma unroll
-                for (int k = 0; k < KMAX; ++k) s = fmaf(gs[bb][k], w[k], s);
-                size_t o = (size_t)(b0 + bb) * F + f;
-                float pvv = __ldg(pv + o);
-                g_u[o] = s * (1.f - pvv) * pvv;
-            }
-        }
-    }
-}
-
-// output_ read-out (last layer): gWout[k,f] = sum_b g_o2[b,k] pv[b,f], gbout[k] = sum_b g_o2[b,k],
-// followed by optimizer2.step() (Adam, lr 1e-4, torch defaults; dcll/pytorch_libdcll.py:636-638,713-714).
-template <int KMAX>
-__global__ void __launch_bounds__(256) wout_grad_adam_kernel(const float *__restrict__ pv, const float *__restrict__ g_o2,
-                                                             int B, int F, int K, float *__restrict__ wout,
-                                                             float *__restrict__ bout, float *__restrict__ m_w,
-                                                             float *__restrict__ v_w, float *__restrict__ m_b,
-                                                             float *__restrict__ v_b, float *__restrict__ grad_w,
-                                                             float *__restrict__ grad_b, int apply, AdamScalars sc) {
-    __shared__ float gs[64][KMAX];
-    const int tid = threadIdx.x;
-    const int f = blockIdx.x * 256 + tid;
-    float acc[KMAX];
+                for (int u = 0; u < 4; ++u) pvv[u] = (bb + u < nb) ? __ldg(pv + (size_t)(b0 + bb + u) * F + f) : 0.f;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
-    float bsum = 0.f;  // block 0, tid < K: bias gradient
-    for (int b0 = 0; b0 < B; b0 += 64) {
-        const int nb = min(64, B - b0);
-        __syncthreads();
-        for (int i = tid; i < 64 * KMAX; i += 256) {
-            int bb = i / KMAX, k = i - bb * KMAX;
-            gs[bb][k] = (bb < nb && k < K) ? g_o2[(size_t)(b0 + bb) * K + k] : 0.f;
-        }
-        __syncthreads();
-        if (f < F) {
-            for (int bb = 0; bb < nb; ++bb) {
-                float pvv = __ldg(pv + (size_t)(b0 + bb) * F + f);
+                for (int u = 0; u < 4; ++u) {
+                    if (bb + u >= nb) break;
+                    float s = 0.f;
 #pragma unroll
-                for (int k = 0; k < KMAX; ++k) acc[k] = fmaf(gs[bb][k], pvv, acc[k]);
-            }
-        }
-        if (blockIdx.x == 0 && tid < K)
-            for (int bb = 0; bb < nb; ++bb) bsum += gs[bb][tid];
-    }
-    if (f < F) {
+                    for (int k = 0; k < KMAX; ++k) s = fmaf(gs[bb + u][k], w[k], s);
+                    g_u[(size_t)(b0 + bb + u) * F + f] = s * (1.f - pvv[u]) * pvv[u];
+                    if (WOUT) {
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-            if (k < K) {
-                size_t o = (size_t)k * F + f;
-                if (grad_w) grad_w[o] = acc[k];
-                if (apply) {
-                    float w = wout[o], m = m_w[o], v = v_w[o];
-                    adam_elem(w, acc[k], m, v, sc);
-                    wout[o] = w, m_w[o] = m, v_w[o] = v;
+                        for (int k = 0; k < KMAX; ++k) acc[k] = fmaf(gs2[bb + u][k], pvv[u], acc[k]);
+                    }
                 }
             }
         }
+        if (WOUT && blockIdx.x == 0 && tid < K)
+            for (int bb = 0; bb < nb; ++bb) bsum += gs2[bb][tid];
     }
-    if (blockIdx.x == 0 && tid < K) {
-        if (grad_b) grad_b[tid] = bsum;
-        if (apply) {
-            float w = bout[tid], m = m_b[tid], v = v_b[tid];
-            adam_elem(w, bsum, m, v, sc);
-            bout[tid] = w, m_b[tid] = m, v_b[tid] = v;
+    if (WOUT) {
+        if (fok) {
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                if (k < K) {
+                    size_t o = (size_t)k * F + f;
+                    if (grad_w) grad_w[o] = acc[k];
+                    if (apply) {
+                        float wv = wout[o], m = m_w[o], v = v_w[o];
+                        adam_elem(wv, acc[k], m, v, sc);
+                        wout[o] = wv, m_w[o] = m, v_w[o] = v;
+                    }
+                }
+            }
+        }
+        if (blockIdx.x == 0 && tid < K) {
+            if (grad_b) grad_b[tid] = bsum;
+            if (apply) {
+                float wv = bout[tid], m = m_b[tid], v = v_b[tid];
+                adam_elem(wv, bsum, m, v, sc);
+                bout[tid] = wv, m_b[tid] = m, v_b[tid] = v;
+            }
         }
     }
 }
@@ -304,27 +298,34 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
     const float *g_o = (const float *)(base + ws.off_go), *g_o2 = (const float *)(base + ws.off_go2);
     DCLL_REQUIRE(L->K <= 32, DCLL_EUNSUPPORTED, "target_size %d > 32 unsupported in the backward read-out", L->K);
     const int fblk = ceil_div(g.F, 256);
-    // enough CTAs to fill the machine: slice the batch when F is small
-    int slices = max(1, min(ceil_div(L->B, 64), ceil_div(2 * 148, fblk)));
-    int b_per = ceil_div(ceil_div(L->B, slices), 64) * 64;
-    slices = ceil_div(L->B, b_per);
-    dim3 grid(fblk, slices);
-    if (L->K <= 16)
-        readout_bwd_kernel<16><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u);
-    else
-        readout_bwd_kernel<32><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u);
-    DCLL_LAUNCH_OK("readout_bwd_kernel");
+    AdamScalars sc = {};
     if (L->output_layer) {
-        AdamScalars sc = adam_scalars(a->adam_out, a->adam_out.step + 1);
+        // the output_ gradient reduces over the whole batch inside one thread: no batch slicing
+        sc = adam_scalars(a->adam_out, a->adam_out.step + 1);
         dcll_adam &o = a->adam_out;
+        dim3 grid(fblk, 1);
         if (L->K <= 16)
-            wout_grad_adam_kernel<16><<<fblk, 256, 0, st>>>(L->pv, g_o2, L->B, g.F, L->K, L->wout, L->bout, o.m_w, o.v_w,
-                                                            o.m_b, o.v_b, a->grad_wout, a->grad_bout, a->apply_update, sc);
+            readout_bwd_kernel<16, true><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, g_o2, L->B, g.F, L->K, L->B, L->g_u, L->wout,
+                                                              L->bout, o.m_w, o.v_w, o.m_b, o.v_b, a->grad_wout, a->grad_bout,
+                                                              a->apply_update, sc);
         else
-            wout_grad_adam_kernel<32><<<fblk, 256, 0, st>>>(L->pv, g_o2, L->B, g.F, L->K, L->wout, L->bout, o.m_w, o.v_w,
-                                                            o.m_b, o.v_b, a->grad_wout, a->grad_bout, a->apply_update, sc);
-        DCLL_LAUNCH_OK("wout_grad_adam_kernel");
+            readout_bwd_kernel<32, true><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, g_o2, L->B, g.F, L->K, L->B, L->g_u, L->wout,
+                                                              L->bout, o.m_w, o.v_w, o.m_b, o.v_b, a->grad_wout, a->grad_bout,
+                                                              a->apply_update, sc);
+    } else {
+        // enough CTAs to fill the machine: slice the batch when F is small
+        int slices = max(1, min(ceil_div(L->B, 64), ceil_div(2 * 148, fblk)));
+        int b_per = ceil_div(ceil_div(L->B, slices), 64) * 64;
+        slices = ceil_div(L->B, b_per);
+        dim3 grid(fblk, slices);
+        if (L->K <= 16)
+            readout_bwd_kernel<16, false><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, nullptr, L->B, g.F, L->K, b_per, L->g_u, nullptr,
+                                                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, sc);
+        else
+            readout_bwd_kernel<32, false><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, nullptr, L->B, g.F, L->K, b_per, L->g_u, nullptr,
+                                                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, sc);
     }
+    DCLL_LAUNCH_OK("readout_bwd_kernel");
     return DCLL_OK;
 }
 

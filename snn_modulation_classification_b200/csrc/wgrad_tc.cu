@@ -79,13 +79,21 @@ struct WgTcP {
     int tiles_h, tiles_w, n_units, n_tot, nW;
 };
 
-struct WgTcGeo {
-    static constexpr int KH = 7, KW = 7, CIN = 32, COUT = 32;
+// CIN = 32: M = 4 kernel rows x 32 channels, two row groups (g = 0,1).
+// CIN = 1 (layer 0): the single channel is zero-padded to one group of 8, M = 16 kernel rows x 8 (rows 7..15 and
+// channels 1..7 are padding), one row group; the work is tiny, the kernel is bound by streaming g_u.
+template <int CIN_>
+struct WgTcGeoT {
+    static constexpr int KH = 7, KW = 7, CIN = CIN_, COUT = 32;
     static constexpr int TH = 16, TW = 16;                   // one 16-column K chunk per output row
-    static constexpr int XROWS = TH + 8 - 1;                 // 4 + 4 kernel rows (the 8th is padding)
+    static constexpr int CGR = CIN == 32 ? 4 : 1;            // channel groups per halo row
+    static constexpr int NG = CIN == 32 ? 2 : 1;             // kernel-row groups
+    static constexpr int DY = 128 / (CGR * 8);               // kernel rows per group (incl. padding)
+    static constexpr int NACC = NG * KW;                     // accumulators of 128 x 32 fp32
+    static constexpr int XROWS = TH + NG * DY - 1;
     static constexpr int XCOLS = TW + KW - 1;                // 22
     static constexpr int X_CP = XCOLS * 16;                  // channel-group pitch (bytes)
-    static constexpr int X_RP = 4 * X_CP;                    // halo-row pitch
+    static constexpr int X_RP = CGR * X_CP;                  // halo-row pitch
     static constexpr int X_PART = XROWS * X_RP;              // one of {hi,lo}
     static constexpr int G_ROW = TW * 16, G_PLANE = TH * G_ROW, G_PART = 4 * G_PLANE;
     static constexpr int X_BYTES = 2 * X_PART, G_BYTES = 2 * G_PART;
@@ -93,6 +101,8 @@ struct WgTcGeo {
     static constexpr int NT = 512;
     static constexpr int LOADER_WARPS = 12;                  // warps 4..15
     static constexpr int SMEM = 2 * BUF + 128 + 16 * 8 * 4;
+    static constexpr int TMEM_COLS = NACC * COUT <= 256 ? 256 : 512;
+    static_assert(CIN == 32 || CIN == 1, "instantiated for 32 and 1 input channels");
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -101,8 +111,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 
 // Persistent, warp-specialised: warps 4..15 stage (eps1, g_u) tiles of unit i+1 into the free half of a double buffer
 // while the elected lane of warp 0 issues the MMAs of unit i; tcgen05.commit hands buffers back to the loaders.
-__global__ void __launch_bounds__(WgTcGeo::NT, 1) wgrad_tc_kernel(const WgTcP p) {
-    using G = WgTcGeo;
+template <int CIN_>
+__global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
+    using G = WgTcGeoT<CIN_>;
     using namespace wtc;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * G::BUF);
@@ -117,7 +128,7 @@ __global__ void __launch_bounds__(WgTcGeo::NT, 1) wgrad_tc_kernel(const WgTcP p)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)G::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -146,32 +157,48 @@ __global__ void __launch_bounds__(WgTcGeo::NT, 1) wgrad_tc_kernel(const WgTcP p)
             const int th_i = tile / p.tiles_w, tw_i = tile - th_i * p.tiles_w;
             const int h0 = th_i * G::TH, w0 = tw_i * G::TW;
             if (i >= 2) mbar_wait(empty + buf, ((i >> 1) - 1) & 1);   // MMAs of unit i-2 have finished reading this half
-            // ---- eps1 halo tile: [row][cg][col][8 ci], bf16 hi | lo; two positions per iteration (16 loads in flight)
-            for (int it = l96; it < G::XROWS * G::XCOLS; it += 2 * 96) {
-                float v[2][8];
-                int r_[2], c_[2];
+            // ---- eps1 halo tile: [row][cg][col][8 ci], bf16 hi | lo
+            if (G::CIN == 32) {
+                // two positions per iteration (16 loads in flight)
+                for (int it = l96; it < G::XROWS * G::XCOLS; it += 2 * 96) {
+                    float v[2][8];
+                    int r_[2], c_[2];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int itt = it + h * 96;
-                    r_[h] = itt / G::XCOLS, c_[h] = itt - r_[h] * G::XCOLS;
-                    const int gh = h0 - p.padH + r_[h], gw = w0 - p.padW + c_[h];
-                    const bool ok = itt < G::XROWS * G::XCOLS && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W;
-                    const size_t off = ok ? ((size_t)(b * G::CIN + cgw * 8) * p.H + gh) * p.W + gw : 0;
+                    for (int h = 0; h < 2; ++h) {
+                        const int itt = it + h * 96;
+                        r_[h] = itt / G::XCOLS, c_[h] = itt - r_[h] * G::XCOLS;
+                        const int gh = h0 - p.padH + r_[h], gw = w0 - p.padW + c_[h];
+                        const bool ok = itt < G::XROWS * G::XCOLS && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W;
+                        const size_t off = ok ? ((size_t)(b * G::CIN + cgw * 8) * p.H + gh) * p.W + gw : 0;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) v[h][k] = ok ? __ldg(ge + off + k * xcs) : 0.f;
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (it + h * 96 >= G::XROWS * G::XCOLS) continue;
-                    __align__(16) __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        hi[k] = __float2bfloat16_rn(v[h][k]);
-                        lo[k] = __float2bfloat16_rn(v[h][k] - __bfloat162float(hi[k]));
+                        for (int k = 0; k < 8; ++k) v[h][k] = ok ? __ldg(ge + off + k * xcs) : 0.f;
                     }
-                    unsigned char *dst = sX + r_[h] * G::X_RP + cgw * G::X_CP + c_[h] * 16;
-                    *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
-                    *reinterpret_cast<uint4 *>(dst + G::X_PART) = *reinterpret_cast<const uint4 *>(lo);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (it + h * 96 >= G::XROWS * G::XCOLS) continue;
+                        __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            hi[k] = __float2bfloat16_rn(v[h][k]);
+                            lo[k] = __float2bfloat16_rn(v[h][k] - __bfloat162float(hi[k]));
+                        }
+                        unsigned char *dst = sX + r_[h] * G::X_RP + cgw * G::X_CP + c_[h] * 16;
+                        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
+                        *reinterpret_cast<uint4 *>(dst + G::X_PART) = *reinterpret_cast<const uint4 *>(lo);
+                    }
+                }
+            } else {
+                // single input channel: all loader lanes share the positions; channels 1..7 of the group are zero
+                for (int it = (warp - 4) * 32 + lane; it < G::XROWS * G::XCOLS; it += G::LOADER_WARPS * 32) {
+                    const int r = it / G::XCOLS, c = it - r * G::XCOLS;
+                    const int gh = h0 - p.padH + r, gw = w0 - p.padW + c;
+                    float v = 0.f;
+                    if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) v = __ldg(ge + ((size_t)b * p.H + gh) * p.W + gw);
+                    __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                    __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+                    unsigned char *dst = sX + r * G::X_RP + c * 16;
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4((uint32_t)__bfloat16_as_ushort(hi), 0u, 0u, 0u);
+                    *reinterpret_cast<uint4 *>(dst + G::X_PART) = make_uint4((uint32_t)__bfloat16_as_ushort(lo), 0u, 0u, 0u);
                 }
             }
             // ---- g_u tile: [cog][row][col][8 co], bf16 hi | lo (zero outside the image)
@@ -235,10 +262,10 @@ __global__ void __launch_bounds__(WgTcGeo::NT, 1) wgrad_tc_kernel(const WgTcP p)
                     const uint64_t b_lo = ((uint64_t)B_HI << 32) | (b_lo0 + (G::G_PART >> 4));
                     const uint32_t acc = (i == 0 && r == 0) ? 0u : 1u;
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
+                    for (int g = 0; g < G::NG; ++g) {
 #pragma unroll
                         for (int kw = 0; kw < G::KW; ++kw) {
-                            const uint32_t a_lo0 = a_base + (((r + 4 * g) * G::X_RP) >> 4) + kw;
+                            const uint32_t a_lo0 = a_base + (((r + G::DY * g) * G::X_RP) >> 4) + kw;
                             const uint64_t a_hi = ((uint64_t)A_HI << 32) | a_lo0;
                             const uint64_t a_lo = ((uint64_t)A_HI << 32) | (a_lo0 + (G::X_PART >> 4));
                             const uint32_t d = tmem_base + (g * G::KW + kw) * G::COUT;
@@ -261,14 +288,16 @@ __global__ void __launch_bounds__(WgTcGeo::NT, 1) wgrad_tc_kernel(const WgTcP p)
     tc_fence_after();
     {
         const int q = warp & 3;                                          // TMEM lane quarter of this warp
-        const int m = q * 32 + lane;                                     // (dy, ci)
-        const int dy = m >> 5, ci = m & 31;
-        for (int a = (warp >> 2); a < 2 * G::KW; a += 4) {
+        const int m = q * 32 + lane;                                     // (dy, ci) resp. (dy, c8)
+        const int dy = G::CIN == 32 ? (m >> 5) : (m >> 3);
+        const int ci = G::CIN == 32 ? (m & 31) : 0;
+        const bool lane_ok = G::CIN == 32 ? true : ((m & 7) == 0);
+        for (int a = (warp >> 2); a < G::NACC; a += 4) {
             const int g = a / G::KW, kw = a - g * G::KW;
-            const int kh = 4 * g + dy;
+            const int kh = G::DY * g + dy;
             uint32_t v[32];
             tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::COUT, v);
-            if (kh < G::KH) {
+            if (kh < G::KH && lane_ok) {
 #pragma unroll
                 for (int co = 0; co < 32; ++co)
                     out[((size_t)(co * G::CIN + ci) * G::KH + kh) * G::KW + kw] = __uint_as_float(v[co]);
@@ -292,13 +321,13 @@ __global__ void __launch_bounds__(WgTcGeo::NT, 1) wgrad_tc_kernel(const WgTcP p)
         out[p.nW + tid] = s;
     }
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)G::TMEM_COLS) : "memory");
     }
 }
 
 bool wgrad_tc_supported(const dcll_conv_layer *L) {
-    return L->precision == DCLL_PREC_BF16X3 && L->KH == 7 && L->KW == 7 && L->Cin == 32 && L->Cout == 32 && L->poolH == 1 &&
-           L->poolW == 1;
+    return L->precision == DCLL_PREC_BF16X3 && L->KH == 7 && L->KW == 7 && (L->Cin == 32 || L->Cin == 1) && L->Cout == 32 &&
+           L->poolH == 1 && L->poolW == 1;
 }
 
 int wgrad_tc_splits(const dcll_conv_layer *L) {
@@ -317,10 +346,12 @@ int launch_wgrad_tc(const dcll_conv_layer *L, float *partial, int S, cudaStream_
     p.nW = g.nW, p.n_tot = g.nW + L->Cout;
     static bool configured = false;
     if (!configured) {
-        DCLL_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgTcGeo::SMEM));
+        DCLL_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgTcGeoT<32>::SMEM));
+        DCLL_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgTcGeoT<1>::SMEM));
         configured = true;
     }
-    wgrad_tc_kernel<<<S, WgTcGeo::NT, WgTcGeo::SMEM, st>>>(p);
+    if (L->Cin == 32) wgrad_tc_kernel<32><<<S, 512, WgTcGeoT<32>::SMEM, st>>>(p);
+    else wgrad_tc_kernel<1><<<S, 512, WgTcGeoT<1>::SMEM, st>>>(p);
     DCLL_LAUNCH_OK("wgrad_tc_kernel");
     return DCLL_OK;
 }

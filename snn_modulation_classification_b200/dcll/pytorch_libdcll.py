@@ -357,7 +357,9 @@ class ContinuousConv2D(nn.Module):
         desc.Cout, desc.KH, desc.KW = self.out_channels, self.kernel_size[0], self.kernel_size[1]
         desc.padH, desc.padW = self.padding
         desc.x_mode = x_mode
-        desc.precision = _lib.PREC_BF16X3 if self.tensor_core_ok() else _lib.PREC_FP32
+        # 'bf16x3' selects the tensor-core kernels wherever the library has an instantiation for the shape
+        # (forward: 7x7, 32->32; weight gradient: 7x7, {1,32}->32); other kernels of the layer stay FP32.
+        desc.precision = _lib.PREC_BF16X3 if self.precision == 'bf16x3' else _lib.PREC_FP32
         desc.alpharp, desc.wrp = float(self.alpharp), float(self.wrp)
         mode, ts = self._coef.get(self, self.in_channels, height, width)
         desc.coef_mode = mode
