@@ -53,7 +53,7 @@ WsLayout ws_layout(const dcll_conv_layer *L) {
     Geo g = geo_of(L);
     WsLayout w;
     // read-out partial blocks: enough CTAs (6 per SM) to hide the load latency of the single-buffered tiles
-    w.n_ro = max(1, min(ceil_div(g.F, 32), 148 * 6));
+    w.n_ro = max(1, min(ceil_div(g.F, 64), 148 * 3));
     w.n_split = max(wgrad_splits(L), wgrad_tc_splits(L));   // room for either weight-gradient kernel
     size_t off = 0;
     w.off_ro_part = off;

@@ -18,20 +18,70 @@
 namespace dcll {
 
 constexpr int RO_BM = 64;   // samples per tile
-constexpr int RO_BK = 32;   // features per tile
-constexpr int RO_PITCH = RO_BK + 4;
+constexpr int RO_BK = 64;   // features per pipeline stage
+constexpr int RO_PITCH = RO_BK + 4;   // floats; (pitch/4) odd -> conflict-free float4 reads across rows
+
+__device__ __forceinline__ void ro_cp16(void *smem_dst, const void *gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void ro_zero16(void *smem_dst) { *reinterpret_cast<float4 *>(smem_dst) = make_float4(0.f, 0.f, 0.f, 0.f); }
 
 // partial[blk][b][kt] = sum over this CTA's feature tiles of pv[b,f] * Wcat[kt,f],  Wcat = [wo ; wout]
-template <int KJ>
-__global__ void __launch_bounds__(256, 4) readout_fwd_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
-                                                          const float *__restrict__ wout, int B, int F, int K, int Ktot,
-                                                          float *__restrict__ partial) {
-    __shared__ __align__(16) float pvs[RO_BM * RO_PITCH];
-    __shared__ __align__(16) float wos[16 * KJ * RO_PITCH];
+// Two-stage cp.async pipeline: the (64 x 64) pv tile and the (Ktot x 64) read-out tile of stage s+1 stream into shared
+// memory while stage s is multiplied; thread = 4 samples x KJ outputs, float4 along the feature axis.
+// Requires F % 4 == 0 and 16-byte aligned rows (checked by the launcher; otherwise the scalar-load variant runs).
+template <int KJ, bool VEC>
+__global__ void __launch_bounds__(256, 3) readout_fwd_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
+                                                             const float *__restrict__ wout, int B, int F, int K, int Ktot,
+                                                             float *__restrict__ partial) {
+    extern __shared__ __align__(16) float ro_smem[];
+    constexpr int ROWS = RO_BM + 16 * KJ;                 // pv rows followed by read-out rows
+    constexpr int STAGE = ROWS * RO_PITCH;
     const int tid = threadIdx.x;
     const int tb = tid & 15, tk = tid >> 4;
     const int n_ft = (F + RO_BK - 1) / RO_BK;
-    const int lr = tid >> 5, lc = tid & 31;  // loader: 8 rows x 32 columns per pass
+
+    auto issue = [&](int stage, int ft, int b0) {
+        float *dst = ro_smem + stage * STAGE;
+        const int f0 = ft * RO_BK;
+        // ROWS x 16 chunks of 16 bytes
+        for (int i = tid; i < ROWS * (RO_BK / 4); i += 256) {
+            const int row = i / (RO_BK / 4), c4 = i - row * (RO_BK / 4);
+            const int f = f0 + c4 * 4;
+            float *d = dst + row * RO_PITCH + c4 * 4;
+            const float *src = nullptr;
+            if (row < RO_BM) {
+                const int b = b0 + row;
+                if (b < B) src = pv + (size_t)b * F + f;
+            } else {
+                const int k = row - RO_BM;
+                if (k < Ktot) src = (k < K ? wo + (size_t)k * F : wout + (size_t)(k - K) * F) + f;
+            }
+            if (VEC) {
+                if (src && f + 4 <= F) ro_cp16(d, src);
+                else {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (src) {
+                        if (f < F) v.x = src[0];
+                        if (f + 1 < F) v.y = src[1];
+                        if (f + 2 < F) v.z = src[2];
+                    }
+                    *reinterpret_cast<float4 *>(d) = v;
+                }
+            } else {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (src) {
+                    if (f < F) v.x = __ldg(src);
+                    if (f + 1 < F) v.y = __ldg(src + 1);
+                    if (f + 2 < F) v.z = __ldg(src + 2);
+                    if (f + 3 < F) v.w = __ldg(src + 3);
+                }
+                *reinterpret_cast<float4 *>(d) = v;
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
 
     for (int b0 = 0; b0 < B; b0 += RO_BM) {
         float acc[4][KJ];
@@ -39,23 +89,20 @@ __global__ void __launch_bounds__(256, 4) readout_fwd_kernel(const float *__rest
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < KJ; ++j) acc[i][j] = 0.f;
-        for (int ft = blockIdx.x; ft < n_ft; ft += gridDim.x) {
-            const int f = ft * RO_BK + lc;
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < RO_BM; r += 8) {
-                int b = b0 + r + lr;
-                pvs[(r + lr) * RO_PITCH + lc] = (b < B && f < F) ? __ldg(pv + (size_t)b * F + f) : 0.f;
-            }
-#pragma unroll
-            for (int r = 0; r < 16 * KJ; r += 8) {
-                int k = r + lr;
-                float v = 0.f;
-                if (f < F && k < Ktot) v = k < K ? __ldg(wo + (size_t)k * F + f) : __ldg(wout + (size_t)(k - K) * F + f);
-                wos[k * RO_PITCH + lc] = v;
+        int ft = blockIdx.x, stage = 0;
+        if (ft < n_ft) issue(0, ft, b0);
+        for (; ft < n_ft; ft += gridDim.x, stage ^= 1) {
+            const int nxt = ft + gridDim.x;
+            if (nxt < n_ft) {
+                issue(stage ^ 1, nxt, b0);
+                asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             }
             __syncthreads();
-#pragma unroll
+            const float *pvs = ro_smem + stage * STAGE;
+            const float *wos = pvs + RO_BM * RO_PITCH;
+#pragma unroll 4
             for (int f4 = 0; f4 < RO_BK; f4 += 4) {
                 float4 a[4], w[KJ];
 #pragma unroll
@@ -72,6 +119,7 @@ __global__ void __launch_bounds__(256, 4) readout_fwd_kernel(const float *__rest
                         acc[i][j] = fmaf(a[i].w, w[j].w, acc[i][j]);
                     }
             }
+            __syncthreads();   // everyone is done with this stage before it is refilled two iterations later
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -177,12 +225,13 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(const float *__restric
         }
         __syncthreads();
         if (fok) {
-            for (int bb = 0; bb < nb; bb += 4) {
-                float pvv[4];
+            constexpr int UB = 8;   // samples in flight per thread
+            for (int bb = 0; bb < nb; bb += UB) {
+                float pvv[UB];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) pvv[u] = (bb + u < nb) ? __ldg(pv + (size_t)(b0 + bb + u) * F + f) : 0.f;
+                for (int u = 0; u < UB; ++u) pvv[u] = (bb + u < nb) ? __ldg(pv + (size_t)(b0 + bb + u) * F + f) : 0.f;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < UB; ++u) {
                     if (bb + u >= nb) break;
                     float s = 0.f;
 #pragma unroll
@@ -267,10 +316,25 @@ int launch_readout_fwd(const dcll_conv_layer *L, const float *target, int loss_k
     float *g_o = (float *)(base + ws.off_go), *g_o2 = (float *)(base + ws.off_go2);
     const int kj = ceil_div(g.Ktot, 16);
     DCLL_REQUIRE(kj >= 1 && kj <= 4, DCLL_EUNSUPPORTED, "read-out width %d > 64 unsupported", g.Ktot);
-#define RO_CASE(J)                                                                                                   \
-    case J:                                                                                                          \
-        readout_fwd_kernel<J><<<ws.n_ro, 256, 0, st>>>(L->pv, L->wo, L->wout, L->B, g.F, L->K, g.Ktot, partial);     \
-        break;
+    const bool vec = (g.F % 4 == 0) && (((uintptr_t)L->pv | (uintptr_t)L->wo | (uintptr_t)L->wout) % 16 == 0);
+    static bool configured = false;
+    if (!configured) {
+#define RO_CFG(J)                                                                                                         \
+    DCLL_CUDA_OK(cudaFuncSetAttribute(readout_fwd_kernel<J, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                      (int)(2 * (RO_BM + 16 * J) * RO_PITCH * sizeof(float))));                           \
+    DCLL_CUDA_OK(cudaFuncSetAttribute(readout_fwd_kernel<J, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                      (int)(2 * (RO_BM + 16 * J) * RO_PITCH * sizeof(float))));
+        RO_CFG(1) RO_CFG(2) RO_CFG(3) RO_CFG(4)
+#undef RO_CFG
+        configured = true;
+    }
+#define RO_CASE(J)                                                                                                        \
+    case J: {                                                                                                             \
+        size_t sm = 2 * (RO_BM + 16 * J) * RO_PITCH * sizeof(float);                                                      \
+        if (vec) readout_fwd_kernel<J, true><<<ws.n_ro, 256, sm, st>>>(L->pv, L->wo, L->wout, L->B, g.F, L->K, g.Ktot, partial); \
+        else readout_fwd_kernel<J, false><<<ws.n_ro, 256, sm, st>>>(L->pv, L->wo, L->wout, L->B, g.F, L->K, g.Ktot, partial);    \
+        break;                                                                                                            \
+    }
     switch (kj) { RO_CASE(1) RO_CASE(2) RO_CASE(3) RO_CASE(4) }
 #undef RO_CASE
     DCLL_LAUNCH_OK("readout_fwd_kernel");
