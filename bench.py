@@ -158,7 +158,7 @@ def run_reference(a):
     vals = []
     big = res >= 64
     for i in range(a.warmup + a.steps):
-        v, desc, _, extra = cpu_port_sample(a.workload, a.timesteps, n_fwd=1, n_train=1 if big else 4)
+        v, desc, _, extra = cpu_port_sample(a.workload, a.timesteps, n_fwd=2 if big else 8, n_train=6 if big else 64)
         if i >= a.warmup:
             vals.append(v)
     v = sum(vals) / len(vals)
@@ -322,7 +322,9 @@ def run_b200(a):
            "gpu_launches": launches, "roofline": roofline, "kernel_ms": per_class, "clocks": clocks}
     if world == 1 and not a.no_cpu:
         big = res >= 64
-        v, desc, spent, extra = cpu_port_sample(a.workload, T, n_fwd=2, n_train=2 if big else 16, reps=1 if big else 2)
+        # ~10-20 s of CPU work on the bounded sample (16 host cores: ~0.45 s / 0.67 s per 128x128 timestep)
+        v, desc, spent, extra = cpu_port_sample(a.workload, T, n_fwd=4 if big else 16, n_train=12 if big else 256,
+                                                reps=1 if big else 3)
         out["cpu_baseline"] = {"value": v, "unit": "windows/s", "cores": torch.get_num_threads(), "kind": "port",
                                "sample": desc, "seconds": spent, **extra}
     print(json.dumps(out))
