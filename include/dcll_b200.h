@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DCLL_ABI_VERSION 4
+#define DCLL_ABI_VERSION 5
 
 enum { DCLL_OK = 0, DCLL_EINVAL = -1, DCLL_ECUDA = -2, DCLL_EUNSUPPORTED = -3 };
 
@@ -63,11 +63,16 @@ typedef struct dcll_conv_layer {
     int32_t cur;                     /* which half of eps0/eps1 holds the current state;
                                         flipped by every forward step                        */
     int32_t write_pvmem;             /* materialise the membrane tensor (API path) or skip   */
+    int32_t quantized;               /* 1: the convolution uses the int8 quantise->dequantise image of `weight`
+                                        (per-output-channel symmetric, oracle/quant.py); `weight` stays the
+                                        float32 master that Adam updates (straight-through)                */
     float alpharp, wrp;              /* wrp > 0: refractory variant                          */
     const float *alpha, *alphas, *tau_m, *tau_s; /* device                                   */
     float *weight;                   /* device [Cout,Cin,KH,KW]  (the nn.Parameter)          */
     float *weight_t;                 /* device [Cin,KH*KW,CoutPad] kernel-side copy,
-                                        CoutPad = 32*ceil(Cout/32); dcll_conv_sync_weights   */
+                                        CoutPad = 32*ceil(Cout/32); dcll_conv_sync_weights.
+                                        With quantized && weight_mma the allocation must hold
+                                        Cout*Cin*KH*KW more floats (dense dequantised copy)   */
     void *weight_mma;                /* device bf16 [KH*KW][Cin/8][2][Cout][8]: {hi,lo} split weights in the
                                         tcgen05 B-operand layout; required when precision is
                                         DCLL_PREC_BF16X3, refreshed together with weight_t       */

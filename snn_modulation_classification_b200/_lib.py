@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdcll_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 OK, EINVAL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3
 COEF_SCALAR, COEF_CHANNEL, COEF_ELEMENT = 0, 1, 2
@@ -30,7 +30,7 @@ class ConvLayer(C.Structure):
                 ("Cout", C.c_int32), ("KH", C.c_int32), ("KW", C.c_int32), ("padH", C.c_int32), ("padW", C.c_int32),
                 ("poolH", C.c_int32), ("poolW", C.c_int32), ("K", C.c_int32), ("output_layer", C.c_int32),
                 ("coef_mode", C.c_int32), ("x_mode", C.c_int32), ("precision", C.c_int32), ("cur", C.c_int32),
-                ("write_pvmem", C.c_int32), ("alpharp", C.c_float), ("wrp", C.c_float),
+                ("write_pvmem", C.c_int32), ("quantized", C.c_int32), ("alpharp", C.c_float), ("wrp", C.c_float),
                 ("alpha", _fp), ("alphas", _fp), ("tau_m", _fp), ("tau_s", _fp),
                 ("weight", _fp), ("weight_t", _fp), ("weight_mma", _fp), ("bias", _fp), ("wo", _fp), ("bo", _fp),
                 ("wout", _fp), ("bout", _fp),

@@ -85,6 +85,7 @@ WsLayout ws_layout(const dcll_conv_layer *L);
 int launch_conv_fwd(const dcll_conv_layer *L, const void *x, cudaStream_t st);
 int launch_conv_fwd_tc(const dcll_conv_layer *L, const void *x, cudaStream_t st);   // tcgen05, split-bf16 x3
 int launch_weight_mma(const dcll_conv_layer *L, const float *w, cudaStream_t st);
+int sync_kernel_weights(const dcll_conv_layer *L, cudaStream_t st);   // weight -> weight_t / weight_mma (quantised or not)
 bool tc_supported(const dcll_conv_layer *L);
 int launch_readout_fwd(const dcll_conv_layer *L, const float *target, int loss_kind, int32_t *clout,
                        float *loss_out, cudaStream_t st);

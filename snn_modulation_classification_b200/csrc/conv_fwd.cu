@@ -328,6 +328,36 @@ __global__ void weight_transpose_kernel(const float *__restrict__ w, float *__re
     wt[i] = co < Cout ? w[(size_t)co * CinKK + r] : 0.f;
 }
 
+// Quantised-weight mode: one CTA per output channel computes s = max|w|/127 (1 if the row is zero) and writes the
+// dequantised row clamp(rint(w/s),-127,127)*s into the kernel-side layout [Cin*KH*KW, CoutPad] (and, through
+// `deq`, a dense [Cout, Cin*KH*KW] copy that feeds the tensor-core weight split).
+__global__ void __launch_bounds__(256) weight_fakequant_transpose_kernel(const float *__restrict__ w, float *__restrict__ wt,
+                                                                         float *__restrict__ deq, int CoutPad, int CinKK) {
+    __shared__ float red[8];
+    __shared__ float s_scale;
+    const int co = blockIdx.x;
+    const float *row = w + (size_t)co * CinKK;
+    float m = 0.f;
+    for (int i = threadIdx.x; i < CinKK; i += 256) m = fmaxf(m, fabsf(row[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mm = 0.f;
+        for (int i = 0; i < 8; ++i) mm = fmaxf(mm, red[i]);
+        s_scale = mm > 0.f ? __fdiv_rn(mm, 127.f) : 1.f;
+    }
+    __syncthreads();
+    const float s = s_scale;
+    for (int i = threadIdx.x; i < CinKK; i += 256) {
+        float q = fminf(fmaxf(rintf(__fdiv_rn(row[i], s)), -127.f), 127.f);
+        float v = __fmul_rn(q, s);
+        wt[(size_t)i * CoutPad + co] = v;
+        if (deq) deq[(size_t)co * CinKK + i] = v;
+    }
+}
+
 template <int KH, int KW, int TH, int SEGS, int CI_T, int PH, int PW>
 static int launch_inst(const FwdP &p, int B, cudaStream_t st) {
     int ncog = min(4, ceil_div(p.Cout, 8));
@@ -359,6 +389,27 @@ static int launch_pool(FwdP &p, int B, int PH, int PW, cudaStream_t st) {
     }
     set_error("pooling (%d,%d) with kernel (%d,%d) has no sm_100a instantiation", PH, PW, KH, KW);
     return DCLL_EUNSUPPORTED;
+}
+
+// weight -> weight_t (and weight_mma): plain transpose, or the int8 quantise->dequantise image in quantised mode.
+// Called after every weight change (Adam step, load_state_dict).
+int sync_kernel_weights(const dcll_conv_layer *L, cudaStream_t st) {
+    Geo g = geo_of(L);
+    const int cinkk = L->Cin * L->KH * L->KW;
+    if (L->quantized) {
+        // the dequantised dense copy for the tensor-core split lives at the tail of weight_t's allocation
+        float *deq = L->weight_mma ? L->weight_t + (size_t)cinkk * g.CoutPad : nullptr;
+        if (g.CoutPad > L->Cout) DCLL_CUDA_OK(cudaMemsetAsync(L->weight_t, 0, sizeof(float) * (size_t)cinkk * g.CoutPad, st));
+        weight_fakequant_transpose_kernel<<<L->Cout, 256, 0, st>>>(L->weight, L->weight_t, deq, g.CoutPad, cinkk);
+        DCLL_LAUNCH_OK("weight_fakequant_transpose_kernel");
+        if (L->weight_mma) return launch_weight_mma(L, deq, st);
+        return DCLL_OK;
+    }
+    const int n = cinkk * g.CoutPad;
+    weight_transpose_kernel<<<ceil_div(n, 256), 256, 0, st>>>(L->weight, L->weight_t, L->Cout, g.CoutPad, cinkk);
+    DCLL_LAUNCH_OK("weight_transpose_kernel");
+    if (L->weight_mma) return launch_weight_mma(L, L->weight, st);
+    return DCLL_OK;
 }
 
 int launch_conv_fwd(const dcll_conv_layer *L, const void *x, cudaStream_t st) {
@@ -394,12 +445,5 @@ using namespace dcll;
 
 extern "C" __attribute__((visibility("default"))) int dcll_conv_sync_weights(const dcll_conv_layer *L, void *stream) {
     DCLL_REQUIRE(L && L->weight && L->weight_t, DCLL_EINVAL, "dcll_conv_sync_weights: null pointer");
-    Geo g = geo_of(L);
-    int cinkk = L->Cin * L->KH * L->KW;
-    int n = cinkk * g.CoutPad;
-    weight_transpose_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(L->weight, L->weight_t, L->Cout,
-                                                                                g.CoutPad, cinkk);
-    DCLL_LAUNCH_OK("weight_transpose_kernel");
-    if (L->weight_mma) return launch_weight_mma(L, L->weight, (cudaStream_t)stream);
-    return DCLL_OK;
+    return sync_kernel_weights(L, (cudaStream_t)stream);
 }

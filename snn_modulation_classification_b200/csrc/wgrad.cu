@@ -291,7 +291,11 @@ int launch_wgrad(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st) 
                                                                o.m_w, o.v_w, o.m_b, o.v_b, a->grad_w, a->grad_b,
                                                                a->apply_update, sc);
     DCLL_LAUNCH_OK("reduce_adam_kernel");
-    if (L->weight_mma && a->apply_update) return launch_weight_mma(L, L->weight, st);
+    if (a->apply_update) {
+        // reduce_adam_kernel already refreshed weight_t; the quantised image and the tensor-core split need a pass
+        if (L->quantized) return sync_kernel_weights(L, st);
+        if (L->weight_mma) return launch_weight_mma(L, L->weight, st);
+    }
     return DCLL_OK;
 }
 

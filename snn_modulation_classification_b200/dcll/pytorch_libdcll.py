@@ -310,33 +310,28 @@ class ContinuousConv2D(nn.Module):
                             .format(st.eps0.shape[0], x.shape[0]))
             self.init_state(x.shape[0], x.shape[2:4])
 
-    def effective_weight(self):
-        """Weights the convolution uses: the fp32 parameter, or its int8 quantise->dequantise image."""
-        if not self.quantized:
-            return self.weight.detach()
-        from ..quant import fake_quantize
-        return fake_quantize(self.weight.detach())
-
     def _sync_weight_t(self, desc):
+        """Kernel-side weight copies: weight_t [Cin*KH*KW, CoutPad] (+ a dense dequantised copy behind it in
+        quantised mode) and, for the tensor-core kernels, weight_mma.  Refreshed by the library after its own Adam
+        steps; refreshed here when Python changed the parameter (load_state_dict, foreign optimiser, mode switch)."""
         w = self.weight
-        key = (w.data_ptr(), w._version, self.quantized)
+        key = (w.data_ptr(), w._version, self.quantized, self.precision)
         cout_pad = (self.out_channels + 31) // 32 * 32
-        n = self.in_channels * self.kernel_size[0] * self.kernel_size[1] * cout_pad
+        cinkk = self.in_channels * self.kernel_size[0] * self.kernel_size[1]
+        n = cinkk * cout_pad + w.numel()
         if self._wt is None or self._wt.numel() != n or self._wt.device != w.device:
-            self._wt = torch.empty(n, dtype=torch.float32, device=w.device)
+            self._wt = torch.zeros(n, dtype=torch.float32, device=w.device)
             self._wt_key = None
         desc.weight_t = _lib.ptr(self._wt)
+        desc.quantized = 1 if self.quantized else 0
         if self.tensor_core_ok():
             n_mma = 2 * self.weight.numel()
             if self._wmma is None or self._wmma.numel() != n_mma or self._wmma.device != w.device:
                 self._wmma = torch.empty(n_mma, dtype=torch.bfloat16, device=w.device)
                 self._wt_key = None
             desc.weight_mma = _lib.ptr(self._wmma)
-        if self._wt_key != key or self.quantized:
-            src = self.effective_weight().contiguous()
-            desc.weight = _lib.ptr(src)
+        if self._wt_key != key:
             _lib.check(_lib.lib.dcll_conv_sync_weights(ctypes.byref(desc), _lib.current_stream()))
-            desc.weight = _lib.ptr(w.data)
             self._wt_key = key
 
     def tensor_core_ok(self):

@@ -53,3 +53,40 @@ def test_quantized_forward_matches_oracle_with_dequantized_weights():
     for i, s in enumerate(net.dcll_slices):
         assert torch.equal(s.dclllayer.i2h.state.eps1.cpu(), onet.states[i].eps1)
         assert rel_err(s.dclllayer._ctx[1]["pvmem"], onet.last[i].pvmem) <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_quantized_training_window_equals_per_step_and_uses_requantized_weights(precision):
+    """Quantised mode inside the C window driver: after every Adam step the library re-derives the int8 image of
+    the updated float32 master weights (straight-through training, oracle/quant.py)."""
+    from snn_modulation_classification_b200 import quant
+    from snn_modulation_classification_b200.data.utils import iq2spiketrain
+    from oracle import dcll_oracle as O
+    from util_build import build_pair
+    B, K, T, W, burnin = 8, 24, 8, 16, 3
+    nets = []
+    for _ in range(2):
+        n, _ = build_pair("radio_ml_conv", (1, W, W), B, K, arp=0.0, burnin=burnin)
+        n.set_precision(precision)
+        nets.append(quant.enable_quantized_weights(n))
+    g = torch.Generator().manual_seed(4)
+    xs = (torch.randn(B, 2, 1, 1024, generator=g) * 0.4).float()
+    y = O.to_one_hot(torch.randint(0, K, (B,), generator=g), K).cuda()
+    np.random.seed(1)
+    cells, tgt = iq2spiketrain(xs, y, out_w=W, out_h=W, max_duration=T, as_cells=True)
+    for n in nets:
+        n.reset()
+    for t in range(T):
+        nets[0].learn(cells[t], tgt[t])
+    nets[1].learn_window(cells, y)
+    for a, b in zip(nets[0].dcll_slices, nets[1].dcll_slices):
+        ia, ib = a.dclllayer.i2h, b.dclllayer.i2h
+        assert torch.equal(ia.weight, ib.weight) and torch.equal(ia.state.eps1, ib.state.eps1)
+        # kernel-side weights = transpose of the fake-quantised master weights, bit for bit
+        cinkk = ib.weight[0].numel()
+        cout_pad = (ib.out_channels + 31) // 32 * 32
+        wt = ib._wt[:cinkk * cout_pad].view(cinkk, cout_pad)[:, :ib.out_channels].t().cpu().numpy()
+        want = Q.fake_quantize(ib.weight.detach().cpu().numpy()).reshape(ib.out_channels, cinkk)
+        assert np.array_equal(wt, want)
+        assert not np.array_equal(want, ib.weight.detach().cpu().numpy().reshape(ib.out_channels, cinkk))
