@@ -11,65 +11,20 @@
 //   (row pitch = 4 x channel-group pitch) the M index (dy, ci/8) has ONE uniform stride, so a single MN-major
 //   no-swizzle descriptor addresses four kernel rows at once; the kernel column kw is a 16-byte start-address shift.
 // * N = 32 output channels, K = 16 consecutive columns of one output row per MMA; G staged as [co/8][row][col][8 co].
-// * 2 x 7 accumulators of 128 x 32 fp32 = 448 of the 512 TMEM columns (the 8th kernel row of group 1 is padding).
-// * bf16 hi/lo split of both operands, three MMAs per product (hi*hi + lo*hi + hi*lo), FP32 accumulation.
+// * bf16 hi/lo split of both operands, products hi*hi + lo*hi + hi*lo, FP32 accumulation.  As in the forward kernel an
+//   N = 32 MMA is bound by re-reading its A tile from shared memory, so [G_hi | G_lo] are ONE operand with N = 64
+//   (X_hi is read once for two products) and X_lo x G_hi is the second MMA.  64-column accumulators x 7 kernel columns
+//   = 448 of the 512 TMEM columns per kernel-row group, hence a CTA owns ONE group (g = blockIdx & 1; the 8th kernel
+//   row of group 1 is padding) and CTA pairs walk the same tiles.
 // * Persistent and warp-specialised: 12 loader warps fill one half of a double buffer with the next (eps1, g_u) tile while
 //   one elected lane issues the 672 MMAs of the current tile; mbarriers (full: loader arrivals, empty: tcgen05.commit).
 // Partials (one per CTA) are reduced in fixed order by reduce_adam_kernel, exactly like the FP32 path.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace dcll {
-
-namespace wtc {
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-}  // namespace wtc
 
 struct WgTcP {
     const float *g_u;   // [B,32,Hc,Wc]
@@ -87,10 +42,11 @@ struct WgTcGeoT {
     static constexpr int KH = 7, KW = 7, CIN = CIN_, COUT = 32;
     static constexpr int TH = 16, TW = 16;                   // one 16-column K chunk per output row
     static constexpr int CGR = CIN == 32 ? 4 : 1;            // channel groups per halo row
-    static constexpr int NG = CIN == 32 ? 2 : 1;             // kernel-row groups
+    static constexpr int NG = CIN == 32 ? 2 : 1;             // kernel-row groups; a CTA handles ONE (g = blockIdx & 1)
     static constexpr int DY = 128 / (CGR * 8);               // kernel rows per group (incl. padding)
-    static constexpr int NACC = NG * KW;                     // accumulators of 128 x 32 fp32
-    static constexpr int XROWS = TH + NG * DY - 1;
+    static constexpr int NACC = KW;                          // accumulators per CTA, each 128 x ACC_COLS fp32
+    static constexpr int ACC_COLS = 2 * COUT;                // [X_hi*G_hi + X_lo*G_hi | X_hi*G_lo], summed when draining
+    static constexpr int XROWS = TH + DY - 1;
     static constexpr int XCOLS = TW + KW - 1;                // 22
     static constexpr int X_CP = XCOLS * 16;                  // channel-group pitch (bytes)
     static constexpr int X_RP = CGR * X_CP;                  // halo-row pitch
@@ -101,20 +57,17 @@ struct WgTcGeoT {
     static constexpr int NT = 512;
     static constexpr int LOADER_WARPS = 12;                  // warps 4..15
     static constexpr int SMEM = 2 * BUF + 128 + 16 * 8 * 4;
-    static constexpr int TMEM_COLS = NACC * COUT <= 256 ? 256 : 512;
+    static constexpr int TMEM_COLS = NACC * ACC_COLS <= 256 ? 256 : 512;
+    static_assert(G_PART == 4 * G_PLANE, "{hi,lo} x channel-group must be uniformly strided for the N = 2*Cout operand");
     static_assert(CIN == 32 || CIN == 1, "instantiated for 32 and 1 input channels");
 };
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(wtc::smem_u32(bar)) : "memory");
-}
 
 // Persistent, warp-specialised: warps 4..15 stage (eps1, g_u) tiles of unit i+1 into the free half of a double buffer
 // while the elected lane of warp 0 issues the MMAs of unit i; tcgen05.commit hands buffers back to the loaders.
 template <int CIN_>
 __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
     using G = WgTcGeoT<CIN_>;
-    using namespace wtc;
+    using namespace tc;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * G::BUF);
     uint64_t *full = bars, *empty = bars + 2, *done = bars + 4;
@@ -125,18 +78,22 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) mbar_init(full + i, G::LOADER_WARPS), mbar_init(empty + i, 1);
         mbar_init(done, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)G::TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        tmem_alloc(tmem_slot, (uint32_t)G::TMEM_COLS);
     }
-    tc_fence_before();
+    fence_before();
     __syncthreads();
-    tc_fence_after();
+    fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int tiles = p.tiles_h * p.tiles_w;
+    // CTA pairs (2k, 2k+1) walk the same units; each CTA accumulates one kernel-row group
+    const int grp = G::NG == 2 ? (blockIdx.x & 1) : 0;
+    const int u_first = G::NG == 2 ? (blockIdx.x >> 1) : blockIdx.x;
+    const int u_step = G::NG == 2 ? (gridDim.x >> 1) : gridDim.x;
+    const int row_off = G::DY * grp;                          // first halo row of this group relative to the tile's halo
     float gsum[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) gsum[k] = 0.f;
@@ -149,7 +106,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
         const int l96 = ((warp >> 2) - 1) * 32 + lane;   // 0..95 within the group
         const size_t xcs = (size_t)p.H * p.W, gcs = (size_t)p.Hc * p.Wc;
         int i = 0;
-        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+        for (int u = u_first; u < p.n_units; u += u_step, ++i) {
             const int buf = i & 1;
             unsigned char *sX = smem + buf * G::BUF, *sG = sX + G::X_BYTES;
             const int b = u / tiles;
@@ -167,7 +124,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
                     for (int h = 0; h < 2; ++h) {
                         const int itt = it + h * 96;
                         r_[h] = itt / G::XCOLS, c_[h] = itt - r_[h] * G::XCOLS;
-                        const int gh = h0 - p.padH + r_[h], gw = w0 - p.padW + c_[h];
+                        const int gh = h0 - p.padH + row_off + r_[h], gw = w0 - p.padW + c_[h];
                         const bool ok = itt < G::XROWS * G::XCOLS && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W;
                         const size_t off = ok ? ((size_t)(b * G::CIN + cgw * 8) * p.H + gh) * p.W + gw : 0;
 #pragma unroll
@@ -222,7 +179,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
                     __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        gsum[k] += v[h][k];
+                        if (grp == 0) gsum[k] += v[h][k];
                         hi[k] = __float2bfloat16_rn(v[h][k]);
                         lo[k] = __float2bfloat16_rn(v[h][k] - __bfloat162float(hi[k]));
                     }
@@ -231,76 +188,69 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
                     *reinterpret_cast<uint4 *>(dst + G::G_PART) = *reinterpret_cast<const uint4 *>(lo);
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's smem writes -> async proxy
+            fence_async_smem();   // this thread's smem writes -> async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(full + buf);
         }
     } else if (warp == 0) {
         // ================= MMA issuer =================
         // a_major = b_major = MN (bits 15,16), bf16 x bf16 -> f32, N = 32, M = 128
-        constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(G::COUT >> 3) << 17) |
-                                   ((uint32_t)(128 >> 4) << 24);
-        constexpr uint32_t A_HI = (G::X_CP >> 4) | (1u << 14);         // SBO: next 8 rows of M = next (dy, cg) group
-        constexpr uint32_t B_HI = (G::G_PLANE >> 4) | (1u << 14);      // SBO: next 8 output channels
-        constexpr uint32_t LBO = (128u >> 4) << 16;                    // next 8 positions (K)
-        uint32_t elected;
-        asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(elected));
+        constexpr uint32_t IDESC_N2 = idesc_bf16(128, 2 * G::COUT, true, true);   // X_hi x [G_hi | G_lo]
+        constexpr uint32_t IDESC_N1 = idesc_bf16(128, G::COUT, true, true);       // X_lo x G_hi
+        constexpr uint32_t A_HI = desc_hi(G::X_CP);          // SBO: next 8 rows of M = next (dy, cg) group
+        constexpr uint32_t B_HI = desc_hi(G::G_PLANE);       // SBO: next 8 columns of N = next ({hi,lo}, co/8) group
+        const uint32_t elected = elect_one();
         int i = 0;
-        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+        for (int u = u_first; u < p.n_units; u += u_step, ++i) {
             const int buf = i & 1;
             const int tile = u % tiles;
             const int h0 = (tile / p.tiles_w) * G::TH;
             const int rows = min(G::TH, p.Hc - h0);
-            const uint32_t a_base = (smem_u32(smem + buf * G::BUF) >> 4) | LBO;
-            const uint32_t b_base = (smem_u32(smem + buf * G::BUF + G::X_BYTES) >> 4) | LBO;
+            const uint32_t a_base = desc_lo(smem_u32(smem + buf * G::BUF), 128);               // LBO: next 8 positions (K)
+            const uint32_t b_base = desc_lo(smem_u32(smem + buf * G::BUF + G::X_BYTES), 128);
             mbar_wait(full + buf, (i >> 1) & 1);
-            tc_fence_after();
+            fence_after();
             if (elected) {
                 for (int r = 0; r < rows; ++r) {
-                    const uint32_t b_lo0 = b_base + r * G::TW;
-                    const uint64_t b_hi = ((uint64_t)B_HI << 32) | b_lo0;
-                    const uint64_t b_lo = ((uint64_t)B_HI << 32) | (b_lo0 + (G::G_PART >> 4));
+                    const uint64_t b = desc(B_HI, b_base + r * G::TW);
                     const uint32_t acc = (i == 0 && r == 0) ? 0u : 1u;
 #pragma unroll
-                    for (int g = 0; g < G::NG; ++g) {
-#pragma unroll
-                        for (int kw = 0; kw < G::KW; ++kw) {
-                            const uint32_t a_lo0 = a_base + (((r + G::DY * g) * G::X_RP) >> 4) + kw;
-                            const uint64_t a_hi = ((uint64_t)A_HI << 32) | a_lo0;
-                            const uint64_t a_lo = ((uint64_t)A_HI << 32) | (a_lo0 + (G::X_PART >> 4));
-                            const uint32_t d = tmem_base + (g * G::KW + kw) * G::COUT;
-                            tc_mma_bf16(d, a_hi, b_hi, IDESC, acc);
-                            tc_mma_bf16(d, a_lo, b_hi, IDESC, 1);
-                            tc_mma_bf16(d, a_hi, b_lo, IDESC, 1);
-                        }
+                    for (int kw = 0; kw < G::KW; ++kw) {
+                        const uint32_t a_lo0 = a_base + ((r * G::X_RP) >> 4) + kw;
+                        const uint32_t d = tmem_base + kw * G::ACC_COLS;
+                        mma_bf16(d, desc(A_HI, a_lo0), b, IDESC_N2, acc);
+                        mma_bf16(d, desc(A_HI, a_lo0 + (G::X_PART >> 4)), b, IDESC_N1, 1);
                     }
                 }
-                tc_commit(empty + buf);
+                commit(empty + buf);
             }
             __syncwarp();
         }
-        if (elected) tc_commit(done);
+        if (elected) commit(done);
         __syncwarp();
     }
-    // ---- drain: every MMA of this CTA has completed when `done` flips
+    // ---- drain: zero this CTA's partial (the other group's kernel rows stay zero), then, once every MMA has completed
+    //      (`done` flips), add the two accumulator halves and scatter into the [Cout,Cin,KH,KW] layout
     float *out = p.partial + (size_t)blockIdx.x * p.n_tot;
+    for (int i = tid; i < p.n_tot; i += G::NT) out[i] = 0.f;
+    __syncthreads();
     mbar_wait(done, 0);
-    tc_fence_after();
+    fence_after();
     {
         const int q = warp & 3;                                          // TMEM lane quarter of this warp
         const int m = q * 32 + lane;                                     // (dy, ci) resp. (dy, c8)
         const int dy = G::CIN == 32 ? (m >> 5) : (m >> 3);
         const int ci = G::CIN == 32 ? (m & 31) : 0;
         const bool lane_ok = G::CIN == 32 ? true : ((m & 7) == 0);
-        for (int a = (warp >> 2); a < G::NACC; a += 4) {
-            const int g = a / G::KW, kw = a - g * G::KW;
-            const int kh = G::DY * g + dy;
-            uint32_t v[32];
-            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::COUT, v);
+        const int kh = G::DY * grp + dy;
+        for (int kw = (warp >> 2); kw < G::KW; kw += 4) {
+            uint32_t v[32], v2[32];
+            ld32(tmem_base + ((uint32_t)(q * 32) << 16) + kw * G::ACC_COLS, v);
+            ld32(tmem_base + ((uint32_t)(q * 32) << 16) + kw * G::ACC_COLS + G::COUT, v2);
             if (kh < G::KH && lane_ok) {
 #pragma unroll
                 for (int co = 0; co < 32; ++co)
-                    out[((size_t)(co * G::CIN + ci) * G::KH + kh) * G::KW + kw] = __uint_as_float(v[co]);
+                    out[((size_t)(co * G::CIN + ci) * G::KH + kh) * G::KW + kw] = __uint_as_float(v[co]) + __uint_as_float(v2[co]);
             }
         }
     }
@@ -312,16 +262,16 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) bias_red[warp * 8 + k] = s;
     }
-    tc_fence_before();
+    fence_before();
     __syncthreads();
     if (tid < 32) {
         const int cog = tid >> 3, k = tid & 7;                            // loader warps with (warp & 3) == cog staged this group
         float s = 0.f;
         for (int w = 4 + cog; w < 16; w += 4) s += bias_red[w * 8 + k];
-        out[p.nW + tid] = s;
+        if (grp == 0) out[p.nW + tid] = s;
     }
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)G::TMEM_COLS) : "memory");
+        tmem_dealloc(tmem_base, (uint32_t)G::TMEM_COLS);
     }
 }
 
@@ -333,6 +283,7 @@ bool wgrad_tc_supported(const dcll_conv_layer *L) {
 int wgrad_tc_splits(const dcll_conv_layer *L) {
     Geo g = geo_of(L);
     int n_units = L->B * ceil_div(g.Hc, 16) * ceil_div(g.Wc, 16);
+    if (L->Cin == 32) return 2 * (n_units < 74 ? n_units : 74);   // CTA pairs: one kernel-row group each
     return n_units < 148 ? n_units : 148;
 }
 
