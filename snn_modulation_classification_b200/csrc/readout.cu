@@ -273,6 +273,77 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(const float *__restric
     }
 }
 
+// output_ gradient + Adam alone, for small feature counts (16x16 planes: F = 8192), where the fused sweep above would
+// leave each thread with a serial loop over the whole batch.  CTA = 32 features x 8 batch slices (one warp each, so the
+// pv loads are 128-byte coalesced and g_o2 is a warp-broadcast load) x KG outputs (grid.y); fixed-order reduction of the
+// 8 slices through shared memory, then Adam.
+template <int KG>
+__global__ void __launch_bounds__(256) wout_grad_adam_kernel(const float *__restrict__ pv, const float *__restrict__ g_o2, int B,
+                                                             int F, int K, float *__restrict__ wout, float *__restrict__ bout,
+                                                             float *__restrict__ m_w, float *__restrict__ v_w,
+                                                             float *__restrict__ m_b, float *__restrict__ v_b,
+                                                             float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
+                                                             AdamScalars sc) {
+    __shared__ float red[8][KG][33];
+    __shared__ float bred[8][KG];
+    const int fx = threadIdx.x & 31, bs = threadIdx.x >> 5;
+    const int f = blockIdx.x * 32 + fx;
+    const int k0 = blockIdx.y * KG;
+    const bool fok = f < F;
+    float acc[KG], bsum[KG];
+#pragma unroll
+    for (int k = 0; k < KG; ++k) acc[k] = 0.f, bsum[k] = 0.f;
+    for (int b = bs; b < B; b += 8 * 4) {
+        float pvv[4], g[4][KG];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int bb = b + 8 * u;
+            pvv[u] = (bb < B && fok) ? __ldg(pv + (size_t)bb * F + f) : 0.f;
+#pragma unroll
+            for (int k = 0; k < KG; ++k) g[u][k] = (bb < B && k0 + k < K) ? __ldg(g_o2 + (size_t)bb * K + k0 + k) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < KG; ++k) acc[k] = fmaf(g[u][k], pvv[u], acc[k]), bsum[k] += g[u][k];
+    }
+#pragma unroll
+    for (int k = 0; k < KG; ++k) red[bs][k][fx] = acc[k];
+    if (fx == 0) {
+#pragma unroll
+        for (int k = 0; k < KG; ++k) bred[bs][k] = bsum[k];
+    }
+    __syncthreads();
+    if (bs == 0 && fok) {
+#pragma unroll
+        for (int k = 0; k < KG; ++k) {
+            if (k0 + k < K) {
+                float gsum = 0.f;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) gsum += red[s][k][fx];
+                size_t o = (size_t)(k0 + k) * F + f;
+                if (grad_w) grad_w[o] = gsum;
+                if (apply) {
+                    float wv = wout[o], m = m_w[o], v = v_w[o];
+                    adam_elem(wv, gsum, m, v, sc);
+                    wout[o] = wv, m_w[o] = m, v_w[o] = v;
+                }
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < KG && k0 + threadIdx.x < K) {
+        const int k = k0 + threadIdx.x;
+        float gsum = 0.f;
+        for (int s = 0; s < 8; ++s) gsum += bred[s][threadIdx.x];
+        if (grad_b) grad_b[k] = gsum;
+        if (apply) {
+            float wv = bout[k], m = m_b[k], v = v_b[k];
+            adam_elem(wv, gsum, m, v, sc);
+            bout[k] = wv, m_b[k] = m, v_b[k] = v;
+        }
+    }
+}
+
 // g_o / g_o2 from stored read-outs (layer-level API: the target is only known after forward returned)
 __global__ void loss_grad_kernel(const float *__restrict__ pvoutput, const float *__restrict__ output,
                                  const float *__restrict__ target, int B, int K, int loss_kind, float *__restrict__ g_o,
@@ -363,7 +434,17 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
     DCLL_REQUIRE(L->K <= 32, DCLL_EUNSUPPORTED, "target_size %d > 32 unsupported in the backward read-out", L->K);
     const int fblk = ceil_div(g.F, 256);
     AdamScalars sc = {};
-    if (L->output_layer) {
+    const bool fused_out = L->output_layer && fblk >= 2 * 148;   // large F: one sweep over pv serves g_u and gWout
+    if (L->output_layer && !fused_out) {
+        // small F: the output_ gradient gets its own kernel (batch split over warps inside the CTA)
+        sc = adam_scalars(a->adam_out, a->adam_out.step + 1);
+        dcll_adam &o = a->adam_out;
+        dim3 grid(ceil_div(g.F, 32), ceil_div(L->K, 8));
+        wout_grad_adam_kernel<8><<<grid, 256, 0, st>>>(L->pv, g_o2, L->B, g.F, L->K, L->wout, L->bout, o.m_w, o.v_w, o.m_b, o.v_b,
+                                                      a->grad_wout, a->grad_bout, a->apply_update, sc);
+        DCLL_LAUNCH_OK("wout_grad_adam_kernel");
+    }
+    if (fused_out) {
         // the output_ gradient reduces over the whole batch inside one thread: no batch slicing
         sc = adam_scalars(a->adam_out, a->adam_out.step + 1);
         dcll_adam &o = a->adam_out;
