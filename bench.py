@@ -170,7 +170,7 @@ def run_reference(a):
            "config": {"workload": a.workload, "timesteps": a.timesteps, "batch_per_gpu": batch, "resolution": res},
            "cpu_baseline": {"value": v, "unit": unit, "cores": torch.get_num_threads(), "kind": "port", "sample": desc},
            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit_json(out)
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -327,9 +327,41 @@ def run_b200(a):
                                                 reps=1 if big else 3)
         out["cpu_baseline"] = {"value": v, "unit": "windows/s", "cores": torch.get_num_threads(), "kind": "port",
                                "sample": desc, "seconds": spent, **extra}
-    print(json.dumps(out))
+    emit_json(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+class _StdoutGuard:
+    """Everything libraries print to fd 1 while the benchmark runs (e.g. NCCL's version banner) goes to stderr;
+    only the final JSON line reaches the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.saved, (line + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+_GUARD = None
+
+
+def emit_json(obj):
+    line = json.dumps(obj)
+    if _GUARD is not None:
+        _GUARD.emit(line)
+    else:
+        print(line, flush=True)
 
 
 def main():
@@ -350,10 +382,15 @@ def main():
         w = list(WORKLOADS[a.workload])
         w[5] = a.burnin
         WORKLOADS[a.workload] = tuple(w)
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_b200(a)
+    global _GUARD
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    with _StdoutGuard() as g:
+        _GUARD = g
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_b200(a)
+    _GUARD = None
 
 
 if __name__ == "__main__":
