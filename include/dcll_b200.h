@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DCLL_ABI_VERSION 5
+#define DCLL_ABI_VERSION 6
 
 enum { DCLL_OK = 0, DCLL_EINVAL = -1, DCLL_ECUDA = -2, DCLL_EUNSUPPORTED = -3 };
 
@@ -182,6 +182,13 @@ int dcll_dense_step_bwd_update(dcll_dense_layer *L, dcll_train_args *a, void *st
 int dcll_net_window(dcll_conv_layer *layers, dcll_train_args *train, int n_layers, const void *x0,
                     const float *target, int64_t target_t_stride, int T, int train_mode, int burnin,
                     const int32_t *iter0, int32_t *clout, void *stream);
+/* Same, plus the activity statistics of DCLLBase.forward :658-661: every `hist_every`-th iteration of slice l
+ * (iter % hist_every == 0) the 19-bin histogram of pv over [0,1] (np.histogram(pv, np.linspace(0,1,20))) is written to
+ * hist[l][n][19] (device int32, n counts the sampled iterations of the window, at most hist_cap per layer).
+ * hist == NULL or hist_every <= 0 disables it. */
+int dcll_net_window_stats(dcll_conv_layer *layers, dcll_train_args *train, int n_layers, const void *x0,
+                          const float *target, int64_t target_t_stride, int T, int train_mode, int burnin,
+                          const int32_t *iter0, int32_t *clout, int32_t *hist, int hist_every, int hist_cap, void *stream);
 
 /* -- vote: dcll/pytorch_libdcll.py:44-61 ------------------------------------------------------ *
  * pred[b] = most frequent class of clout[t0..T,b] (first-seen wins ties, as Counter does).    */

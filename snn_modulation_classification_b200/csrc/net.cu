@@ -330,10 +330,37 @@ extern "C" __attribute__((visibility("default"))) int dcll_conv_apply_update(dcl
     return dcll_conv_sync_weights(L, stream);
 }
 
-extern "C" __attribute__((visibility("default"))) int dcll_net_window(dcll_conv_layer *layers, dcll_train_args *train, int n_layers, const void *x0,
+// 19 equal bins over [0,1], last bin closed on the right (numpy.histogram with bins = linspace(0,1,20))
+__global__ void __launch_bounds__(256) activity_hist_kernel(const float *__restrict__ pv, size_t n, int32_t *__restrict__ hist) {
+    __shared__ int sh[19];
+    if (threadIdx.x < 19) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v = pv[i];
+        if (v >= 0.f && v <= 1.f) {
+            int b = (int)(v * 19.f);
+            atomicAdd(&sh[b > 18 ? 18 : b], 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 19 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+extern "C" __attribute__((visibility("default"))) int dcll_net_window(dcll_conv_layer *layers, dcll_train_args *train, int n_layers,
+                                                                       const void *x0, const float *target,
+                                                                       int64_t target_t_stride, int T, int train_mode, int burnin,
+                                                                       const int32_t *iter0, int32_t *clout, void *stream) {
+    return dcll_net_window_stats(layers, train, n_layers, x0, target, target_t_stride, T, train_mode, burnin, iter0, clout, nullptr, 0,
+                                 0, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int dcll_net_window_stats(dcll_conv_layer *layers, dcll_train_args *train, int n_layers, const void *x0,
                                const float *target, int64_t target_t_stride, int T, int train_mode, int burnin,
-                               const int32_t *iter0, int32_t *clout, void *stream) {
+                               const int32_t *iter0, int32_t *clout, int32_t *hist, int hist_every, int hist_cap, void *stream) {
     DCLL_REQUIRE(layers && n_layers > 0 && x0 && T > 0 && iter0, DCLL_EINVAL, "dcll_net_window: bad arguments");
+    DCLL_REQUIRE(!hist || (hist_every > 0 && hist_cap > 0), DCLL_EINVAL, "dcll_net_window: bad histogram arguments");
+    int hist_n[16] = {0};
+    DCLL_REQUIRE(!hist || n_layers <= 16, DCLL_EINVAL, "dcll_net_window: statistics support at most 16 layers");
     DCLL_REQUIRE(!train_mode || (train && target), DCLL_EINVAL, "dcll_net_window: training needs train args and a target");
     for (int l = 0; l < n_layers; ++l) {
         int rc = check_layer(&layers[l], "dcll_net_window");
@@ -367,6 +394,14 @@ extern "C" __attribute__((visibility("default"))) int dcll_net_window(dcll_conv_
             int32_t *co = clout ? clout + ((size_t)t * n_layers + l) * L->B : nullptr;
             int rc = step_fwd(L, x, do_train ? tgt : nullptr, do_train ? train[l].loss_kind : 0, co, nullptr, st);
             if (rc != DCLL_OK) return rc;
+            if (hist && (it % hist_every) == 0 && hist_n[l] < hist_cap) {          // DCLLBase.forward :658-661
+                Geo g = geo_of(L);
+                const size_t n = (size_t)L->B * g.F;
+                int32_t *dst = hist + ((size_t)l * hist_cap + hist_n[l]++) * 19;
+                const int blocks = (int)(n / 256 / 8 + 1 < 296 ? n / 256 / 8 + 1 : 296);
+                activity_hist_kernel<<<blocks, 256, 0, st>>>(L->pv, n, dst);
+                DCLL_LAUNCH_OK("activity_hist_kernel");
+            }
             if (do_train) {
                 rc = step_bwd(L, &train[l], st);
                 if (rc != DCLL_OK) return rc;

@@ -200,9 +200,13 @@ class ConvNetwork(torch.nn.Module):
         iter0 = (ctypes.c_int32 * n)(*[int(s.iter) for s in self.dcll_slices])
         clout = torch.empty((T, n, batch), dtype=torch.int32, device=x_t.device)
         burnin = int(self.dcll_slices[0].burnin)
-        _lib.check(_lib.lib.dcll_net_window(layers, trains if train else None, n, _lib.ptr(x_t), _lib.ptr(target),
-                                            t_stride, T, 1 if train else 0, burnin, iter0, _lib.ptr(clout),
-                                            _lib.current_stream()))
+        # activity statistics (DCLLBase.forward :658-661): 19-bin pv histogram every 20 iterations, kept on the device
+        collect = any(getattr(s, 'collect_stats', False) for s in self.dcll_slices)
+        hist_cap = T // 20 + 1
+        hist = torch.zeros((n, hist_cap, 19), dtype=torch.int32, device=x_t.device) if collect else None
+        _lib.check(_lib.lib.dcll_net_window_stats(layers, trains if train else None, n, _lib.ptr(x_t), _lib.ptr(target),
+                                                  t_stride, T, 1 if train else 0, burnin, iter0, _lib.ptr(clout),
+                                                  _lib.ptr(hist), 20 if collect else 0, hist_cap, _lib.current_stream()))
         for i, s in enumerate(self.dcll_slices):
             s.dclllayer.i2h._commit_state(*olds[i], flips=T)
             s.dclllayer._ctx = None
@@ -210,6 +214,10 @@ class ConvNetwork(torch.nn.Module):
             first = 0 if not train else max(0, int(s.burnin) - int(s.iter) - 1)
             if first < T:
                 s.clout.extend(clout[first:, i, :])
+            if collect and s.collect_stats:
+                n_h = (int(s.iter) + T) // 20 - int(s.iter) // 20        # iterations with iter % 20 == 0 in this window
+                for j in range(n_h):
+                    s.activity_hist.append(hist[i, j].float())
             s.iter += T
             if train:
                 _store_steps(states[i][0], trains[i].adam_i2h.step)

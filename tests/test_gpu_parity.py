@@ -408,3 +408,41 @@ def test_dense_layer_vs_oracle(wrp, random_tau):
     # stand-alone i2h call (ref :131-148)
     o2, pv2, vm2 = m.forward(torch.zeros(B, In, device="cuda"))
     assert o2.shape == (B, Out) and vm2.shape == (B, Out)
+
+
+def test_window_activity_histogram_matches_numpy():
+    """collect_stats in the C window driver (ref :658-661): 19-bin pv histogram every 20 iterations."""
+    net, onet = build_pair("radio_ml_conv", (1, 16, 16), 4, 24, arp=0.0, train=False)
+    g = torch.Generator().manual_seed(2)
+    x = (torch.rand(45, 4, 1, 16, 16, generator=g) < 0.1).float()
+    net.reset()
+    onet.reset()
+    net.test_window(x.cuda())
+    bins = np.linspace(0, 1, 20)
+    want = [[] for _ in range(3)]
+    for t in range(45):
+        onet.test(x[t])
+        if (t + 1) % 20 == 0:
+            for i in range(3):
+                want[i].append(np.histogram(onet.last[i].pv.numpy(), bins=bins)[0])
+    for i, s in enumerate(net.dcll_slices):
+        assert len(s.activity_hist) == 2
+        got = torch.stack(s.activity_hist).cpu().numpy()
+        # pv differs from the oracle by ~1e-7 at bin edges: compare with a tolerance of a few elements per bin
+        assert np.abs(got - np.array(want[i])).max() <= 3, (i, got, want[i])
+        assert got.sum(axis=1).tolist() == [4 * 32 * 256] * 2
+
+    class W:
+        def __init__(self):
+            self.scalars = {}
+
+        def add_histogram(self, *a, **k):
+            pass
+
+        def add_scalar(self, name, v, epoch):
+            self.scalars[name] = v
+
+    w = W()
+    net.accuracy(torch.zeros(45, 4, 24))
+    net.write_stats(w, epoch=0)
+    assert "conv0/low_pv/test" in w.scalars and "conv2/acc/test" in w.scalars
