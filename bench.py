@@ -28,7 +28,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 WORKLOADS = {
     # name: (spec, resolution, per-GPU batch, train, arp, burnin)
@@ -176,10 +175,38 @@ def run_reference(a):
 # --------------------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------------------
+def make_args(arp=0.0):
+    """train.py argparse defaults (ref train.py:75-90) as the namespace ConvNetwork reads."""
+    import types
+    return types.SimpleNamespace(netscale=1.0, alpha=0.92, alphas=0.85, alpharp=0.65, arp=arp, lc_ampl=0.5, random_tau=True)
+
+
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed `ncu --set full`
+    summary of this round (profiles/); None when the capture is absent."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_tc_v3_conv_fwd_and_wgrad.txt")
+    if not os.path.exists(path):
+        return None
+    cur, vals = None, {}
+    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+    for line in open(path):
+        parts = line.split()
+        if line.startswith("Kernel Name"):
+            cur = line
+            if kernel_substr in cur and vals.get("done"):
+                break
+        elif cur and kernel_substr in cur and parts and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            vals[parts[0]] = float(parts[1]) * scale.get(parts[2], 1.0)
+            if len(vals) == 2:
+                vals["done"] = True
+    if "dram__bytes_read.sum" in vals and "dram__bytes_write.sum" in vals:
+        return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
+    return None
+
+
 def build_net(wl):
     import numpy as np
     import torch
-    from util_build import make_args
     from snn_modulation_classification_b200 import networks as N
     spec, res, batch, train, arp, burnin = WORKLOADS[wl]
     torch.manual_seed(1)
@@ -290,7 +317,10 @@ def run_b200(a):
     roofline = {"kernel": ("conv_fwd_tc_kernel<7,7,32,32> (layer 1: 32->32 ch, tcgen05 split-bf16 x3, TMEM accumulators)" if tc
                            else "conv_fwd_kernel<7,7,...> (layer 1: 32->32 ch, FP32 FMA path)"), "bound": "tensor",
                 "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tensor"] if achieved else None, "traffic": None,
+                "frac": achieved / pk["tensor"] if achieved else None,
+                "traffic": ncu_traffic("conv_fwd_tc_kernel") if (tc and res == 128 and batch == 64) else None,
+                "traffic_unit": "bytes per launch (dram read + write, ncu --set full, profiles/r01_ncu_tc_v3_conv_fwd_and_wgrad.txt); "
+                                "algorithmic: 0.89e9",
                 "peak_source": "%s bf16 dense sustained (MEASURED_PEAKS.json)" % pk["src"],
                 "avg_launch_ms": avg_ms, "launches_sampled": c_n, "algorithmic_flops_per_launch": conv_flops,
                 "fp32_fma_peak_tflops_at_clock": fp32_peak, "frac_of_fp32_fma_peak": achieved / fp32_peak if achieved else None,

@@ -12,6 +12,8 @@
 // slice of gW in registers: thread = (4 output channels, 1 input channel, 1 kernel row) x KW taps.
 // Partials are summed in a fixed order by reduce_adam_kernel, which also applies Adam and refreshes the
 // [Cin,KH*KW,CoutPad] weight copy the forward kernel consumes -- deterministic, no float atomics.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace dcll {
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(256) reduce_adam_kernel(const float *__restric
                                                           float *__restrict__ m_w, float *__restrict__ v_w,
                                                           float *__restrict__ m_b, float *__restrict__ v_b,
                                                           float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
-                                                          AdamScalars sc) {
+                                                          AdamScalars sc, __nv_bfloat16 *__restrict__ w_mma, int Cin, int KHKW) {
     int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n_tot) return;
     float g = 0.f;
@@ -195,6 +197,14 @@ __global__ void __launch_bounds__(256) reduce_adam_kernel(const float *__restric
             w[i] = wv, m_w[i] = m, v_w[i] = v;
             int co = i / CinKK, r = i - co * CinKK;
             wt[(size_t)r * CoutPad + co] = wv;
+            if (w_mma) {   // bf16 {hi,lo} copy in the tcgen05 B-operand layout [tap][ci/8][{hi,lo}][co][8] (conv_fwd_tc.cu)
+                const int ci = r / KHKW, tap = r - ci * KHKW;
+                __nv_bfloat16 hi = __float2bfloat16_rn(wv);
+                __nv_bfloat16 lo = __float2bfloat16_rn(wv - __bfloat162float(hi));
+                size_t o = (size_t)tap * (2 * Cin * Cout) + ((size_t)(ci >> 3) * 2 * Cout + co) * 8 + (ci & 7);
+                w_mma[o] = hi;
+                w_mma[o + (size_t)Cout * 8] = lo;
+            }
         }
     } else {
         int co = i - nW;
@@ -289,13 +299,12 @@ int launch_wgrad(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st) 
     reduce_adam_kernel<<<ceil_div(p.n_tot, 256), 256, 0, st>>>(p.partial, p.S, p.n_tot, p.nW, L->Cout, g.CoutPad,
                                                                L->Cin * L->KH * L->KW, L->weight, L->weight_t, L->bias,
                                                                o.m_w, o.v_w, o.m_b, o.v_b, a->grad_w, a->grad_b,
-                                                               a->apply_update, sc);
+                                                               a->apply_update, sc,
+                                                               L->quantized ? nullptr : reinterpret_cast<__nv_bfloat16 *>(L->weight_mma),
+                                                               L->Cin, L->KH * L->KW);
     DCLL_LAUNCH_OK("reduce_adam_kernel");
-    if (a->apply_update) {
-        // reduce_adam_kernel already refreshed weight_t; the quantised image and the tensor-core split need a pass
-        if (L->quantized) return sync_kernel_weights(L, st);
-        if (L->weight_mma) return launch_weight_mma(L, L->weight, st);
-    }
+    // reduce_adam_kernel refreshed weight_t and the tensor-core split itself; only the quantised image needs a pass
+    if (a->apply_update && L->quantized) return sync_kernel_weights(L, st);
     return DCLL_OK;
 }
 
