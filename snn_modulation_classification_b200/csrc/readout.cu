@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(256, 3) readout_fwd_kernel(const float *__rest
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
 
-    for (int b0 = 0; b0 < B; b0 += RO_BM) {
+    // grid.y strides over 64-sample tiles (small F / large B: not enough feature tiles to fill the machine)
+    for (int b0 = blockIdx.y * RO_BM; b0 < B; b0 += gridDim.y * RO_BM) {
         float acc[4][KJ];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -399,11 +400,14 @@ int launch_readout_fwd(const dcll_conv_layer *L, const float *target, int loss_k
 #undef RO_CFG
         configured = true;
     }
+    // batch tiles in grid.y until the grid holds ~4 CTAs per SM
+    const int b_tiles = ceil_div(L->B, RO_BM);
+    dim3 grid(ws.n_ro, max(1, min(b_tiles, ceil_div(4 * 148, ws.n_ro))));
 #define RO_CASE(J)                                                                                                        \
     case J: {                                                                                                             \
         size_t sm = 2 * (RO_BM + 16 * J) * RO_PITCH * sizeof(float);                                                      \
-        if (vec) readout_fwd_kernel<J, true><<<ws.n_ro, 256, sm, st>>>(L->pv, L->wo, L->wout, L->B, g.F, L->K, g.Ktot, partial); \
-        else readout_fwd_kernel<J, false><<<ws.n_ro, 256, sm, st>>>(L->pv, L->wo, L->wout, L->B, g.F, L->K, g.Ktot, partial);    \
+        if (vec) readout_fwd_kernel<J, true><<<grid, 256, sm, st>>>(L->pv, L->wo, L->wout, L->B, g.F, L->K, g.Ktot, partial); \
+        else readout_fwd_kernel<J, false><<<grid, 256, sm, st>>>(L->pv, L->wo, L->wout, L->B, g.F, L->K, g.Ktot, partial);    \
         break;                                                                                                            \
     }
     switch (kj) { RO_CASE(1) RO_CASE(2) RO_CASE(3) RO_CASE(4) }
