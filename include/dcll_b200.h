@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DCLL_ABI_VERSION 6
+#define DCLL_ABI_VERSION 7
 
 enum { DCLL_OK = 0, DCLL_EINVAL = -1, DCLL_ECUDA = -2, DCLL_EUNSUPPORTED = -3 };
 
@@ -189,6 +189,16 @@ int dcll_net_window(dcll_conv_layer *layers, dcll_train_args *train, int n_layer
 int dcll_net_window_stats(dcll_conv_layer *layers, dcll_train_args *train, int n_layers, const void *x0,
                           const float *target, int64_t target_t_stride, int T, int train_mode, int burnin,
                           const int32_t *iter0, int32_t *clout, int32_t *hist, int hist_every, int hist_cap, void *stream);
+
+/* -- multi-timestep inference of the radio_ml_conv stack on a 16x16 plane (test_radio_ml.py:144-145, script geometry) -- *
+ * One launch runs Tc timesteps of the three conv cores (1->32, 32->32, 32->32; 7x7, padding 3, no pooling) with one CTA
+ * per sample: synaptic traces stay in registers, inter-layer spikes in shared memory, membranes in TMEM (tcgen05, split-bf16).
+ * cells: device int32 [Tc][B][2]; pv_out[l]: device float32 [Tc][B][32*256] (sigmoid outputs of layer l, the read-out
+ * input).  State (eps0/eps1 of the current half, arp) is read at the start and written back at the end; `cur` is not
+ * flipped.  The read-outs then run batched over Tc*B rows with dcll_conv_readout_rows (descriptor with B = Tc*B).      */
+int dcll_infer_stack16(const dcll_conv_layer *layers, int n_layers, const int32_t *cells, int Tc, float *const *pv_out,
+                       void *stream);
+int dcll_conv_readout_rows(const dcll_conv_layer *L, int32_t *clout, void *stream);
 
 /* -- vote: dcll/pytorch_libdcll.py:44-61 ------------------------------------------------------ *
  * pred[b] = most frequent class of clout[t0..T,b] (first-seen wins ties, as Counter does).    */

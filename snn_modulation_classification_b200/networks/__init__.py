@@ -302,5 +302,72 @@ class ConvNetwork(torch.nn.Module):
         return self._run_window(x, labels, True)
 
     def test_window(self, x):
-        """``for t in range(T): self.test(x[t])`` (test_radio_ml.py:144-145) in one call."""
+        """``for t in range(T): self.test(x[t])`` (test_radio_ml.py:144-145) in one call.  The radio_ml_conv stack on a
+        16x16 plane in 'bf16x3' mode with cell input takes the multi-timestep kernel (state on chip across timesteps)."""
+        if self._stack16_ok(x):
+            return self._run_stack16(x)
         return self._run_window(x, None, False)
+
+    # -- multi-timestep inference kernel (dcll_infer_stack16) -----------------------------------------
+    def _stack16_ok(self, x):
+        if not isinstance(x, SpikeCells) or self.num_layers != 3 or x.cells.dim() != 3:
+            return False
+        for i, s in enumerate(self.dcll_slices):
+            lay, i2h = s.dclllayer, s.dclllayer.i2h
+            if (tuple(int(v) for v in lay.im_dims) != (16, 16) or i2h.kernel_size != (7, 7) or i2h.padding != (3, 3)
+                    or tuple(lay.pooling) != (1, 1) or i2h.out_channels != 32 or i2h.in_channels != (1 if i == 0 else 32)
+                    or i2h.precision != 'bf16x3' or i2h.quantized or i2h.state.eps0.shape[0] != x.cells.shape[1]):
+                return False
+        return True
+
+    def _run_stack16(self, x, chunk=None):
+        n, cells = 3, x.cells
+        T, batch = int(cells.shape[0]), int(cells.shape[1])
+        dev = cells.device
+        win = self._window_buffers(batch)
+        Layers = _lib.ConvLayer * n
+        layers = Layers()
+        for i, s in enumerate(self.dcll_slices):
+            s.dclllayer._fill_desc(layers[i], batch, _lib.X_CELLS if i == 0 else _lib.X_DENSE, win['outs'][i])
+            if layers[i].coef_mode == _lib.COEF_ELEMENT:
+                return self._run_window(x, None, False)
+        fsz = 32 * 256
+        tc_max = chunk or max(1, min(16, T, int(3e9 // (3 * batch * fsz * 4))))
+        key = ('stack16', batch, tc_max, dev)
+        if getattr(self, '_s16', None) is None or self._s16['key'] != key:
+            rows = tc_max * batch
+            bufs = dict(key=key, pv=[torch.empty((rows, fsz), device=dev) for _ in range(n)], descs=[], keep=[])
+            for i, s in enumerate(self.dcll_slices):
+                lay = s.dclllayer
+                d = _lib.ConvLayer()
+                ctypes.memmove(ctypes.byref(d), ctypes.byref(layers[i]), ctypes.sizeof(d))
+                d.B = rows
+                po = torch.empty((rows, lay.target_size), device=dev)
+                out = torch.empty((rows, lay.target_size), device=dev) if lay.output_layer else None
+                d.pv, d.pvoutput, d.output = _lib.ptr(bufs['pv'][i]), _lib.ptr(po), _lib.ptr(out)
+                ws = torch.empty(_lib.lib.dcll_conv_workspace_bytes(ctypes.byref(d)), dtype=torch.uint8, device=dev)
+                d.workspace, d.workspace_bytes = _lib.ptr(ws), ws.numel()
+                bufs['descs'].append(d)
+                bufs['keep'] += [po, out, ws]
+            bufs['clrows'] = torch.empty(rows, dtype=torch.int32, device=dev)
+            self._s16 = bufs
+        s16 = self._s16
+        for i in range(n):      # parameter pointers may have moved since the buffers were built
+            d = s16['descs'][i]
+            d.wo, d.bo, d.wout, d.bout = layers[i].wo, layers[i].bo, layers[i].wout, layers[i].bout
+        pv_ptrs = (ctypes.c_void_p * n)(*[_lib.ptr(t) for t in s16['pv']])
+        clout = torch.empty((T, n, batch), dtype=torch.int32, device=dev)
+        stream = _lib.current_stream()
+        for t0 in range(0, T, tc_max):
+            tc = min(tc_max, T - t0)
+            _lib.check(_lib.lib.dcll_infer_stack16(layers, n, cells[t0].data_ptr(), tc, pv_ptrs, stream))
+            for i in range(n):
+                d = s16['descs'][i]
+                d.B = tc * batch
+                _lib.check(_lib.lib.dcll_conv_readout_rows(ctypes.byref(d), _lib.ptr(s16['clrows']), stream))
+                clout[t0:t0 + tc, i, :] = s16['clrows'][:tc * batch].view(tc, batch)
+        for i, s in enumerate(self.dcll_slices):
+            s.dclllayer._ctx = None
+            s.clout.extend(clout[:, i, :])
+            s.iter += T
+        return clout

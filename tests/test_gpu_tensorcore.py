@@ -153,3 +153,43 @@ def test_tc_window_equals_per_step_and_is_deterministic():
         assert torch.equal(b.dclllayer.i2h.weight, c.dclllayer.i2h.weight)       # run-to-run reproducible
         assert torch.equal(a.dclllayer.i2h.state.eps1, b.dclllayer.i2h.state.eps1)
         assert np.array_equal(np.array(a.clout), np.array(b.clout))
+
+
+@pytest.mark.parametrize("arp", [0.0, 1.0])
+def test_multi_timestep_stack_kernel_matches_per_step_path(arp):
+    """dcll_infer_stack16 (state in registers/shared memory/TMEM across timesteps) vs the per-timestep kernels of the
+    same precision mode: identical MMA order, so traces, state and predictions must agree (layer 0 runs a different FMA
+    order: predictions may differ on exact ties only) -- and both against the FP32 oracle within the headline bounds."""
+    from snn_modulation_classification_b200.data.utils import iq2spiketrain
+    B, K, T, W = 12, 24, 37, 16
+    a, onet = build_pair("radio_ml_conv", (1, W, W), B, K, arp=arp, train=False)
+    b, _ = build_pair("radio_ml_conv", (1, W, W), B, K, arp=arp, train=False)
+    a.set_precision("bf16x3")
+    b.set_precision("bf16x3")
+    g = torch.Generator().manual_seed(9)
+    xs = (torch.randn(B, 2, 1, 1024, generator=g) * 0.4).float()
+    y = O.to_one_hot(torch.randint(0, K, (B,), generator=g), K)
+    np.random.seed(1)
+    cells, tgt = iq2spiketrain(xs, y, out_w=W, out_h=W, max_duration=T, as_cells=True)
+    a.reset()
+    b.reset()
+    onet.reset()
+    assert a._stack16_ok(cells)
+    a._run_stack16(cells, chunk=5)                    # 8 launches incl. a ragged last chunk
+    b._run_window(cells, None, False)                 # per-timestep kernels
+    frames = cells.dense().cpu()
+    for t in range(T):
+        onet.test(frames[t])
+    for i, (sa, sb) in enumerate(zip(a.dcll_slices, b.dcll_slices)):
+        ea, eb = sa.dclllayer.i2h.state, sb.dclllayer.i2h.state
+        assert float((ea.eps1 != eb.eps1).float().mean()) <= 1e-3, i      # differs only after an upstream spike flip
+        assert float((ea.eps1.cpu() != onet.states[i].eps1).float().mean()) <= 2e-3, i
+        if arp > 0:
+            assert float((ea.arp - eb.arp).abs().gt(1e-5).float().mean()) <= 1e-3
+        ca, cb = np.array(sa.clout), np.array(sb.clout)
+        assert ca.shape == cb.shape == (T, B)
+        assert (ca == cb).mean() >= 0.995 and (ca == np.array(onet.clout[i])).mean() >= 0.99
+        assert sa.iter == sb.iter == T
+    # layer 0 in isolation is bit-exact in its traces (same FP32 recurrences, one rounding per op)
+    assert torch.equal(a.dcll_slices[0].dclllayer.i2h.state.eps1, b.dcll_slices[0].dclllayer.i2h.state.eps1)
+    assert a.accuracy(tgt) == b.accuracy(tgt)
