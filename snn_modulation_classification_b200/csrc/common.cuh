@@ -71,9 +71,10 @@ static inline Geo geo_of(const dcll_conv_layer *L) {
 
 // Workspace carve-up (offsets in bytes, 256-B aligned).
 struct WsLayout {
-    int n_ro;            // read-out partial blocks
+    int n_ro;            // read-out partial blocks (FP32 kernel)
+    int n_ro_tc;         // read-out partial blocks of the tcgen05 kernel (512 features each)
     int n_split;         // weight-gradient position splits
-    size_t off_ro_part;  // float [n_ro][B][Ktot]
+    size_t off_ro_part;  // float [max(n_ro, n_ro_tc)][B][Ktot]
     size_t off_go;       // float [B][K]   dL/dpvoutput
     size_t off_go2;      // float [B][K]   dL/doutput (output layer)
     size_t off_wg_part;  // float [n_split][nW + Cout]
@@ -89,6 +90,9 @@ int sync_kernel_weights(const dcll_conv_layer *L, cudaStream_t st);   // weight 
 bool tc_supported(const dcll_conv_layer *L);
 int launch_readout_fwd(const dcll_conv_layer *L, const float *target, int loss_kind, int32_t *clout,
                        float *loss_out, cudaStream_t st);
+bool readout_tc_supported(const dcll_conv_layer *L);
+int readout_tc_blocks(const dcll_conv_layer *L);
+int launch_readout_tc(const dcll_conv_layer *L, float *partial, cudaStream_t st);   // tcgen05, split-bf16 x3
 int launch_loss_grad(const dcll_conv_layer *L, const float *target, int loss_kind, float *loss_out, cudaStream_t st);
 int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st);
 int launch_wgrad(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st);

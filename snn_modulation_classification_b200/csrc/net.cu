@@ -54,10 +54,11 @@ WsLayout ws_layout(const dcll_conv_layer *L) {
     WsLayout w;
     // read-out partial blocks: enough CTAs (6 per SM) to hide the load latency of the single-buffered tiles
     w.n_ro = max(1, min(ceil_div(g.F, 64), 148 * 3));
+    w.n_ro_tc = readout_tc_blocks(L);
     w.n_split = max(wgrad_splits(L), wgrad_tc_splits(L));   // room for either weight-gradient kernel
     size_t off = 0;
     w.off_ro_part = off;
-    off = align_up(off + sizeof(float) * (size_t)w.n_ro * L->B * g.Ktot, 256);
+    off = align_up(off + sizeof(float) * (size_t)max(w.n_ro, w.n_ro_tc) * L->B * g.Ktot, 256);
     w.off_go = off;
     off = align_up(off + sizeof(float) * (size_t)L->B * L->K, 256);
     w.off_go2 = off;

@@ -135,20 +135,21 @@ __global__ void __launch_bounds__(256, 3) readout_fwd_kernel(const float *__rest
 }
 
 // One CTA per sample: fixed-order reduction of the partials, + bias, loss gradient, argmax.
-__global__ void __launch_bounds__(256) readout_finish_kernel(const float *__restrict__ partial, int n_part, int B, int K,
+// blockDim.x / 64 slices walk the partial blocks (4 after the FP32 kernel, 16 after the tcgen05 kernel's many blocks).
+__global__ void __launch_bounds__(1024) readout_finish_kernel(const float *__restrict__ partial, int n_part, int B, int K,
                                                              int Ktot, const float *__restrict__ bo,
                                                              const float *__restrict__ bout, const float *__restrict__ target,
                                                              int loss_kind, float *__restrict__ pvoutput,
                                                              float *__restrict__ output, float *__restrict__ g_o,
                                                              float *__restrict__ g_o2, int32_t *__restrict__ clout,
                                                              float *__restrict__ loss_out) {
-    __shared__ float red[4][64];
+    __shared__ float red[16][64];
     __shared__ float vals[64];
     const int b = blockIdx.x, tid = threadIdx.x;
-    const int kk = tid & 63, sl = tid >> 6;
+    const int kk = tid & 63, sl = tid >> 6, n_sl = blockDim.x >> 6;
     float s = 0.f;
     if (kk < Ktot)
-        for (int c = sl; c < n_part; c += 4) s += partial[((size_t)c * B + b) * Ktot + kk];
+        for (int c = sl; c < n_part; c += n_sl) s += partial[((size_t)c * B + b) * Ktot + kk];
     red[sl][kk] = s;
     __syncthreads();
     float lsum = 0.f;
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(256) readout_finish_kernel(const float *__rest
         const bool second = tid >= K;
         const int k = second ? tid - K : tid;
         float v = ((red[0][tid] + red[1][tid]) + red[2][tid]) + red[3][tid];
+        for (int q = 4; q < n_sl; ++q) v += red[q][tid];
         v += second ? bout[k] : bo[k];
         vals[tid] = v;
         (second ? output : pvoutput)[(size_t)b * K + k] = v;
@@ -386,6 +388,14 @@ int launch_readout_fwd(const dcll_conv_layer *L, const float *target, int loss_k
     char *base = (char *)L->workspace;
     float *partial = (float *)(base + ws.off_ro_part);
     float *g_o = (float *)(base + ws.off_go), *g_o2 = (float *)(base + ws.off_go2);
+    if (readout_tc_supported(L)) {
+        int rc = launch_readout_tc(L, partial, st);
+        if (rc != DCLL_OK) return rc;
+        readout_finish_kernel<<<L->B, ws.n_ro_tc > 16 ? 1024 : 256, 0, st>>>(partial, ws.n_ro_tc, L->B, L->K, g.Ktot, L->bo, L->bout, target, loss_kind,
+                                                      L->pvoutput, L->output, g_o, g_o2, clout, loss_out);
+        DCLL_LAUNCH_OK("readout_finish_kernel");
+        return DCLL_OK;
+    }
     const int kj = ceil_div(g.Ktot, 16);
     DCLL_REQUIRE(kj >= 1 && kj <= 4, DCLL_EUNSUPPORTED, "read-out width %d > 64 unsupported", g.Ktot);
     const bool vec = (g.F % 4 == 0) && (((uintptr_t)L->pv | (uintptr_t)L->wo | (uintptr_t)L->wout) % 16 == 0);
