@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DCLL_ABI_VERSION 7
+#define DCLL_ABI_VERSION 8
 
 enum { DCLL_OK = 0, DCLL_EINVAL = -1, DCLL_ECUDA = -2, DCLL_EUNSUPPORTED = -3 };
 
@@ -80,6 +80,12 @@ typedef struct dcll_conv_layer {
     const float *wo, *bo;            /* device [K,F], [K]   frozen local read-out i2o        */
     float *wout, *bout;              /* device [K,F], [K]   output_ or NULL                  */
     float *eps0[2], *eps1[2];        /* device [B,Cin,H,W]  ping-pong state                  */
+    void *eps1_mma;                  /* device bf16 [B][2][Cin/8][H][W][8]: {hi,lo} split image of the eps1 the last
+                                        forward step produced, in the tcgen05 operand layout (16 bytes per position
+                                        and channel group).  Required (same byte size as one eps1 array) when
+                                        precision is DCLL_PREC_BF16X3 and weight_mma is set; written by
+                                        dcll_conv_step_fwd / dcll_conv_core_fwd, read by the convolution and by
+                                        dcll_conv_step_bwd_update of the same timestep          */
     float *arp;                      /* device [B,Cout,Hc,Wc] or NULL                        */
     /* per-step outputs (device) */
     float *spikes;                   /* [B,Cout,Hp,Wp] pooled spikes                         */
@@ -118,8 +124,8 @@ size_t dcll_sizeof_train_args(void);
  * dcll_launch_count: kernels launched by this library since load (or since the last reset).
  * dcll_profile_enable(every_n): bracket the kernels of every n-th layer-step with CUDA events on the
  * launching stream (0 disables).  dcll_profile_read synchronises those events and returns, per kernel
- * class c (0 encode, 1 conv_fwd, 2 readout_fwd, 3 readout_bwd, 4 wgrad, 5 adam, 6 misc) and layer l
- * (< 8), the summed milliseconds ms[c*8+l] and the number of sampled brackets n[c*8+l]; then clears. */
+ * class c (0 encode, 1 conv_fwd, 2 readout_fwd, 3 readout_bwd, 4 wgrad, 5 adam, 6 misc, 7 trace -- the trace/image
+ * kernel of a tensor-core conv step, also contained in its conv_fwd bracket) and layer l (< 8), the summed milliseconds ms[c*8+l] and the number of sampled brackets n[c*8+l]; then clears. */
 int64_t dcll_launch_count(int reset);
 int dcll_profile_enable(int every_n);
 int dcll_profile_read(double *ms, int64_t *n);

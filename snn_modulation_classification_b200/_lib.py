@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdcll_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 OK, EINVAL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3
 COEF_SCALAR, COEF_CHANNEL, COEF_ELEMENT = 0, 1, 2
@@ -34,7 +34,7 @@ class ConvLayer(C.Structure):
                 ("alpha", _fp), ("alphas", _fp), ("tau_m", _fp), ("tau_s", _fp),
                 ("weight", _fp), ("weight_t", _fp), ("weight_mma", _fp), ("bias", _fp), ("wo", _fp), ("bo", _fp),
                 ("wout", _fp), ("bout", _fp),
-                ("eps0", _fp * 2), ("eps1", _fp * 2), ("arp", _fp),
+                ("eps0", _fp * 2), ("eps1", _fp * 2), ("eps1_mma", _fp), ("arp", _fp),
                 ("spikes", _fp), ("pv", _fp), ("pvmem", _fp), ("pool_idx", _fp), ("pvoutput", _fp),
                 ("output", _fp), ("g_u", _fp), ("workspace", _fp), ("workspace_bytes", C.c_size_t)]
 
@@ -111,7 +111,7 @@ def _load():
 
 
 lib = _load()
-KERNEL_CLASSES = ["encode", "conv_fwd", "readout_fwd", "readout_bwd", "wgrad", "adam", "misc"]
+KERNEL_CLASSES = ["encode", "conv_fwd", "readout_fwd", "readout_bwd", "wgrad", "adam", "misc", "trace"]
 
 
 def profile_read():

@@ -29,7 +29,8 @@ void set_error(const char *fmt, ...);
     } while (0)
 
 // Kernel classes for the launch counter and the optional CUDA-event profile (dcll_profile_*).
-enum KClass { KC_ENCODE = 0, KC_CONV_FWD, KC_READOUT_FWD, KC_READOUT_BWD, KC_WGRAD, KC_ADAM, KC_MISC, KC_COUNT };
+enum KClass { KC_ENCODE = 0, KC_CONV_FWD, KC_READOUT_FWD, KC_READOUT_BWD, KC_WGRAD, KC_ADAM, KC_MISC, KC_TRACE, KC_COUNT };
+int prof_layer();   // layer index of the step being enqueued (profile key only)
 void count_launch(const char *name);
 // RAII: brackets the launches of one kernel class with CUDA events when profiling samples this step.
 struct ProfScope {

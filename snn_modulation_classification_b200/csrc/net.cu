@@ -98,8 +98,8 @@ static int check_layer(const dcll_conv_layer *L, const char *who) {
                  g.Hc, g.Wc, L->poolH, L->poolW);
     DCLL_REQUIRE(L->precision == DCLL_PREC_FP32 || L->precision == DCLL_PREC_BF16X3, DCLL_EINVAL, "%s: unknown precision mode %d",
                  who, L->precision);
-    DCLL_REQUIRE(L->precision != DCLL_PREC_BF16X3 || !tc_supported(L) || L->weight_mma, DCLL_EINVAL,
-                 "%s: the bf16x3 tensor-core conv needs weight_mma", who);
+    DCLL_REQUIRE(L->precision != DCLL_PREC_BF16X3 || !tc_supported(L) || (L->weight_mma && L->eps1_mma), DCLL_EINVAL,
+                 "%s: the bf16x3 tensor-core conv needs weight_mma and eps1_mma", who);
     DCLL_REQUIRE(L->alpha && L->alphas && L->tau_m && L->tau_s && L->weight && L->weight_t && L->bias && L->wo && L->bo,
                  DCLL_EINVAL, "%s: null parameter pointer", who);
     DCLL_REQUIRE(!L->output_layer || (L->wout && L->bout && L->output), DCLL_EINVAL, "%s: output layer without output_", who);
@@ -117,6 +117,7 @@ static int check_layer(const dcll_conv_layer *L, const char *who) {
 }
 
 static int g_layer = 0;  // layer index of the step being enqueued (profile key only)
+int prof_layer() { return g_layer; }
 
 static int step_fwd(dcll_conv_layer *L, const void *x, const float *target, int loss_kind, int32_t *clout, float *loss_out,
                     cudaStream_t st) {

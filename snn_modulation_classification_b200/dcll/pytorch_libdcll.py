@@ -252,6 +252,7 @@ class ContinuousConv2D(nn.Module):
         self.quantized = False     # see quant.py
         self.precision = 'fp32'    # 'fp32' (parity mode) or 'bf16x3' (tcgen05 tensor cores, where instantiated)
         self._wmma = None          # bf16 {hi,lo} weights in the tcgen05 B-operand layout
+        self._e1mma = None         # bf16 {hi,lo} image of eps1 in the tcgen05 A-operand layout (written by the forward)
 
     # ref:359-366
     def reset_parameters(self):
@@ -373,6 +374,10 @@ class ContinuousConv2D(nn.Module):
         desc.eps0[0], desc.eps0[1] = _lib.ptr(e0), _lib.ptr(self._spare[0])
         desc.eps1[0], desc.eps1[1] = _lib.ptr(e1), _lib.ptr(self._spare[1])
         desc.cur = 0
+        if self.tensor_core_ok():
+            if self._e1mma is None or self._e1mma.numel() != 2 * e1.numel() or self._e1mma.device != e1.device:
+                self._e1mma = torch.empty(2 * e1.numel(), dtype=torch.bfloat16, device=e1.device)
+            desc.eps1_mma = _lib.ptr(self._e1mma)
         arp = self._arp()
         desc.arp = _lib.ptr(arp) if arp is not None else None
         return e0, e1, arp

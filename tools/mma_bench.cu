@@ -1,0 +1,115 @@
+// tcgen05 issue-rate microbenchmark for the short MMAs of the DCLL conv / wgrad kernels (M=128, K=16, N=64/32, SWIZZLE_NONE).
+// One CTA per SM; lane 0 of `issuers` warps issues `n` MMAs each, then commits; cycles are taken around issue+completion.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I snn_modulation_classification_b200/csrc -I include tools/mma_bench.cu -o tools/_build/mma_bench
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include "tc_ptx.cuh"
+
+using namespace dcll::tc;
+
+struct Cfg {
+    int n;          // MMAs per issuer
+    int n_acc;      // accumulators cycled through per issuer
+    int pair;       // 1: alternate N=64 / N=32 (as the conv kernel), 0: all N=nsize
+    int nsize;      // N of the MMAs when !pair
+    int shift;      // vary the A start address per MMA (implicit im2col) or not
+    int issuers;    // issuing warps (each its own accumulators)
+    int commit_every;   // tcgen05.commit + wait every k MMAs (0 = only at the end)
+    int swz;            // 0: SWIZZLE_NONE canonical layout, 2: SWIZZLE_128B, 4: 64B, 6: 32B (descriptor bits 61..63), K-major
+};
+
+__global__ void __launch_bounds__(256, 1) bench(Cfg c, long long *out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar[8];
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u + i;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; ++i) mbar_init(bar + i, 1);
+        mbar_fence_init();
+    }
+    if (warp == 7) tmem_alloc(&slot, 512);
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = slot;
+    long long t0 = 0, t1 = 0;
+    if (warp < c.issuers) {
+        const uint32_t elected = elect_one();
+        const uint32_t a_base = desc_lo(smem_u32(smem), c.swz ? 16 : 7744), b_base = desc_lo(smem_u32(smem + 128 * 1024), c.swz ? 16 : 1024);
+        const uint32_t swz = (uint32_t)c.swz << 29;
+        const uint32_t sbo_sw = c.swz == 2 ? 1024 : (c.swz == 4 ? 512 : 256);
+        const uint32_t A_HI = c.swz ? (desc_hi(sbo_sw) | swz) : desc_hi(352), B_HI = c.swz ? (desc_hi(sbo_sw) | swz) : desc_hi(128);
+        const uint32_t i64 = idesc_bf16(128, 64, false, false), i32 = idesc_bf16(128, 32, false, false);
+        const uint32_t iN = idesc_bf16(128, c.nsize, false, false);
+        __syncwarp();
+        t0 = clock64();
+        if (elected) {
+            int ph = 0;
+            const uint32_t dbase = tmem + warp * (512 / c.issuers);
+            const uint32_t acc_mask = c.n_acc - 1, acc_cols = 64 * (c.nsize > 64 ? c.nsize / 64 : 1);
+            const uint32_t sh_mask = c.shift ? 31u : 0u;
+            const uint32_t lo_off = c.pair ? (32768 >> 4) : 0;
+            const int ce = c.commit_every ? c.commit_every : (1 << 30);
+            int since = 0;
+#pragma unroll 1
+            for (int k = 0; k < c.n; k += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t kk = k + u;
+                    const uint32_t d = dbase + (((kk >> 1) & acc_mask) * acc_cols);
+                    const uint32_t sh = c.swz ? ((kk >> 1) & sh_mask & 3) * 2 : ((kk >> 1) & sh_mask);
+                    const uint64_t a = desc(A_HI, a_base + sh + ((u & 1) ? lo_off : 0));
+                    const uint64_t b = desc(B_HI, b_base + (c.swz ? (sh & 3) * 2 : (sh & 7) * 256));
+                    const uint32_t id = c.pair ? ((u & 1) ? i32 : i64) : iN;
+                    mma_bf16(d, a, b, id, 1);
+                }
+                since += 8;
+                if (since >= ce) {
+                    since = 0;
+                    commit(bar + warp);
+                    mbar_wait(bar + warp, ph);
+                    ph ^= 1;
+                }
+            }
+            commit(bar + 4 + warp);
+            mbar_wait(bar + 4 + warp, 0);
+        }
+        __syncwarp();
+        t1 = clock64();
+    }
+    if (lane == 0 && warp < c.issuers && blockIdx.x == 0) out[warp] = t1 - t0;
+    fence_before();
+    __syncthreads();
+    if (warp == 7) tmem_dealloc(tmem, 512);
+}
+
+int main() {
+    long long *out;
+    cudaMallocManaged(&out, 64);
+    cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const Cfg cfgs[] = {
+        // n, n_acc, pair, nsize, shift, issuers, commit_every, swz
+        {4096, 1, 0, 64, 1, 1, 0, 0}, {4096, 1, 0, 32, 1, 1, 0, 0}, {4096, 1, 0, 128, 1, 1, 0, 0}, {4096, 1, 0, 256, 1, 1, 0, 0},
+        {4096, 1, 1, 64, 1, 1, 0, 0}, {4096, 1, 1, 64, 1, 2, 0, 0},
+        {4096, 1, 0, 64, 0, 1, 0, 2}, {4096, 1, 0, 32, 0, 1, 0, 2}, {4096, 1, 0, 128, 0, 1, 0, 2}, {4096, 1, 0, 64, 1, 1, 0, 2},
+        {4096, 1, 0, 32, 1, 1, 0, 2}, {4096, 1, 1, 64, 1, 1, 0, 2},
+        {4096, 1, 0, 64, 0, 1, 0, 4}, {4096, 1, 0, 32, 0, 1, 0, 4}, {4096, 1, 0, 64, 1, 1, 0, 4}, {4096, 1, 1, 64, 1, 1, 0, 4},
+        {4096, 1, 0, 64, 0, 1, 0, 6}, {4096, 1, 0, 32, 0, 1, 0, 6},
+    };
+    printf("%6s %5s %4s %5s %5s %7s %6s %3s | cycles/MMA (issuer 0)\n", "n", "n_acc", "pair", "N", "shift", "issuers", "commit", "swz");
+    for (const Cfg &c : cfgs) {
+        for (int rep = 0; rep < 2; ++rep) {
+            bench<<<148, 256, 200 * 1024>>>(c, out);
+            if (cudaDeviceSynchronize() != cudaSuccess) {
+                printf("CUDA error: %s\n", cudaGetErrorString(cudaGetLastError()));
+                return 1;
+            }
+        }
+        printf("%6d %5d %4d %5d %5d %7d %6d %3d | %.1f\n", c.n, c.n_acc, c.pair, c.nsize, c.shift, c.issuers, c.commit_every, c.swz,
+               (double)out[0] / c.n);
+    }
+    return 0;
+}
