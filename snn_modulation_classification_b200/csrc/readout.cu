@@ -203,8 +203,10 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(const float *__restric
                                                           float *__restrict__ m_b, float *__restrict__ v_b,
                                                           float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
                                                           AdamScalars sc) {
-    __shared__ float gs[64][KMAX];
-    __shared__ float gs2[WOUT ? 64 : 1][KMAX];
+    // rows are read back as float4 (one broadcast LDS.128 per 4 FMAs; scalar LDS made the sweep LDS-issue bound)
+    __shared__ __align__(16) float gs[64][KMAX];
+    __shared__ __align__(16) float gs2[WOUT ? 64 : 1][KMAX];
+    static_assert(KMAX % 4 == 0, "float4 rows");
     const int tid = threadIdx.x;
     const int f = blockIdx.x * 256 + tid;
     const bool fok = f < F;
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(const float *__restric
         }
         __syncthreads();
         if (fok) {
-            constexpr int UB = 8;   // samples in flight per thread
+            constexpr int UB = 8;   // samples in flight per thread (16 was slower: fewer resident CTAs)
             for (int bb = 0; bb < nb; bb += UB) {
                 float pvv[UB];
 #pragma unroll
@@ -237,12 +239,21 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(const float *__restric
                 for (int u = 0; u < UB; ++u) {
                     if (bb + u >= nb) break;
                     float s = 0.f;
+                    const float4 *g4 = reinterpret_cast<const float4 *>(gs[bb + u]);
 #pragma unroll
-                    for (int k = 0; k < KMAX; ++k) s = fmaf(gs[bb + u][k], w[k], s);
+                    for (int k = 0; k < KMAX; k += 4) {
+                        const float4 g = g4[k >> 2];
+                        s = fmaf(g.x, w[k], s), s = fmaf(g.y, w[k + 1], s), s = fmaf(g.z, w[k + 2], s), s = fmaf(g.w, w[k + 3], s);
+                    }
                     g_u[(size_t)(b0 + bb + u) * F + f] = s * (1.f - pvv[u]) * pvv[u];
                     if (WOUT) {
+                        const float4 *h4 = reinterpret_cast<const float4 *>(gs2[bb + u]);
 #pragma unroll
-                        for (int k = 0; k < KMAX; ++k) acc[k] = fmaf(gs2[bb + u][k], pvv[u], acc[k]);
+                        for (int k = 0; k < KMAX; k += 4) {
+                            const float4 g = h4[k >> 2];
+                            acc[k] = fmaf(g.x, pvv[u], acc[k]), acc[k + 1] = fmaf(g.y, pvv[u], acc[k + 1]);
+                            acc[k + 2] = fmaf(g.z, pvv[u], acc[k + 2]), acc[k + 3] = fmaf(g.w, pvv[u], acc[k + 3]);
+                        }
                     }
                 }
             }
@@ -467,6 +478,10 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
             readout_bwd_kernel<16, true><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, g_o2, L->B, g.F, L->K, L->B, L->g_u, L->wout,
                                                               L->bout, o.m_w, o.v_w, o.m_b, o.v_b, a->grad_wout, a->grad_bout,
                                                               a->apply_update, sc);
+        else if (L->K <= 24)
+            readout_bwd_kernel<24, true><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, g_o2, L->B, g.F, L->K, L->B, L->g_u, L->wout,
+                                                              L->bout, o.m_w, o.v_w, o.m_b, o.v_b, a->grad_wout, a->grad_bout,
+                                                              a->apply_update, sc);
         else
             readout_bwd_kernel<32, true><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, g_o2, L->B, g.F, L->K, L->B, L->g_u, L->wout,
                                                               L->bout, o.m_w, o.v_w, o.m_b, o.v_b, a->grad_wout, a->grad_bout,
@@ -479,6 +494,9 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
         dim3 grid(fblk, slices);
         if (L->K <= 16)
             readout_bwd_kernel<16, false><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, nullptr, L->B, g.F, L->K, b_per, L->g_u, nullptr,
+                                                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, sc);
+        else if (L->K <= 24)
+            readout_bwd_kernel<24, false><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, nullptr, L->B, g.F, L->K, b_per, L->g_u, nullptr,
                                                                nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, sc);
         else
             readout_bwd_kernel<32, false><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, nullptr, L->B, g.F, L->K, b_per, L->g_u, nullptr,

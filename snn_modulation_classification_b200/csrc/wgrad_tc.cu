@@ -16,8 +16,10 @@
 //   (X_hi is read once for two products) and X_lo x G_hi is the second MMA.  64-column accumulators x 7 kernel columns
 //   = 448 of the 512 TMEM columns per kernel-row group, hence a CTA owns ONE group (g = blockIdx & 1; the 8th kernel
 //   row of group 1 is padding) and CTA pairs walk the same tiles.
-// * Persistent and warp-specialised: 12 loader warps fill one half of a double buffer with the next (eps1, g_u) tile while
-//   one elected lane issues the 672 MMAs of the current tile; mbarriers (full: loader arrivals, empty: tcgen05.commit).
+// * Persistent and warp-specialised: 12 loader warps fill one half of a double buffer with the next (eps1, g_u) tile
+//   (eps1 straight from the bf16 operand image the forward wrote, by cp.async; g_u converted fp32 -> bf16 hi/lo) while
+//   two issuer warps (kernel columns 0..3 / 4..6) issue the MMAs of the current tile; mbarriers (full: loader
+//   arrivals, empty: tcgen05.commit of both issuers).
 // Partials (one per CTA) are reduced in fixed order by reduce_adam_kernel, exactly like the FP32 path.
 #include <cuda_bf16.h>
 
@@ -29,6 +31,7 @@ namespace dcll {
 struct WgTcP {
     const float *g_u;   // [B,32,Hc,Wc]
     const float *eps1;  // [B,32,H,W] (state after the forward step)
+    const uint4 *img;   // bf16 {hi,lo} operand image of eps1 written by the tensor-core forward ([b][part][ci/8][H][W][8]), or null
     float *partial;     // [S][nW + Cout]
     int B, H, W, padH, padW, Hc, Wc;
     int tiles_h, tiles_w, n_units, n_tot, nW;
@@ -76,8 +79,8 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) mbar_init(full + i, G::LOADER_WARPS), mbar_init(empty + i, 1);
-        mbar_init(done, 1);
+        for (int i = 0; i < 2; ++i) mbar_init(full + i, G::LOADER_WARPS), mbar_init(empty + i, 2);
+        mbar_init(done, 2);
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -115,7 +118,28 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
             const int h0 = th_i * G::TH, w0 = tw_i * G::TW;
             if (i >= 2) mbar_wait(empty + buf, ((i >> 1) - 1) & 1);   // MMAs of unit i-2 have finished reading this half
             // ---- eps1 halo tile: [row][cg][col][8 ci], bf16 hi | lo
-            if (G::CIN == 32) {
+            if (G::CIN == 32 && p.img) {
+                // the forward already wrote eps1 as a bf16 {hi,lo} image in 16-byte (position, channel group) pieces:
+                // asynchronous copies (zero fill outside the picture) that land while g_u is converted below
+                const int l384 = (warp - 4) * 32 + lane;
+                const size_t hw = (size_t)p.H * p.W;
+                const uint4 *src0 = p.img + (size_t)b * 2 * G::CGR * hw;
+                const uint32_t dst0 = smem_u32(sX);
+                for (int idx = l384; idx < 2 * G::XROWS * G::CGR * G::XCOLS; idx += G::LOADER_WARPS * 32) {
+                    const int c = idx % G::XCOLS;
+                    int t = idx / G::XCOLS;
+                    const int cg = t % G::CGR;
+                    t /= G::CGR;
+                    const int r = t % G::XROWS, part = t / G::XROWS;
+                    const int gh = h0 - p.padH + row_off + r, gw = w0 - p.padW + c;
+                    const bool in = gh >= 0 && gh < p.H && gw >= 0 && gw < p.W;
+                    const uint4 *src = in ? src0 + (size_t)(part * G::CGR + cg) * hw + (size_t)gh * p.W + gw : src0;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + part * G::X_PART + r * G::X_RP + cg * G::X_CP + c * 16),
+                                 "l"(src), "r"(in ? 16u : 0u)
+                                 : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            } else if (G::CIN == 32) {
                 // two positions per iteration (16 loads in flight)
                 for (int it = l96; it < G::XROWS * G::XCOLS; it += 2 * 96) {
                     float v[2][8];
@@ -188,11 +212,12 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
                     *reinterpret_cast<uint4 *>(dst + G::G_PART) = *reinterpret_cast<const uint4 *>(lo);
                 }
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             fence_async_smem();   // this thread's smem writes -> async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(full + buf);
         }
-    } else if (warp == 0) {
+    } else if (warp < 2) {
         // ================= MMA issuer =================
         // a_major = b_major = MN (bits 15,16), bf16 x bf16 -> f32, N = 32, M = 128
         constexpr uint32_t IDESC_N2 = idesc_bf16(128, 2 * G::COUT, true, true);   // X_hi x [G_hi | G_lo]
@@ -200,6 +225,9 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
         constexpr uint32_t A_HI = desc_hi(G::X_CP);          // SBO: next 8 rows of M = next (dy, cg) group
         constexpr uint32_t B_HI = desc_hi(G::G_PLANE);       // SBO: next 8 columns of N = next ({hi,lo}, co/8) group
         const uint32_t elected = elect_one();
+        // two issuer warps (a single issuing thread tops out at ~54 cycles per MMA, the tensor pipe at ~44 for these
+        // short MMAs): warp 0 owns the accumulators of kernel columns 0..3, warp 1 those of 4..6
+        const int kw0 = warp == 0 ? 0 : 4, kw1 = warp == 0 ? 4 : G::KW;
         int i = 0;
         for (int u = u_first; u < p.n_units; u += u_step, ++i) {
             const int buf = i & 1;
@@ -214,8 +242,8 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
                 for (int r = 0; r < rows; ++r) {
                     const uint64_t b = desc(B_HI, b_base + r * G::TW);
                     const uint32_t acc = (i == 0 && r == 0) ? 0u : 1u;
-#pragma unroll
-                    for (int kw = 0; kw < G::KW; ++kw) {
+#pragma unroll 4
+                    for (int kw = kw0; kw < kw1; ++kw) {
                         const uint32_t a_lo0 = a_base + ((r * G::X_RP) >> 4) + kw;
                         const uint32_t d = tmem_base + kw * G::ACC_COLS;
                         mma_bf16(d, desc(A_HI, a_lo0), b, IDESC_N2, acc);
@@ -291,6 +319,7 @@ int launch_wgrad_tc(const dcll_conv_layer *L, float *partial, int S, cudaStream_
     Geo g = geo_of(L);
     WgTcP p;
     p.g_u = L->g_u, p.eps1 = L->eps1[L->cur & 1], p.partial = partial;
+    p.img = (L->Cin == 32 && tc_supported(L)) ? reinterpret_cast<const uint4 *>(L->eps1_mma) : nullptr;
     p.B = L->B, p.H = L->H, p.W = L->W, p.padH = L->padH, p.padW = L->padW, p.Hc = g.Hc, p.Wc = g.Wc;
     p.tiles_h = ceil_div(g.Hc, 16), p.tiles_w = ceil_div(g.Wc, 16);
     p.n_units = L->B * p.tiles_h * p.tiles_w;
