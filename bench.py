@@ -10,7 +10,7 @@ and Adam step per layer per timestep), or of inference for the infer workloads. 
   value        windows/s with the IQ records already resident in HBM (encode + T timesteps timed)
   e2e          the same through the public API with HOST buffers: pinned-host IQ -> H2D -> iq2spiketrain ->
                ConvNetwork.learn_window -> device vote -> D2H of the per-sample predictions, all timed
-  roofline     dominant kernel (conv_fwd of a 32->32 layer) from CUDA events sampled inside the timed region
+  roofline     dominant kernel (convolution of a 32->32 layer) from CUDA events sampled inside the timed region
   cpu_baseline the oracle port (same operator sequence as the reference: F.conv2d / autograd / torch.optim.Adam)
                on the box's host cores, on a bounded sample of the same workload
 
@@ -181,10 +181,13 @@ def make_args(arp=0.0):
     return types.SimpleNamespace(netscale=1.0, alpha=0.92, alphas=0.85, alpharp=0.65, arp=arp, lc_ampl=0.5, random_tau=True)
 
 
+NCU_SUMMARY = "r01_ncu_final_top_kernels.txt"
+
+
 def ncu_traffic(kernel_substr):
     """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed `ncu --set full`
     summary of this round (profiles/); None when the capture is absent."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_tc_v3_conv_fwd_and_wgrad.txt")
+    path = os.path.join(ROOT, "profiles", NCU_SUMMARY)
     if not os.path.exists(path):
         return None
     cur, vals = None, {}
@@ -306,28 +309,38 @@ def run_b200(a):
     value = world * batch * a.steps / (ms / 1e3)
     e2e = world * batch * a.steps / (ms_e2e / 1e3)
     pk = peaks()
-    # ---- roofline of the dominant kernel: conv_fwd of a 32->32 layer (layers 1 and 2 are identical)
+    # ---- roofline of the dominant kernel: the convolution of a 32->32 layer (layers 1 and 2 are identical).
+    # In bf16x3 mode the conv_fwd bracket holds trace_image_kernel + conv_mma_kernel and the trace bracket the former alone.
     hw = res * res
     conv_flops = 2.0 * 32 * 49 * 32 * hw * batch                     # algorithmic FLOPs per launch
     c_ms, c_n = prof.get(("conv_fwd", 1), (0.0, 0))
-    avg_ms = c_ms / c_n if c_n else None
+    t_ms, t_n = prof.get(("trace", 1), (0.0, 0))
+    avg_ms = (c_ms / c_n - (t_ms / t_n if t_n else 0.0)) if c_n else None
     achieved = conv_flops / (avg_ms * 1e-3) / 1e12 if avg_ms else None
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    roofline = {"kernel": ("conv_fwd_tc_kernel<7,7,32,32> (layer 1: 32->32 ch, tcgen05 split-bf16 x3, TMEM accumulators)" if tc
+    # issue floor of this decomposition: 2 M-tiles x 49 taps x 2 k-chunks x 2 MMAs per 16x16-position tile, ~44 cycles per
+    # SS-mode M=128 MMA with N <= 64 (A-operand read; tools/mma_bench.cu), tiles spread over 148 SMs
+    n_tiles = batch * ((res + 15) // 16) ** 2
+    floor_ms = (n_tiles + 147) // 148 * 392 * 44 / (sm_mhz * 1e3)
+    roofline = {"kernel": ("conv_mma_kernel<7,7,32,32> (layer 1: 32->32 ch, tcgen05 split-bf16 x3, TMEM accumulators)" if tc
                            else "conv_fwd_kernel<7,7,...> (layer 1: 32->32 ch, FP32 FMA path)"), "bound": "tensor",
                 "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tensor"] if achieved else None,
-                "traffic": ncu_traffic("conv_fwd_tc_kernel") if (tc and res == 128 and batch == 64) else None,
-                "traffic_unit": "bytes per launch (dram read + write, ncu --set full, profiles/r01_ncu_tc_v3_conv_fwd_and_wgrad.txt); "
-                                "algorithmic: 0.89e9",
+                "traffic": ncu_traffic("conv_mma_kernel") if (tc and res == 128 and batch == 64) else None,
+                "traffic_unit": "bytes per launch (dram read + write, ncu --set full, profiles/%s); algorithmic: 0.40e9 "
+                                "(operand image in, spikes + pv out)" % NCU_SUMMARY,
                 "peak_source": "%s bf16 dense sustained (MEASURED_PEAKS.json)" % pk["src"],
                 "avg_launch_ms": avg_ms, "launches_sampled": c_n, "algorithmic_flops_per_launch": conv_flops,
                 "fp32_fma_peak_tflops_at_clock": fp32_peak, "frac_of_fp32_fma_peak": achieved / fp32_peak if achieved else None,
                 "executed_tensor_flops_per_launch": conv_flops * (3 if tc else 0),
                 "frac_executed": (3 * achieved / pk["tensor"]) if (achieved and tc) else None,
-                "note": ("achieved counts ALGORITHMIC conv FLOPs; the split-bf16 mode executes 3 bf16 MMAs per product "
-                         "(frac_executed = tensor-pipe share actually used). wgrad still runs on the FP32 FMA pipe." if tc else
+                "mma_issue_floor_ms": floor_ms if tc else None,
+                "frac_of_issue_floor": (floor_ms / avg_ms) if (tc and avg_ms) else None,
+                "note": ("achieved counts ALGORITHMIC conv FLOPs; the split-bf16 mode executes 3 bf16 products per FLOP "
+                         "(frac_executed = tensor-pipe share actually used). With Cout = 32 the MMAs are N = 64 / 32 and "
+                         "bound by the A-operand read (~44 cycles each, measured), not by math: mma_issue_floor_ms is the "
+                         "floor of this decomposition." if tc else
                          "FP32-exact parity mode runs on the CUDA-core FMA pipe")}
     per_class = {}
     for (name, layer), (tms, n) in sorted(prof.items()):

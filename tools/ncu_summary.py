@@ -21,7 +21,9 @@ KEYS = ["Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "dra
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
         "smsp__inst_executed.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.max",
-        "smsp__average_warp_latency_issue_stalled_barrier.ratio" ]
+        "smsp__average_warp_latency_issue_stalled_barrier.ratio",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct"]
 
 
 def launches(path):
