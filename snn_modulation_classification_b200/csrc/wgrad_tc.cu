@@ -37,9 +37,10 @@ struct WgTcP {
     int tiles_h, tiles_w, n_units, n_tot, nW;
 };
 
-// CIN = 32: M = 4 kernel rows x 32 channels, two row groups (g = 0,1).
-// CIN = 1 (layer 0): the single channel is zero-padded to one group of 8, M = 16 kernel rows x 8 (rows 7..15 and
-// channels 1..7 are padding), one row group; the work is tiny, the kernel is bound by streaming g_u.
+// CIN = 32: M = 4 kernel rows x 32 channels, two row groups (g = 0,1), one accumulator per kernel column.
+// CIN = 1 (layer 0): the 8 slots of a 16-byte piece hold the 8 column shifts eps1[row][col .. col+7] instead of 8
+// channels, so M = 16 kernel rows x 8 kernel columns (rows 7..15 and column 7 are padding) and ONE MMA pair per
+// output row covers every tap: 32 MMAs per tile instead of 224; the kernel is bound by streaming g_u.
 template <int CIN_>
 struct WgTcGeoT {
     static constexpr int KH = 7, KW = 7, CIN = CIN_, COUT = 32;
@@ -47,10 +48,10 @@ struct WgTcGeoT {
     static constexpr int CGR = CIN == 32 ? 4 : 1;            // channel groups per halo row
     static constexpr int NG = CIN == 32 ? 2 : 1;             // kernel-row groups; a CTA handles ONE (g = blockIdx & 1)
     static constexpr int DY = 128 / (CGR * 8);               // kernel rows per group (incl. padding)
-    static constexpr int NACC = KW;                          // accumulators per CTA, each 128 x ACC_COLS fp32
+    static constexpr int NACC = CIN == 32 ? KW : 1;          // accumulators per CTA, each 128 x ACC_COLS fp32
     static constexpr int ACC_COLS = 2 * COUT;                // [X_hi*G_hi + X_lo*G_hi | X_hi*G_lo], summed when draining
     static constexpr int XROWS = TH + DY - 1;
-    static constexpr int XCOLS = TW + KW - 1;                // 22
+    static constexpr int XCOLS = CIN == 32 ? TW + KW - 1 : TW;   // 22; CIN = 1: the column shifts live inside the pieces
     static constexpr int X_CP = XCOLS * 16;                  // channel-group pitch (bytes)
     static constexpr int X_RP = CGR * X_CP;                  // halo-row pitch
     static constexpr int X_PART = XROWS * X_RP;              // one of {hi,lo}
@@ -169,17 +170,22 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
                     }
                 }
             } else {
-                // single input channel: all loader lanes share the positions; channels 1..7 of the group are zero
+                // single input channel: piece (r, c) = the 8 column shifts eps1[r][c + 0..7] (slot 7 is padding)
                 for (int it = (warp - 4) * 32 + lane; it < G::XROWS * G::XCOLS; it += G::LOADER_WARPS * 32) {
                     const int r = it / G::XCOLS, c = it - r * G::XCOLS;
-                    const int gh = h0 - p.padH + r, gw = w0 - p.padW + c;
-                    float v = 0.f;
-                    if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) v = __ldg(ge + ((size_t)b * p.H + gh) * p.W + gw);
-                    __nv_bfloat16 hi = __float2bfloat16_rn(v);
-                    __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+                    const int gh = h0 - p.padH + r, gw0 = w0 - p.padW + c;
+                    __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int gw = gw0 + k;
+                        float v = 0.f;
+                        if (k < G::KW && gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) v = __ldg(ge + ((size_t)b * p.H + gh) * p.W + gw);
+                        hi[k] = __float2bfloat16_rn(v);
+                        lo[k] = __float2bfloat16_rn(v - __bfloat162float(hi[k]));
+                    }
                     unsigned char *dst = sX + r * G::X_RP + c * 16;
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4((uint32_t)__bfloat16_as_ushort(hi), 0u, 0u, 0u);
-                    *reinterpret_cast<uint4 *>(dst + G::X_PART) = make_uint4((uint32_t)__bfloat16_as_ushort(lo), 0u, 0u, 0u);
+                    *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
+                    *reinterpret_cast<uint4 *>(dst + G::X_PART) = *reinterpret_cast<const uint4 *>(lo);
                 }
             }
             // ---- g_u tile: [cog][row][col][8 co], bf16 hi | lo (zero outside the image)
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
         const uint32_t elected = elect_one();
         // two issuer warps (a single issuing thread tops out at ~54 cycles per MMA, the tensor pipe at ~44 for these
         // short MMAs): warp 0 owns the accumulators of kernel columns 0..3, warp 1 those of 4..6
-        const int kw0 = warp == 0 ? 0 : 4, kw1 = warp == 0 ? 4 : G::KW;
+        const int kw0 = warp == 0 ? 0 : 4, kw1 = G::NACC == 1 ? (warp == 0 ? 1 : 0) : (warp == 0 ? 4 : G::KW);
         int i = 0;
         for (int u = u_first; u < p.n_units; u += u_step, ++i) {
             const int buf = i & 1;
@@ -266,15 +272,16 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
     fence_after();
     {
         const int q = warp & 3;                                          // TMEM lane quarter of this warp
-        const int m = q * 32 + lane;                                     // (dy, ci) resp. (dy, c8)
+        const int m = q * 32 + lane;                                     // (dy, ci) resp. (dy, kw)
         const int dy = G::CIN == 32 ? (m >> 5) : (m >> 3);
         const int ci = G::CIN == 32 ? (m & 31) : 0;
-        const bool lane_ok = G::CIN == 32 ? true : ((m & 7) == 0);
+        const bool lane_ok = G::CIN == 32 ? true : ((m & 7) < G::KW);
         const int kh = G::DY * grp + dy;
-        for (int kw = (warp >> 2); kw < G::KW; kw += 4) {
+        for (int a = (warp >> 2); a < G::NACC; a += 4) {
             uint32_t v[32], v2[32];
-            ld32(tmem_base + ((uint32_t)(q * 32) << 16) + kw * G::ACC_COLS, v);
-            ld32(tmem_base + ((uint32_t)(q * 32) << 16) + kw * G::ACC_COLS + G::COUT, v2);
+            ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS, v);
+            ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS + G::COUT, v2);
+            const int kw = G::CIN == 32 ? a : (m & 7);
             if (kh < G::KH && lane_ok) {
 #pragma unroll
                 for (int co = 0; co < 32; ++co)
