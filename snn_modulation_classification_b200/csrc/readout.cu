@@ -607,9 +607,9 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
         else
             RB_LAUNCH(32, true, grid, L->B, L->wout, L->bout, o.m_w, o.v_w, o.m_b, o.v_b, a->grad_wout, a->grad_bout, a->apply_update, sc);
     } else {
-        // enough CTAs to fill the machine: slice the batch when F is small
-        int slices = max(1, min(ceil_div(L->B, 64), ceil_div(2 * 148, fblk)));
-        int b_per = ceil_div(ceil_div(L->B, slices), 64) * 64;
+        // enough CTAs for >= 4 waves of 3 CTAs per SM (a 2.3-wave grid loses 23 % to the partial last wave): slice the batch
+        int slices = max(1, min(ceil_div(L->B, 32), ceil_div(4 * 3 * 148, fblk)));
+        int b_per = ceil_div(ceil_div(L->B, slices), 32) * 32;
         slices = ceil_div(L->B, b_per);
         dim3 grid(fblk, slices);
         float *nf = nullptr;
