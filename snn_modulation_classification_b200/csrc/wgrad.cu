@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) reduce_adam_kernel(const float *__restric
                                                           float *__restrict__ m_w, float *__restrict__ v_w,
                                                           float *__restrict__ m_b, float *__restrict__ v_b,
                                                           float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
-                                                          AdamScalars sc, __nv_bfloat16 *__restrict__ w_mma, int Cin, int KHKW) {
+                                                          AdamScalars sc, __nv_bfloat16 *__restrict__ w_mma, int Cin, int KHKW, int KW) {
     int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n_tot) return;
     float g = 0.f;
@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(256) reduce_adam_kernel(const float *__restric
                 __nv_bfloat16 hi = __float2bfloat16_rn(wv);
                 __nv_bfloat16 lo = __float2bfloat16_rn(wv - __bfloat162float(hi));
                 size_t o = (size_t)tap * (2 * Cin * Cout) + ((size_t)(ci >> 3) * 2 * Cout + co) * 8 + (ci & 7);
+                if (Cin == 1) o = ((size_t)(tap / KW) * 2 * Cout + co) * 8 + tap % KW;   // [kh][part][co][8 column shifts]
                 w_mma[o] = hi;
                 w_mma[o + (size_t)Cout * 8] = lo;
             }
@@ -301,7 +302,7 @@ int launch_wgrad(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st) 
                                                                o.m_w, o.v_w, o.m_b, o.v_b, a->grad_w, a->grad_b,
                                                                a->apply_update, sc,
                                                                L->quantized ? nullptr : reinterpret_cast<__nv_bfloat16 *>(L->weight_mma),
-                                                               L->Cin, L->KH * L->KW);
+                                                               L->Cin, L->KH * L->KW, L->KW);
     DCLL_LAUNCH_OK("reduce_adam_kernel");
     // reduce_adam_kernel refreshed weight_t and the tensor-core split itself; only the quantised image needs a pass
     if (a->apply_update && L->quantized) return sync_kernel_weights(L, st);

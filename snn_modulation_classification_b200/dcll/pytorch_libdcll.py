@@ -326,7 +326,7 @@ class ContinuousConv2D(nn.Module):
         desc.weight_t = _lib.ptr(self._wt)
         desc.quantized = 1 if self.quantized else 0
         if self.tensor_core_ok():
-            n_mma = 2 * self.weight.numel()
+            n_mma = max(2 * self.weight.numel(), 4096)     # single input channel: [4 row pairs][2][2][32][8]
             if self._wmma is None or self._wmma.numel() != n_mma or self._wmma.device != w.device:
                 self._wmma = torch.empty(n_mma, dtype=torch.bfloat16, device=w.device)
                 self._wt_key = None
@@ -336,10 +336,10 @@ class ContinuousConv2D(nn.Module):
             self._wt_key = key
 
     def tensor_core_ok(self):
-        """True when this core runs on the tcgen05 split-bf16 kernel (precision 'bf16x3' and an instantiated
-        shape: 7x7, 32 -> 32 channels).  Other shapes (e.g. layer 0 with a single input channel, K = 49) stay on
-        the FP32 FMA kernel by design."""
-        return (self.precision == 'bf16x3' and self.kernel_size == (7, 7) and self.in_channels == 32
+        """True when this core runs on the tcgen05 split-bf16 kernels (precision 'bf16x3' and an instantiated
+        shape: 7x7, {1, 32} -> 32 channels; the layer additionally needs pooling 1, checked by the library).
+        Other shapes stay on the FP32 FMA kernel."""
+        return (self.precision == 'bf16x3' and self.kernel_size == (7, 7) and self.in_channels in (1, 32)
                 and self.out_channels == 32)
 
     def _fill_core(self, desc, batch, height, width, x_mode):
@@ -375,8 +375,10 @@ class ContinuousConv2D(nn.Module):
         desc.eps1[0], desc.eps1[1] = _lib.ptr(e1), _lib.ptr(self._spare[1])
         desc.cur = 0
         if self.tensor_core_ok():
-            if self._e1mma is None or self._e1mma.numel() != 2 * e1.numel() or self._e1mma.device != e1.device:
-                self._e1mma = torch.empty(2 * e1.numel(), dtype=torch.bfloat16, device=e1.device)
+            # 16 bytes per position and group of 8 channels (a single channel fills the 8 slots with column shifts)
+            n_img = 2 * e1.numel() // self.in_channels * max(self.in_channels, 8)
+            if self._e1mma is None or self._e1mma.numel() != n_img or self._e1mma.device != e1.device:
+                self._e1mma = torch.empty(n_img, dtype=torch.bfloat16, device=e1.device)
             desc.eps1_mma = _lib.ptr(self._e1mma)
         arp = self._arp()
         desc.arp = _lib.ptr(arp) if arp is not None else None

@@ -24,7 +24,7 @@ def test_tc_forward_teacher_forced(im, B, arp):
     K, steps = 24, 4
     net, onet = build_pair("radio_ml_conv", (1,) + im, B, K, arp=arp, train=False)
     net.set_precision("bf16x3")
-    assert [s.dclllayer.i2h.tensor_core_ok() for s in net.dcll_slices] == [False, True, True]
+    assert [s.dclllayer.i2h.tensor_core_ok() for s in net.dcll_slices] == [True, True, True]
     g = torch.Generator().manual_seed(5)
     x = (torch.rand(steps, B, 1, *im, generator=g) < 0.1).float()
     net.reset()
