@@ -140,6 +140,24 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
                                  : "memory");
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
+            } else if (G::CIN == 1 && p.img) {
+                // layer 0: the forward's image already holds the pieces eps1[y][x-3 .. x+4] = our piece (r, c) at x = w0 + c
+                const int l384 = (warp - 4) * 32 + lane;
+                const size_t hw = (size_t)p.H * p.W;
+                const uint4 *src0 = p.img + (size_t)b * 2 * hw;
+                const uint32_t dst0 = smem_u32(sX);
+                for (int idx = l384; idx < 2 * G::XROWS * G::XCOLS; idx += G::LOADER_WARPS * 32) {
+                    const int c = idx % G::XCOLS;
+                    const int t = idx / G::XCOLS;
+                    const int r = t % G::XROWS, part = t / G::XROWS;
+                    const int gh = h0 - p.padH + r, gw = w0 + c;
+                    const bool in = gh >= 0 && gh < p.H && gw < p.W;
+                    const uint4 *src = in ? src0 + (size_t)part * hw + (size_t)gh * p.W + gw : src0;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + part * G::X_PART + r * G::X_RP + c * 16), "l"(src),
+                                 "r"(in ? 16u : 0u)
+                                 : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
             } else if (G::CIN == 32) {
                 // two positions per iteration (16 loads in flight)
                 for (int it = l96; it < G::XROWS * G::XCOLS; it += 2 * 96) {
@@ -326,7 +344,7 @@ int launch_wgrad_tc(const dcll_conv_layer *L, float *partial, int S, cudaStream_
     Geo g = geo_of(L);
     WgTcP p;
     p.g_u = L->g_u, p.eps1 = L->eps1[L->cur & 1], p.partial = partial;
-    p.img = (L->Cin == 32 && tc_supported(L)) ? reinterpret_cast<const uint4 *>(L->eps1_mma) : nullptr;
+    p.img = (tc_supported(L) && L->padW == 3) ? reinterpret_cast<const uint4 *>(L->eps1_mma) : nullptr;
     p.B = L->B, p.H = L->H, p.W = L->W, p.padH = L->padH, p.padW = L->padW, p.Hc = g.Hc, p.Wc = g.Wc;
     p.tiles_h = ceil_div(g.Hc, 16), p.tiles_w = ceil_div(g.Wc, 16);
     p.n_units = L->B * p.tiles_h * p.tiles_w;
