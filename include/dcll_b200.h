@@ -74,7 +74,8 @@ typedef struct dcll_conv_layer {
                                         With quantized && weight_mma the allocation must hold
                                         Cout*Cin*KH*KW more floats (dense dequantised copy)   */
     void *weight_mma;                /* device bf16 [KH*KW][Cin/8][2][Cout][8]: {hi,lo} split weights in the
-                                        tcgen05 B-operand layout; required when precision is
+                                        tcgen05 B-operand layout (Cin = 1: [(KH+1)/2][2][2][Cout][8], the 8 slots
+                                        being kernel columns; at least 4096 elements); required when precision is
                                         DCLL_PREC_BF16X3, refreshed together with weight_t       */
     float *bias;                     /* device [Cout]                                        */
     const float *wo, *bo;            /* device [K,F], [K]   frozen local read-out i2o        */
@@ -82,7 +83,8 @@ typedef struct dcll_conv_layer {
     float *eps0[2], *eps1[2];        /* device [B,Cin,H,W]  ping-pong state                  */
     void *eps1_mma;                  /* device bf16 [B][2][Cin/8][H][W][8]: {hi,lo} split image of the eps1 the last
                                         forward step produced, in the tcgen05 operand layout (16 bytes per position
-                                        and channel group).  Required (same byte size as one eps1 array) when
+                                        and channel group; with Cin = 1 the 8 slots hold eps1[y][x-3..x+4], i.e.
+                                        2*B*8*H*W elements).  Required (2*B*max(Cin,8)*H*W bf16) when
                                         precision is DCLL_PREC_BF16X3 and weight_mma is set; written by
                                         dcll_conv_step_fwd / dcll_conv_core_fwd, read by the convolution and by
                                         dcll_conv_step_bwd_update of the same timestep          */
