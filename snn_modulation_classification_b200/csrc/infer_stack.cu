@@ -84,8 +84,8 @@ __global__ void __launch_bounds__(st16::NT, 1) infer_stack16_kernel(const StackP
     }
     for (int i = tid; i < 3 * C; i += NT) bias_s[i] = p.bias[i / C][i % C];
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
-        mbar_init(acc_full, 1);
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 2);   // two MMA issuers commit
+        mbar_init(acc_full, 2);
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -210,8 +210,10 @@ __global__ void __launch_bounds__(st16::NT, 1) infer_stack16_kernel(const StackP
             }
             fence_async_smem();
             __syncthreads();
-            // ---- MMA issue (warp 0) / weight refill (one lane of warp 1)
-            if (warp == 0) {
+            // ---- MMA issue (warps 0 and 2, one M-tile each: a single issuing thread tops out at ~53 cycles per MMA, the
+            //      tensor pipe at ~44) / weight refill (one lane of warp 1)
+            if (warp == 0 || warp == 2) {
+                const int mt = warp >> 1;
                 int kh = 0, kw = 0;
                 for (int i = 0; i < NTAPS; ++i) {
                     const uint32_t g = gtap + i, s = g % NSTAGE;
@@ -219,8 +221,7 @@ __global__ void __launch_bounds__(st16::NT, 1) infer_stack16_kernel(const StackP
                     fence_after();
                     if (elected) {
                         const uint32_t b_tap = b_lo_base + ((s * TAP_BYTES) >> 4);
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
+                        {
                             const uint32_t a_tap = a_lo_base + (kh * ROWP + 8 * mt + kw);
                             const uint32_t d = tmem_base + mt * ACC_COLS;
 #pragma unroll
