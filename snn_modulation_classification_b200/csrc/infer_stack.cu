@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(st16::NT, 1) infer_stack16_kernel(const StackP
     // ---- thread-owned state: layer 0 (threads 0..255: one position), hidden layers (2 items x 8 channels each)
     const float c0_ts = p.tau_s[0][0], c0_as = p.alphas[0][0], c0_al = p.alpha[0][0], c0_tm = p.tau_m[0][0];
     float s0_e0 = 0.f, s0_e1 = 0.f;
-    if (tid < NPOS) s0_e0 = p.e0[0][(size_t)b * NPOS + pos], s0_e1 = p.e1[0][(size_t)b * NPOS + pos];
+    if (half == 1) s0_e0 = p.e0[0][(size_t)b * NPOS + pos], s0_e1 = p.e1[0][(size_t)b * NPOS + pos];   // owners: warps 8..15
     float he0[2][2][8], he1[2][2][8];
 #pragma unroll
     for (int l = 0; l < 2; ++l)
@@ -119,60 +119,66 @@ __global__ void __launch_bounds__(st16::NT, 1) infer_stack16_kernel(const StackP
     uint32_t gtap = 0;      // taps consumed so far (MMA warp / producer lane keep identical copies)
     uint32_t acc_uses = 0;  // completed accumulator hand-overs
 
-    for (int t = 0; t < p.Tc; ++t) {
-        // ================= layer 0: trace update, 7x7 conv of a single channel on the FMA pipe =================
-        const int2 cell = __ldg(p.cells + (size_t)t * p.B + b);
-        if (tid < NPOS) {
-            const float xin = (r == cell.x && c == cell.y) ? 1.f : 0.f;
-            s0_e0 = __fadd_rn(__fmul_rn(xin, c0_ts), __fmul_rn(c0_as, s0_e0));
-            s0_e1 = __fadd_rn(__fmul_rn(c0_al, s0_e1), __fmul_rn(s0_e0, c0_tm));
-            l0t[(r + 3) * 24 + c + 3] = s0_e1;
-        }
-        __syncthreads();
-        {
-            float acc[16];
+    // ---- layer 0 (single input channel, K = 49, FMA pipe), split so that timestep t+1 can run in the shadow of timestep t's MMAs
+    auto layer0_trace = [&](int tt) {                 // state owners (warps 8..15, one position each)
+        const int2 cell = __ldg(p.cells + (size_t)tt * p.B + b);
+        const float xin = (r == cell.x && c == cell.y) ? 1.f : 0.f;
+        s0_e0 = __fadd_rn(__fmul_rn(xin, c0_ts), __fmul_rn(c0_as, s0_e0));
+        s0_e1 = __fadd_rn(__fmul_rn(c0_al, s0_e1), __fmul_rn(s0_e0, c0_tm));
+        l0t[(r + 3) * 24 + c + 3] = s0_e1;
+    };
+    auto layer0_conv = [&](int tt, int hf) {          // this thread's position x output channels 16*hf .. 16*hf+15
+        float acc[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+        for (int k = 0; k < 16; ++k) acc[k] = 0.f;
 #pragma unroll 1
-            for (int kh = 0; kh < KH; ++kh) {
+        for (int kh = 0; kh < KH; ++kh) {
 #pragma unroll
-                for (int kw = 0; kw < KW; ++kw) {
-                    const float xv = l0t[(r + kh) * 24 + c + kw];
-                    const float4 *w4 = reinterpret_cast<const float4 *>(w0s + (kh * KW + kw) * C + half * 16);
+            for (int kw = 0; kw < KW; ++kw) {
+                const float xv = l0t[(r + kh) * 24 + c + kw];
+                const float4 *w4 = reinterpret_cast<const float4 *>(w0s + (kh * KW + kw) * C + hf * 16);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 w = w4[q];
-                        acc[4 * q] = fmaf(xv, w.x, acc[4 * q]), acc[4 * q + 1] = fmaf(xv, w.y, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(xv, w.z, acc[4 * q + 2]), acc[4 * q + 3] = fmaf(xv, w.w, acc[4 * q + 3]);
-                    }
+                for (int q = 0; q < 4; ++q) {
+                    const float4 w = w4[q];
+                    acc[4 * q] = fmaf(xv, w.x, acc[4 * q]), acc[4 * q + 1] = fmaf(xv, w.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(xv, w.z, acc[4 * q + 2]), acc[4 * q + 3] = fmaf(xv, w.w, acc[4 * q + 3]);
                 }
             }
-            float *__restrict__ pvout = p.pv[0] + ((size_t)t * p.B + b) * (C * NPOS);
-            float *__restrict__ arp0 = p.arp[0] ? p.arp[0] + ((size_t)b * C + half * 16) * NPOS + pos : nullptr;
-            float av[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) av[k] = arp0 ? arp0[k * NPOS] : 0.f;      // all refractory loads before any store
-            __align__(16) unsigned char sb[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int co = half * 16 + k;
-                float u = __fadd_rn(acc[k], bias_s[co]);
-                float a = 0.f;
-                if (arp0) {
-                    a = __fmul_rn(p.alpharp[0], av[k]);
-                    u = __fadd_rn(u, a);
-                }
-                const float sp = u > 0.f ? 1.f : 0.f;
-                av[k] = __fsub_rn(a, __fmul_rn(sp, p.wrp[0]));
-                sb[k] = (unsigned char)sp;
-                pvout[co * NPOS + pos] = sigmoidf_ref(u);
-            }
-            if (arp0) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) arp0[k * NPOS] = av[k];
-            }
-            *reinterpret_cast<uint4 *>(spk[0] + pos * C + half * 16) = *reinterpret_cast<const uint4 *>(sb);
         }
+        float *__restrict__ pvout = p.pv[0] + ((size_t)tt * p.B + b) * (C * NPOS);
+        float *__restrict__ arp0 = p.arp[0] ? p.arp[0] + ((size_t)b * C + hf * 16) * NPOS + pos : nullptr;
+        float av[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) av[k] = arp0 ? arp0[k * NPOS] : 0.f;      // all refractory loads before any store
+        __align__(16) unsigned char sb[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int co = hf * 16 + k;
+            float u = __fadd_rn(acc[k], bias_s[co]);
+            float a = 0.f;
+            if (arp0) {
+                a = __fmul_rn(p.alpharp[0], av[k]);
+                u = __fadd_rn(u, a);
+            }
+            const float sp = u > 0.f ? 1.f : 0.f;
+            av[k] = __fsub_rn(a, __fmul_rn(sp, p.wrp[0]));
+            sb[k] = (unsigned char)sp;
+            pvout[co * NPOS + pos] = sigmoidf_ref(u);
+        }
+        if (arp0) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) arp0[k * NPOS] = av[k];
+        }
+        *reinterpret_cast<uint4 *>(spk[0] + pos * C + hf * 16) = *reinterpret_cast<const uint4 *>(sb);
+    };
+    // timestep 0: everybody helps (512 threads = 256 positions x 2 channel halves)
+    if (p.Tc > 0) {
+        if (half == 1) layer0_trace(0);
+        __syncthreads();
+        layer0_conv(0, half);
+    }
+
+    for (int t = 0; t < p.Tc; ++t) {
         // ================= layers 1, 2: tcgen05 =================
 #pragma unroll
         for (int l = 0; l < 2; ++l) {
@@ -244,20 +250,28 @@ __global__ void __launch_bounds__(st16::NT, 1) infer_stack16_kernel(const StackP
                     mbar_expect_tx(full + s, TAP_BYTES);
                     bulk_g2s(sW + s * TAP_BYTES, w_src + (size_t)i * TAP_BYTES, TAP_BYTES, full + s);
                 }
+            } else if (l == 1 && half == 1 && t + 1 < p.Tc) {
+                // warps 8..15 are idle while layer 2 is multiplied: they run layer 0 of the NEXT timestep now (its spike
+                // buffer spk[0] was consumed by layer 1's prologue of this timestep; the __syncthreads at the top of
+                // the next layer-1 step publishes it)
+                layer0_trace(t + 1);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                layer0_conv(t + 1, 0);
+                layer0_conv(t + 1, 1);
             }
             gtap += NTAPS;
             __syncwarp();
-            // ---- epilogue: warps 0..7, thread = one position x 32 channels, 16 channels at a time
+            // ---- epilogue: all 16 warps (TMEM lane quarter = warp % 4), thread = one position x 16 channels
             mbar_wait(acc_full, acc_uses & 1);
             ++acc_uses;
             fence_after();
-            if (warp < 8) {
-                const int q = warp & 3, mt = warp >> 2;
+            {
+                const int q = warp & 3, mt = (warp >> 2) & 1;
                 const int m = q * 32 + lane, er = m >> 3, ec = 8 * mt + (m & 7), epos = er * HW + ec;
                 float *__restrict__ pvout = p.pv[l + 1] + ((size_t)t * p.B + b) * (C * NPOS);
                 float *__restrict__ arp = p.arp[l + 1] ? p.arp[l + 1] + (size_t)b * C * NPOS + epos : nullptr;
-#pragma unroll
-                for (int n0 = 0; n0 < C; n0 += 16) {
+                {
+                    const int n0 = 16 * (warp >> 3);
                     float av[16];
 #pragma unroll
                     for (int k = 0; k < 16; ++k) av[k] = arp ? arp[(n0 + k) * NPOS] : 0.f;   // loads first, stores last
@@ -292,7 +306,7 @@ __global__ void __launch_bounds__(st16::NT, 1) infer_stack16_kernel(const StackP
         fence_after();
     }
     // ---- state back to global
-    if (tid < NPOS) p.e0[0][(size_t)b * NPOS + pos] = s0_e0, p.e1[0][(size_t)b * NPOS + pos] = s0_e1;
+    if (half == 1) p.e0[0][(size_t)b * NPOS + pos] = s0_e0, p.e1[0][(size_t)b * NPOS + pos] = s0_e1;
 #pragma unroll
     for (int l = 0; l < 2; ++l)
 #pragma unroll
