@@ -120,12 +120,12 @@ static int g_layer = 0;  // layer index of the step being enqueued (profile key 
 int prof_layer() { return g_layer; }
 
 static int step_fwd(dcll_conv_layer *L, const void *x, const float *target, int loss_kind, int32_t *clout, float *loss_out,
-                    cudaStream_t st) {
+                    cudaStream_t st, const dcll_conv_layer *next = nullptr, bool trace_done = false) {
     prof_begin_layer_step();
     int rc;
     {
         ProfScope ps(KC_CONV_FWD, g_layer, st);
-        rc = launch_conv_fwd(L, x, st);
+        rc = launch_conv_fwd(L, x, st, next, trace_done);
     }
     if (rc != DCLL_OK) return rc;
     L->cur ^= 1;
@@ -394,7 +394,11 @@ extern "C" __attribute__((visibility("default"))) int dcll_net_window_stats(dcll
             const int it = iter0[l] + t + 1;                       // DCLLBase.forward :656
             const bool do_train = train_mode && it >= burnin;      // train_dcll :692
             int32_t *co = clout ? clout + ((size_t)t * n_layers + l) * L->B : nullptr;
-            int rc = step_fwd(L, x, do_train ? tgt : nullptr, do_train ? train[l].loss_kind : 0, co, nullptr, st);
+            // the trace update of layer l+1 rides in the epilogue of layer l's tensor-core convolution where that is free
+            const bool fuse_next = l + 1 < n_layers && tc_trace_fusable(L, &layers[l + 1]);
+            const bool trace_done = l > 0 && tc_trace_fusable(&layers[l - 1], L);
+            int rc = step_fwd(L, x, do_train ? tgt : nullptr, do_train ? train[l].loss_kind : 0, co, nullptr, st,
+                              fuse_next ? &layers[l + 1] : nullptr, trace_done);
             if (rc != DCLL_OK) return rc;
             if (hist && (it % hist_every) == 0 && hist_n[l] < hist_cap) {          // DCLLBase.forward :658-661
                 Geo g = geo_of(L);
