@@ -185,10 +185,18 @@ __global__ void __launch_bounds__(256) reduce_adam_kernel(const float *__restric
                                                           float *__restrict__ m_b, float *__restrict__ v_b,
                                                           float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
                                                           AdamScalars sc, __nv_bfloat16 *__restrict__ w_mma, int Cin, int KHKW, int KW) {
-    int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n_tot) return;
+    // CTA = 64 elements x 4 slices of the partial blocks (a single serial walk over ~150 blocks was pure load latency);
+    // the slices are combined in a fixed order, so the result stays bit-reproducible
+    __shared__ float red[4][64];
+    const int e = threadIdx.x & 63, sl = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + e;
     float g = 0.f;
-    for (int s = 0; s < S; ++s) g += __ldg(partial + (size_t)s * n_tot + i);
+    if (i < n_tot)
+        for (int s = sl; s < S; s += 4) g += __ldg(partial + (size_t)s * n_tot + i);
+    red[sl][e] = g;
+    __syncthreads();
+    if (sl != 0 || i >= n_tot) return;
+    g = ((red[0][e] + red[1][e]) + red[2][e]) + red[3][e];
     if (i < nW) {
         if (grad_w) grad_w[i] = g;
         if (apply) {
@@ -297,7 +305,7 @@ int launch_wgrad(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st) 
     AdamScalars sc = adam_scalars(a->adam_i2h, a->adam_i2h.step + 1);
     dcll_adam &o = a->adam_i2h;
     ProfScope ps(KC_ADAM, 0, st);
-    reduce_adam_kernel<<<ceil_div(p.n_tot, 256), 256, 0, st>>>(p.partial, p.S, p.n_tot, p.nW, L->Cout, g.CoutPad,
+    reduce_adam_kernel<<<ceil_div(p.n_tot, 64), 256, 0, st>>>(p.partial, p.S, p.n_tot, p.nW, L->Cout, g.CoutPad,
                                                                L->Cin * L->KH * L->KW, L->weight, L->weight_t, L->bias,
                                                                o.m_w, o.v_w, o.m_b, o.v_b, a->grad_w, a->grad_b,
                                                                a->apply_update, sc,
