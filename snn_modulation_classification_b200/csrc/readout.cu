@@ -287,11 +287,12 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(const float *__restric
     }
 }
 
-// Packed variant of the sweep above: thread = TWO adjacent feature columns, every multiply-add is one FFMA2
-// (fma.rn.f32x2: two independent IEEE FMAs, so each lane-half is bit-identical to the scalar kernel).  The scalar
-// kernel is instruction-issue bound (64 instructions per sample-feature, issue slots 67 % busy at 3.4 TB/s);
-// here a sample costs 12 broadcast LDS.128 (g rows stored duplicated {g,g}) + 24 FFMA2 for two features.
-// Needs an even F and 8-byte aligned rows.
+// Packed variant of the non-fused sweep above (g_u only): thread = TWO adjacent feature columns, every multiply-add is one
+// FFMA2 (fma.rn.f32x2: two independent IEEE FMAs, so each lane-half is bit-identical to the scalar kernel).  The scalar
+// kernel is instruction-issue bound (64 instructions per sample-feature, issue slots 67 % busy at 3.4 TB/s); here a
+// sample costs 12 broadcast LDS.128 (g rows stored duplicated {g,g}) + 24 FFMA2 for two features.  Needs an even F and
+// 8-byte aligned rows.  (With the output_ gradient fused in it needs 179 registers -- one CTA per SM, slower than the
+// scalar fused sweep -- so the output layer keeps readout_bwd_kernel<., true>.)
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
                        rc = *reinterpret_cast<unsigned long long *>(&c), rd;
@@ -299,46 +300,30 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return *reinterpret_cast<float2 *>(&rd);
 }
 
-template <int KMAX, bool WOUT>
-__global__ void __launch_bounds__(256, WOUT ? 1 : 3) readout_bwd2_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
-                                                           const float *__restrict__ g_o, const float *__restrict__ g_o2, int B,
-                                                           int F, int K, int b_per_blk, float *__restrict__ g_u,
-                                                           float *__restrict__ wout, float *__restrict__ bout,
-                                                           float *__restrict__ m_w, float *__restrict__ v_w,
-                                                           float *__restrict__ m_b, float *__restrict__ v_b,
-                                                           float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
-                                                           AdamScalars sc) {
+template <int KMAX>
+__global__ void __launch_bounds__(256, 3) readout_bwd2_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
+                                                              const float *__restrict__ g_o, int B, int F, int K, int b_per_blk,
+                                                              float *__restrict__ g_u) {
     __shared__ __align__(16) float2 gd[64][KMAX];                 // {g,g}
-    __shared__ __align__(16) float2 gd2[WOUT ? 64 : 1][KMAX];
     static_assert(KMAX % 2 == 0, "float4 rows of two duplicated values");
     const int tid = threadIdx.x;
     const int f = 2 * (blockIdx.x * 256 + tid);
     const bool fok = f < F;
-    float2 w[KMAX], acc[WOUT ? KMAX : 1];
+    float2 w[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) w[k] = (k < K && fok) ? __ldg(reinterpret_cast<const float2 *>(wo + (size_t)k * F + f)) : make_float2(0.f, 0.f);
-    if (WOUT) {
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) acc[k] = make_float2(0.f, 0.f);
-    }
-    float bsum = 0.f;
     const int b_begin = blockIdx.y * b_per_blk, b_end = min(B, b_begin + b_per_blk);
     for (int b0 = b_begin; b0 < b_end; b0 += 64) {
         const int nb = min(64, b_end - b0);
         __syncthreads();
         for (int i = tid; i < 64 * KMAX; i += 256) {
             int bb = i / KMAX, k = i - bb * KMAX;
-            const bool ok = bb < nb && k < K;
-            const float g = ok ? g_o[(size_t)(b0 + bb) * K + k] : 0.f;
+            const float g = (bb < nb && k < K) ? g_o[(size_t)(b0 + bb) * K + k] : 0.f;
             gd[bb][k] = make_float2(g, g);
-            if (WOUT) {
-                const float g2 = ok ? g_o2[(size_t)(b0 + bb) * K + k] : 0.f;
-                gd2[bb][k] = make_float2(g2, g2);
-            }
         }
         __syncthreads();
         if (fok) {
-            constexpr int UB = 8;   // samples in flight per thread
+            constexpr int UB = 8;   // samples in flight per thread (16, or a cp.async prefetch ring, were not faster)
             const float *pvp = pv + (size_t)b0 * F + f;
             float *gup = g_u + (size_t)b0 * F + f;
             for (int bb = 0; bb < nb; bb += UB) {
@@ -360,45 +345,7 @@ __global__ void __launch_bounds__(256, WOUT ? 1 : 3) readout_bwd2_kernel(const f
                     float2 o;
                     o.x = s.x * (1.f - pvv[u].x) * pvv[u].x, o.y = s.y * (1.f - pvv[u].y) * pvv[u].y;
                     *reinterpret_cast<float2 *>(gup + (size_t)(bb + u) * F) = o;
-                    if (WOUT) {
-                        const float4 *h4 = reinterpret_cast<const float4 *>(gd2[bb + u]);
-#pragma unroll
-                        for (int k = 0; k < KMAX; k += 2) {
-                            const float4 g = h4[k >> 1];
-                            acc[k] = ffma2(make_float2(g.x, g.y), pvv[u], acc[k]);
-                            acc[k + 1] = ffma2(make_float2(g.z, g.w), pvv[u], acc[k + 1]);
-                        }
-                    }
                 }
-            }
-        }
-        if (WOUT && blockIdx.x == 0 && tid < K)
-            for (int bb = 0; bb < nb; ++bb) bsum += gd2[bb][tid].x;
-    }
-    if (WOUT) {
-        if (fok) {
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                if (k < K) {
-                    size_t o = (size_t)k * F + f;
-                    if (grad_w) *reinterpret_cast<float2 *>(grad_w + o) = acc[k];
-                    if (apply) {
-                        float2 wv = *reinterpret_cast<float2 *>(wout + o), m = *reinterpret_cast<float2 *>(m_w + o),
-                               v = *reinterpret_cast<float2 *>(v_w + o);
-                        adam_elem(wv.x, acc[k].x, m.x, v.x, sc);
-                        adam_elem(wv.y, acc[k].y, m.y, v.y, sc);
-                        *reinterpret_cast<float2 *>(wout + o) = wv, *reinterpret_cast<float2 *>(m_w + o) = m,
-                                                    *reinterpret_cast<float2 *>(v_w + o) = v;
-                    }
-                }
-            }
-        }
-        if (blockIdx.x == 0 && tid < K) {
-            if (grad_b) grad_b[tid] = bsum;
-            if (apply) {
-                float wv = bout[tid], m = m_b[tid], v = v_b[tid];
-                adam_elem(wv, bsum, m, v, sc);
-                bout[tid] = wv, m_b[tid] = m, v_b[tid] = v;
             }
         }
     }
@@ -574,13 +521,13 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
     char *base = (char *)L->workspace;
     const float *g_o = (const float *)(base + ws.off_go), *g_o2 = (const float *)(base + ws.off_go2);
     DCLL_REQUIRE(L->K <= 32, DCLL_EUNSUPPORTED, "target_size %d > 32 unsupported in the backward read-out", L->K);
-    // packed (two features per thread, FFMA2) when rows are 8-byte aligned, else the scalar kernel
-    const bool packed = (g.F % 2 == 0) && (((uintptr_t)L->pv | (uintptr_t)L->wo | (uintptr_t)L->g_u | (uintptr_t)L->wout |
-                                            (uintptr_t)a->adam_out.m_w | (uintptr_t)a->adam_out.v_w | (uintptr_t)a->grad_wout) % 8 == 0);
+    // g_u alone: packed kernel (two features per thread, FFMA2) when rows are 8-byte aligned, else the scalar kernel.
+    // Output layer with a large F: ONE scalar sweep over pv serves g_u and gWout (+ Adam); with a small F the output_
+    // gradient gets its own kernel below.
+    const bool packed = (g.F % 2 == 0) && (((uintptr_t)L->pv | (uintptr_t)L->wo | (uintptr_t)L->g_u) % 8 == 0);
     AdamScalars sc = {};
     const bool fused_out = L->output_layer && ceil_div(g.F, 256) >= 2 * 148;
-    // (the packed kernel needs 179 registers with the fused output_ gradient: one CTA per SM, slower than the scalar sweep)
-    const int fblk = ceil_div(g.F, (packed && !fused_out) ? 512 : 256);   // large F: one sweep over pv serves g_u and gWout
+    const int fblk = ceil_div(g.F, (packed && !fused_out) ? 512 : 256);
     if (L->output_layer && !fused_out) {
         // small F: the output_ gradient gets its own kernel (batch split over warps inside the CTA)
         sc = adam_scalars(a->adam_out, a->adam_out.step + 1);
@@ -590,11 +537,8 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
                                                       a->grad_wout, a->grad_bout, a->apply_update, sc);
         DCLL_LAUNCH_OK("wout_grad_adam_kernel");
     }
-#define RB_LAUNCH(KM, WO, GRID, BPER, ...)                                                                                     \
-    do {                                                                                                                      \
-        if (packed && !WO) readout_bwd2_kernel<KM, WO><<<GRID, 256, 0, st>>>(L->pv, L->wo, g_o, WO ? g_o2 : nullptr, L->B, g.F, L->K, BPER, L->g_u, __VA_ARGS__); \
-        else readout_bwd_kernel<KM, WO><<<GRID, 256, 0, st>>>(L->pv, L->wo, g_o, WO ? g_o2 : nullptr, L->B, g.F, L->K, BPER, L->g_u, __VA_ARGS__);         \
-    } while (0)
+#define RB_LAUNCH(KM, WO, GRID, BPER, ...) \
+    readout_bwd_kernel<KM, WO><<<GRID, 256, 0, st>>>(L->pv, L->wo, g_o, WO ? g_o2 : nullptr, L->B, g.F, L->K, BPER, L->g_u, __VA_ARGS__)
     if (fused_out) {
         // the output_ gradient reduces over the whole batch inside one thread: no batch slicing
         sc = adam_scalars(a->adam_out, a->adam_out.step + 1);
@@ -613,7 +557,11 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
         slices = ceil_div(L->B, b_per);
         dim3 grid(fblk, slices);
         float *nf = nullptr;
-        if (L->K <= 16)
+        if (packed) {
+            if (L->K <= 16) readout_bwd2_kernel<16><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u);
+            else if (L->K <= 24) readout_bwd2_kernel<24><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u);
+            else readout_bwd2_kernel<32><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u);
+        } else if (L->K <= 16)
             RB_LAUNCH(16, false, grid, b_per, nf, nf, nf, nf, nf, nf, nf, nf, 0, sc);
         else if (L->K <= 24)
             RB_LAUNCH(24, false, grid, b_per, nf, nf, nf, nf, nf, nf, nf, nf, 0, sc);
