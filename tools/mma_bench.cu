@@ -86,6 +86,72 @@ __global__ void __launch_bounds__(256, 1) bench(Cfg c, long long *out) {
     if (warp == 7) tmem_dealloc(tmem, 512);
 }
 
+// ---- CTA-pair variant: tcgen05.mma.cta_group::2, M = 256 (128 rows of A from each CTA's shared memory), each CTA holds half of B.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) bench2(Cfg c, long long *out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar[2];
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u + i;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1), mbar_init(bar + 1, 1);
+        mbar_fence_init();
+    }
+    if (warp == 7) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    fence_after();
+    const uint32_t tmem = slot;
+    long long t0 = 0, t1 = 0;
+    if (warp == 0) {
+        const uint32_t elected = elect_one();
+        const uint32_t a_base = desc_lo(smem_u32(smem), 7744), b_base = desc_lo(smem_u32(smem + 128 * 1024), 1024);
+        constexpr uint32_t A_HI = desc_hi(352), B_HI = desc_hi(128);
+        const uint32_t i64 = idesc_bf16(256, 64, false, false), i32 = idesc_bf16(256, 32, false, false);
+        const uint32_t iN = idesc_bf16(256, c.nsize, false, false);
+        __syncwarp();
+        t0 = clock64();
+        if (elected && rank == 0) {
+            const uint32_t sh_mask = c.shift ? 31u : 0u;
+            const uint32_t lo_off = c.pair ? (32768 >> 4) : 0;
+#pragma unroll 1
+            for (int k = 0; k < c.n; k += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t kk = k + u;
+                    const uint32_t sh = (kk >> 1) & sh_mask;
+                    const uint64_t a = desc(A_HI, a_base + sh + ((u & 1) ? lo_off : 0));
+                    const uint64_t b = desc(B_HI, b_base + (sh & 7) * 256);
+                    const uint32_t id = c.pair ? ((u & 1) ? i32 : i64) : iN;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem),
+                        "l"(a), "l"(b), "r"(id), "r"(1u)
+                        : "memory");
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                         "h"((uint16_t)3)
+                         : "memory");
+        }
+        __syncwarp();
+        mbar_wait(bar, 0);          // both CTAs: the multicast commit arrives on each CTA's barrier
+        t1 = clock64();
+    }
+    if (lane == 0 && warp == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+    fence_before();
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 7) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 int main() {
     long long *out;
     cudaMallocManaged(&out, 64);
@@ -110,6 +176,19 @@ int main() {
         }
         printf("%6d %5d %4d %5d %5d %7d %6d %3d | %.1f\n", c.n, c.n_acc, c.pair, c.nsize, c.shift, c.issuers, c.commit_every, c.swz,
                (double)out[0] / c.n);
+    }
+    cudaFuncSetAttribute(bench2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    printf("\nCTA pairs (cta_group::2, M = 256 = 128 rows per CTA, half of B per CTA), 148 CTAs = 74 pairs\n");
+    const Cfg c2[] = {{4096, 1, 0, 64, 1, 1, 0, 0}, {4096, 1, 0, 32, 1, 1, 0, 0}, {4096, 1, 0, 128, 1, 1, 0, 0}, {4096, 1, 1, 64, 1, 1, 0, 0}};
+    for (const Cfg &c : c2) {
+        for (int rep = 0; rep < 2; ++rep) {
+            bench2<<<148, 256, 200 * 1024>>>(c, out);
+            if (cudaDeviceSynchronize() != cudaSuccess) {
+                printf("CUDA error: %s\n", cudaGetErrorString(cudaGetLastError()));
+                return 1;
+            }
+        }
+        printf("pair=%d N=%3d | %.1f cycles per M=256 MMA\n", c.pair, c.nsize, (double)out[0] / c.n);
     }
     return 0;
 }
