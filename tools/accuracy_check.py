@@ -35,7 +35,22 @@ def run(mode, res=16, B=256, T=300, burnin=50, n_train=24, n_test=4, K=24, lr=1e
         accs.append(net.accuracy(tgt))
     return np.mean(accs, axis=0), np.mean(accs_train[-4:], axis=0)
 
+def seed_sweep(snr=6.0, seeds=(1, 2, 3, 4, 5)):
+    """Mid-SNR accuracy over several network-initialisation seeds per mode: training is chaotic, so single runs of the
+    two modes (or of one mode with another summation order) differ by points; the distributions are what compare."""
+    out = {}
+    for mode in ("fp32", "bf16x3"):
+        accs = np.array([run(mode, snr=snr, seed=sd)[0] for sd in seeds])
+        out[mode] = dict(test_acc_per_layer_by_seed=[[round(float(a), 4) for a in r] for r in accs],
+                         mean=[round(float(a), 4) for a in accs.mean(0)], std=[round(float(a), 4) for a in accs.std(0)])
+    print(json.dumps(dict(config="seed sweep: radio_ml_conv 16x16, B=256, T=300, 24 training windows, 1024 held-out samples, "
+                                 "%g dB, seeds %s" % (snr, list(seeds)), **out)), flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "seeds":
+        seed_sweep()
+        sys.exit(0)
     for snr, n_train in ((18.0, 24), (6.0, 24), (0.0, 24)):
         out = {}
         for mode in ("fp32", "bf16x3"):
