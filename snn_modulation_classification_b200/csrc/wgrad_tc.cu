@@ -20,7 +20,7 @@
 //   (eps1 straight from the bf16 operand image the forward wrote, by cp.async; g_u converted fp32 -> bf16 hi/lo) while
 //   two issuer warps (kernel columns 0..3 / 4..6) issue the MMAs of the current tile; mbarriers (full: loader
 //   arrivals, empty: tcgen05.commit of both issuers).
-// Partials (one per CTA) are reduced in fixed order by reduce_adam_kernel, exactly like the FP32 path.
+// Partials (one per CTA pair) are reduced in fixed order by reduce_adam_kernel, exactly like the FP32 path.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -281,11 +281,10 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
         if (elected) commit(done);
         __syncwarp();
     }
-    // ---- drain: zero this CTA's partial (the other group's kernel rows stay zero), then, once every MMA has completed
-    //      (`done` flips), add the two accumulator halves and scatter into the [Cout,Cin,KH,KW] layout
-    float *out = p.partial + (size_t)blockIdx.x * p.n_tot;
-    for (int i = tid; i < p.n_tot; i += G::NT) out[i] = 0.f;
-    __syncthreads();
+    // ---- drain: once every MMA has completed (`done` flips), add the two accumulator halves and scatter into the
+    //      [Cout,Cin,KH,KW] layout.  The two CTAs of a pair own complementary kernel rows and SHARE one partial block
+    //      (every element is written by exactly one of them: no zero fill, half as many blocks to reduce).
+    float *out = p.partial + (size_t)(G::NG == 2 ? blockIdx.x >> 1 : blockIdx.x) * p.n_tot;
     mbar_wait(done, 0);
     fence_after();
     {
@@ -336,7 +335,7 @@ bool wgrad_tc_supported(const dcll_conv_layer *L) {
 int wgrad_tc_splits(const dcll_conv_layer *L) {
     Geo g = geo_of(L);
     int n_units = L->B * ceil_div(g.Hc, 16) * ceil_div(g.Wc, 16);
-    if (L->Cin == 32) return 2 * (n_units < 74 ? n_units : 74);   // CTA pairs: one kernel-row group each
+    if (L->Cin == 32) return n_units < 74 ? n_units : 74;   // partial blocks = CTA pairs (one kernel-row group per CTA)
     return n_units < 148 ? n_units : 148;
 }
 
@@ -355,7 +354,7 @@ int launch_wgrad_tc(const dcll_conv_layer *L, float *partial, int S, cudaStream_
         DCLL_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgTcGeoT<1>::SMEM));
         configured = true;
     }
-    if (L->Cin == 32) wgrad_tc_kernel<32><<<S, 512, WgTcGeoT<32>::SMEM, st>>>(p);
+    if (L->Cin == 32) wgrad_tc_kernel<32><<<2 * S, 512, WgTcGeoT<32>::SMEM, st>>>(p);
     else wgrad_tc_kernel<1><<<S, 512, WgTcGeoT<1>::SMEM, st>>>(p);
     DCLL_LAUNCH_OK("wgrad_tc_kernel");
     return DCLL_OK;
