@@ -294,15 +294,39 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
         const int ci = G::CIN == 32 ? (m & 31) : 0;
         const bool lane_ok = G::CIN == 32 ? true : ((m & 7) < G::KW);
         const int kh = G::DY * grp + dy;
-        for (int a = (warp >> 2); a < G::NACC; a += 4) {
-            uint32_t v[32], v2[32];
-            ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS, v);
-            ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS + G::COUT, v2);
-            const int kw = G::CIN == 32 ? a : (m & 7);
-            if (kh < G::KH && lane_ok) {
+        if (G::CIN == 32) {
+            // A thread holds gW[co = 0..31][ci][kh][kw] for its (ci, kh): 196 bytes apart between lanes in the output.  The tile
+            // buffers are idle now (all MMAs done), so the block is staged there as [co][ci][dy][kw] (pitch 29 floats per
+            // (co,ci): conflict-free) and written out in runs of DY*KW contiguous floats.
+            float *stg = reinterpret_cast<float *>(smem);
+            constexpr int RUN = G::DY * G::KW, PITCH = RUN + 1;          // 28 values (+1 pad) per (co, ci)
+            static_assert(G::COUT * G::CIN * PITCH * 4 <= 2 * G::BUF, "staging fits the tile buffers");
+            for (int a = (warp >> 2); a < G::NACC; a += 4) {
+                uint32_t v[32], v2[32];
+                ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS, v);
+                ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS + G::COUT, v2);
 #pragma unroll
                 for (int co = 0; co < 32; ++co)
-                    out[((size_t)(co * G::CIN + ci) * G::KH + kh) * G::KW + kw] = __uint_as_float(v[co]) + __uint_as_float(v2[co]);
+                    stg[(co * G::CIN + ci) * PITCH + dy * G::KW + a] = __uint_as_float(v[co]) + __uint_as_float(v2[co]);
+            }
+            __syncthreads();
+            const int rows_valid = min(G::DY, G::KH - G::DY * grp);      // kernel rows of this group that exist (4 or 3)
+            const int run = rows_valid * G::KW;
+            for (int i = tid; i < G::COUT * G::CIN * RUN; i += G::NT) {
+                const int cc = i / RUN, e = i - cc * RUN;                // cc = co * CIN + ci
+                if (e < run) out[(size_t)cc * (G::KH * G::KW) + G::DY * grp * G::KW + e] = stg[cc * PITCH + e];
+            }
+        } else {
+            for (int a = (warp >> 2); a < G::NACC; a += 4) {
+                uint32_t v[32], v2[32];
+                ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS, v);
+                ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS + G::COUT, v2);
+                const int kw = m & 7;
+                if (kh < G::KH && lane_ok) {
+#pragma unroll
+                    for (int co = 0; co < 32; ++co)
+                        out[((size_t)(co * G::CIN + ci) * G::KH + kh) * G::KW + kw] = __uint_as_float(v[co]) + __uint_as_float(v2[co]);
+                }
             }
         }
     }
