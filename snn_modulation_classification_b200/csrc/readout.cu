@@ -290,9 +290,8 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(const float *__restric
 // Packed variant of the non-fused sweep above (g_u only): thread = TWO adjacent feature columns, every multiply-add is one
 // FFMA2 (fma.rn.f32x2: two independent IEEE FMAs, so each lane-half is bit-identical to the scalar kernel).  The scalar
 // kernel is instruction-issue bound (64 instructions per sample-feature, issue slots 67 % busy at 3.4 TB/s); here a
-// sample costs 12 broadcast LDS.128 (g rows stored duplicated {g,g}) + 24 FFMA2 for two features.  Needs an even F and
-// 8-byte aligned rows.  (With the output_ gradient fused in it needs 179 registers -- one CTA per SM, slower than the
-// scalar fused sweep -- so the output layer keeps readout_bwd_kernel<., true>.)
+// sample costs 6 broadcast LDS.128 + 24 FFMA2 for two features.  Needs an even F and 8-byte aligned rows.  On the output
+// layer it is paired with wout_grad_adam2_kernel (a fused packed sweep needs 179 registers -- one CTA per SM).
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
                        rc = *reinterpret_cast<unsigned long long *>(&c), rd;
@@ -300,12 +299,21 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return *reinterpret_cast<float2 *>(&rd);
 }
 
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
 template <int KMAX>
 __global__ void __launch_bounds__(256, 3) readout_bwd2_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
                                                               const float *__restrict__ g_o, int B, int F, int K, int b_per_blk,
                                                               float *__restrict__ g_u) {
-    __shared__ __align__(16) float2 gd[64][KMAX];                 // {g,g}
-    static_assert(KMAX % 2 == 0, "float4 rows of two duplicated values");
+    // g rows are read back as broadcast LDS.128 (4 k per load) and enter the FFMA2 as a scalar-broadcast operand: ptxas folds
+    // the {g,g} pair into `FFMA2 Rd, Rg.F32, Rw.F32x2, Rs.F32x2`.  (Storing the rows duplicated {g,g} doubled the LDS traffic
+    // and made the sweep L1TEX-bound: ncu l1tex throughput 74 %, short-scoreboard stalls above the DRAM ones.)
+    __shared__ __align__(16) float gd[64][KMAX];
+    static_assert(KMAX % 4 == 0, "float4 rows");
     const int tid = threadIdx.x;
     const int f = 2 * (blockIdx.x * 256 + tid);
     const bool fok = f < F;
@@ -318,35 +326,45 @@ __global__ void __launch_bounds__(256, 3) readout_bwd2_kernel(const float *__res
         __syncthreads();
         for (int i = tid; i < 64 * KMAX; i += 256) {
             int bb = i / KMAX, k = i - bb * KMAX;
-            const float g = (bb < nb && k < K) ? g_o[(size_t)(b0 + bb) * K + k] : 0.f;
-            gd[bb][k] = make_float2(g, g);
+            gd[bb][k] = (bb < nb && k < K) ? g_o[(size_t)(b0 + bb) * K + k] : 0.f;
         }
         __syncthreads();
         if (fok) {
             constexpr int UB = 8;   // samples in flight per thread (16, or a cp.async prefetch ring, were not faster)
+            const size_t rowF = (size_t)F;
             const float *pvp = pv + (size_t)b0 * F + f;
             float *gup = g_u + (size_t)b0 * F + f;
-            for (int bb = 0; bb < nb; bb += UB) {
-                float2 pvv[UB];
+            const float2 one2 = make_float2(1.f, 1.f), neg2 = make_float2(-1.f, -1.f);
+            auto sample = [&](int bb, float2 p) {
+                float2 s = make_float2(0.f, 0.f);
+                const float4 *g4 = reinterpret_cast<const float4 *>(gd[bb]);
 #pragma unroll
-                for (int u = 0; u < UB; ++u)
-                    pvv[u] = (bb + u < nb) ? __ldg(reinterpret_cast<const float2 *>(pvp + (size_t)(bb + u) * F)) : make_float2(0.f, 0.f);
-#pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    if (bb + u >= nb) break;
-                    float2 s = make_float2(0.f, 0.f);
-                    const float4 *g4 = reinterpret_cast<const float4 *>(gd[bb + u]);
-#pragma unroll
-                    for (int k = 0; k < KMAX; k += 2) {
-                        const float4 g = g4[k >> 1];
-                        s = ffma2(make_float2(g.x, g.y), w[k], s);
-                        s = ffma2(make_float2(g.z, g.w), w[k + 1], s);
-                    }
-                    float2 o;
-                    o.x = s.x * (1.f - pvv[u].x) * pvv[u].x, o.y = s.y * (1.f - pvv[u].y) * pvv[u].y;
-                    *reinterpret_cast<float2 *>(gup + (size_t)(bb + u) * F) = o;
+                for (int k = 0; k < KMAX; k += 4) {
+                    const float4 g = g4[k >> 2];
+                    s = ffma2(make_float2(g.x, g.x), w[k], s);
+                    s = ffma2(make_float2(g.y, g.y), w[k + 1], s);
+                    s = ffma2(make_float2(g.z, g.z), w[k + 2], s);
+                    s = ffma2(make_float2(g.w, g.w), w[k + 3], s);
                 }
+                // s * (1 - pv) * pv, each lane-half rounded exactly like the scalar expression (1 - pv == fma(pv, -1, 1))
+                return fmul2(fmul2(s, ffma2(p, neg2, one2)), p);
+            };
+            int bb = 0;
+            // full groups: no per-load predicates, row pointers advance by F (the predicated form spent ~12 instructions
+            // per load on 64-bit address arithmetic and made the sweep as issue-bound as it is memory-bound)
+            for (; bb + UB <= nb; bb += UB) {
+                float2 pvv[UB];
+                const float *p = pvp;
+#pragma unroll
+                for (int u = 0; u < UB; ++u, p += rowF) pvv[u] = __ldg(reinterpret_cast<const float2 *>(p));
+                pvp = p;
+                float *q = gup;
+#pragma unroll
+                for (int u = 0; u < UB; ++u, q += rowF) *reinterpret_cast<float2 *>(q) = sample(bb + u, pvv[u]);
+                gup = q;
             }
+            for (; bb < nb; ++bb, pvp += rowF, gup += rowF)
+                *reinterpret_cast<float2 *>(gup) = sample(bb, __ldg(reinterpret_cast<const float2 *>(pvp)));
         }
     }
 }
@@ -418,6 +436,127 @@ __global__ void __launch_bounds__(256) wout_grad_adam_kernel(const float *__rest
             float wv = bout[k], m = m_b[k], v = v_b[k];
             adam_elem(wv, gsum, m, v, sc);
             bout[k] = wv, m_b[k] = m, v_b[k] = v;
+        }
+    }
+}
+
+// output_ gradient + Adam for LARGE feature counts (128x128 planes: F = 524 288), the companion of readout_bwd2_kernel on
+// the output layer.  The fused scalar sweep (readout_bwd_kernel<., true>) keeps the whole batch serial in one thread with
+// 48 scalar FMAs per sample-feature and a 2.3-wave grid (0.27 ms against a 0.09 ms HBM floor); splitting it into the packed
+// g_u sweep plus this kernel re-reads pv once (134 MB, 0.02 ms) but both halves run packed and with >= 4 waves.
+// CTA = 128 feature PAIRS x 2 batch halves: a thread accumulates gWout[k][f, f+1] over its half of every 64-sample chunk
+// (FFMA2, g rows duplicated {g,g} in shared memory), the halves are combined in fixed order (first half + second half)
+// through shared memory, and the Adam tail is split over the two halves by k.
+template <int KMAX>
+__global__ void __launch_bounds__(256, 2) wout_grad_adam2_kernel(const float *__restrict__ pv, const float *__restrict__ g_o2, int B,
+                                                                 int F, int K, float *__restrict__ wout, float *__restrict__ bout,
+                                                                 float *__restrict__ m_w, float *__restrict__ v_w,
+                                                                 float *__restrict__ m_b, float *__restrict__ v_b,
+                                                                 float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
+                                                                 AdamScalars sc) {
+    __shared__ __align__(16) float gd[64][KMAX];                  // broadcast LDS.128 rows, see readout_bwd2_kernel
+    __shared__ __align__(16) float2 red[KMAX][128];
+    static_assert(KMAX % 8 == 0, "the Adam tail walks each half's k range in groups of 4 or 6");
+    const int tid = threadIdx.x, pair = tid & 127, half = tid >> 7;
+    const int f = 2 * (blockIdx.x * 128 + pair);
+    const bool fok = f < F;
+    float2 acc[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) acc[k] = make_float2(0.f, 0.f);
+    for (int b0 = 0; b0 < B; b0 += 64) {
+        const int nb = min(64, B - b0);
+        __syncthreads();
+        for (int i = tid; i < 64 * KMAX; i += 256) {
+            int bb = i / KMAX, k = i - bb * KMAX;
+            gd[bb][k] = (bb < nb && k < K) ? g_o2[(size_t)(b0 + bb) * K + k] : 0.f;
+        }
+        __syncthreads();
+        if (fok) {
+            constexpr int UB = 8;
+            const int lo = half * 32, hi = min(nb, lo + 32);
+            const size_t rowF = (size_t)F;
+            const float *pvp = pv + (size_t)(b0 + lo) * F + f;
+            auto sample = [&](int bb, float2 p) {
+                const float4 *g4 = reinterpret_cast<const float4 *>(gd[bb]);
+#pragma unroll
+                for (int k = 0; k < KMAX; k += 4) {
+                    const float4 g = g4[k >> 2];
+                    acc[k] = ffma2(make_float2(g.x, g.x), p, acc[k]);
+                    acc[k + 1] = ffma2(make_float2(g.y, g.y), p, acc[k + 1]);
+                    acc[k + 2] = ffma2(make_float2(g.z, g.z), p, acc[k + 2]);
+                    acc[k + 3] = ffma2(make_float2(g.w, g.w), p, acc[k + 3]);
+                }
+            };
+            int bb = lo;
+            for (; bb + UB <= hi; bb += UB) {                      // full groups: unpredicated loads, pointer increments
+                float2 pvv[UB];
+                const float *p = pvp;
+#pragma unroll
+                for (int u = 0; u < UB; ++u, p += rowF) pvv[u] = __ldg(reinterpret_cast<const float2 *>(p));
+                pvp = p;
+#pragma unroll
+                for (int u = 0; u < UB; ++u) sample(bb + u, pvv[u]);
+            }
+            for (; bb < hi; ++bb, pvp += rowF) sample(bb, __ldg(reinterpret_cast<const float2 *>(pvp)));
+        }
+    }
+    // combine the halves in fixed order; afterwards red[k][pair] holds the gradient of features (f, f+1)
+    if (half == 1) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) red[k][pair] = acc[k];
+    }
+    __syncthreads();
+    if (half == 0) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            const float2 o = red[k][pair];
+            red[k][pair] = make_float2(__fadd_rn(acc[k].x, o.x), __fadd_rn(acc[k].y, o.y));
+        }
+    }
+    __syncthreads();
+    if (fok) {
+        // Adam tail: this half's k range in groups of TB rows, every load of a group issued before its first store (the
+        // accumulators are dead by now, so TB * 3 float2 of state fit the registers)
+        constexpr int KH = KMAX / 2, TB = (KH % 6 == 0) ? 6 : 4;
+        static_assert(KH % TB == 0, "tail groups");
+#pragma unroll 1
+        for (int kk = 0; kk < KH; kk += TB) {
+            const int k0 = half * KH + kk;
+            float2 g[TB], w[TB], m[TB], v[TB];
+#pragma unroll
+            for (int j = 0; j < TB; ++j) {
+                const size_t o = (size_t)(k0 + j) * F + f;
+                g[j] = red[k0 + j][pair];
+                if (apply && k0 + j < K) {
+                    w[j] = *reinterpret_cast<const float2 *>(wout + o);
+                    m[j] = *reinterpret_cast<const float2 *>(m_w + o);
+                    v[j] = *reinterpret_cast<const float2 *>(v_w + o);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < TB; ++j) {
+                if (k0 + j < K) {
+                    const size_t o = (size_t)(k0 + j) * F + f;
+                    if (grad_w) *reinterpret_cast<float2 *>(grad_w + o) = g[j];
+                    if (apply) {
+                        adam_elem(w[j].x, g[j].x, m[j].x, v[j].x, sc);
+                        adam_elem(w[j].y, g[j].y, m[j].y, v[j].y, sc);
+                        *reinterpret_cast<float2 *>(wout + o) = w[j];
+                        *reinterpret_cast<float2 *>(m_w + o) = m[j];
+                        *reinterpret_cast<float2 *>(v_w + o) = v[j];
+                    }
+                }
+            }
+        }
+    }
+    if (blockIdx.x == 0 && tid < K) {
+        float bsum = 0.f;
+        for (int b = 0; b < B; ++b) bsum += g_o2[(size_t)b * K + tid];
+        if (grad_b) grad_b[tid] = bsum;
+        if (apply) {
+            float wv = bout[tid], m = m_b[tid], v = v_b[tid];
+            adam_elem(wv, bsum, m, v, sc);
+            bout[tid] = wv, m_b[tid] = m, v_b[tid] = v;
         }
     }
 }
@@ -526,9 +665,25 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
     // gradient gets its own kernel below.
     const bool packed = (g.F % 2 == 0) && (((uintptr_t)L->pv | (uintptr_t)L->wo | (uintptr_t)L->g_u) % 8 == 0);
     AdamScalars sc = {};
-    const bool fused_out = L->output_layer && ceil_div(g.F, 256) >= 2 * 148;
+    const bool big_out = L->output_layer && ceil_div(g.F, 256) >= 2 * 148;
+    const bool packed_out = big_out && packed && a->adam_out.m_w && a->adam_out.v_w &&
+                            (((uintptr_t)L->wout | (uintptr_t)a->adam_out.m_w | (uintptr_t)a->adam_out.v_w | (uintptr_t)a->grad_wout) % 8 == 0);
+    const bool fused_out = big_out && !packed_out;                 // odd F / unaligned rows: the scalar fused sweep
     const int fblk = ceil_div(g.F, (packed && !fused_out) ? 512 : 256);
-    if (L->output_layer && !fused_out) {
+    if (packed_out) {
+        // large F: packed g_u sweep below + packed output_ gradient/Adam kernel (pv read twice, both at >= 4 waves)
+        sc = adam_scalars(a->adam_out, a->adam_out.step + 1);
+        dcll_adam &o = a->adam_out;
+        const int grid = ceil_div(g.F, 256);
+#define WG2(KM)                                                                                                           \
+    wout_grad_adam2_kernel<KM><<<grid, 256, 0, st>>>(L->pv, g_o2, L->B, g.F, L->K, L->wout, L->bout, o.m_w, o.v_w, o.m_b, \
+                                                     o.v_b, a->grad_wout, a->grad_bout, a->apply_update, sc)
+        if (L->K <= 16) WG2(16);
+        else if (L->K <= 24) WG2(24);
+        else WG2(32);
+#undef WG2
+        DCLL_LAUNCH_OK("wout_grad_adam2_kernel");
+    } else if (L->output_layer && !fused_out) {
         // small F: the output_ gradient gets its own kernel (batch split over warps inside the CTA)
         sc = adam_scalars(a->adam_out, a->adam_out.step + 1);
         dcll_adam &o = a->adam_out;
