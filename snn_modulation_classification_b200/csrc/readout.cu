@@ -305,8 +305,8 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
     return *reinterpret_cast<float2 *>(&rd);
 }
 
-template <int KMAX>
-__global__ void __launch_bounds__(256, 3) readout_bwd2_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
+template <int KMAX, int UB, int MINB>
+__global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
                                                               const float *__restrict__ g_o, int B, int F, int K, int b_per_blk,
                                                               float *__restrict__ g_u) {
     // g rows are read back as broadcast LDS.128 (4 k per load) and enter the FFMA2 as a scalar-broadcast operand: ptxas folds
@@ -330,7 +330,6 @@ __global__ void __launch_bounds__(256, 3) readout_bwd2_kernel(const float *__res
         }
         __syncthreads();
         if (fok) {
-            constexpr int UB = 8;   // samples in flight per thread (16, or a cp.async prefetch ring, were not faster)
             const size_t rowF = (size_t)F;
             const float *pvp = pv + (size_t)b0 * F + f;
             float *gup = g_u + (size_t)b0 * F + f;
@@ -351,17 +350,31 @@ __global__ void __launch_bounds__(256, 3) readout_bwd2_kernel(const float *__res
             };
             int bb = 0;
             // full groups: no per-load predicates, row pointers advance by F (the predicated form spent ~12 instructions
-            // per load on 64-bit address arithmetic and made the sweep as issue-bound as it is memory-bound)
-            for (; bb + UB <= nb; bb += UB) {
-                float2 pvv[UB];
+            // per load on 64-bit address arithmetic).  The loads of group i+1 are issued before group i is multiplied, so
+            // every thread keeps UB rows in flight all the time instead of only between its compute phases.
+            if (nb >= UB) {
+                float2 cur[UB], nxt[UB];
                 const float *p = pvp;
 #pragma unroll
-                for (int u = 0; u < UB; ++u, p += rowF) pvv[u] = __ldg(reinterpret_cast<const float2 *>(p));
+                for (int u = 0; u < UB; ++u, p += rowF) cur[u] = __ldg(reinterpret_cast<const float2 *>(p));
                 pvp = p;
-                float *q = gup;
+                for (; bb + UB <= nb; bb += UB) {
+                    const bool more = bb + 2 * UB <= nb;
+                    if (more) {
+                        p = pvp;
 #pragma unroll
-                for (int u = 0; u < UB; ++u, q += rowF) *reinterpret_cast<float2 *>(q) = sample(bb + u, pvv[u]);
-                gup = q;
+                        for (int u = 0; u < UB; ++u, p += rowF) nxt[u] = __ldg(reinterpret_cast<const float2 *>(p));
+                        pvp = p;
+                    }
+                    float *q = gup;
+#pragma unroll
+                    for (int u = 0; u < UB; ++u, q += rowF) *reinterpret_cast<float2 *>(q) = sample(bb + u, cur[u]);
+                    gup = q;
+                    if (more) {
+#pragma unroll
+                        for (int u = 0; u < UB; ++u) cur[u] = nxt[u];
+                    }
+                }
             }
             for (; bb < nb; ++bb, pvp += rowF, gup += rowF)
                 *reinterpret_cast<float2 *>(gup) = sample(bb, __ldg(reinterpret_cast<const float2 *>(pvp)));
@@ -713,9 +726,12 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
         dim3 grid(fblk, slices);
         float *nf = nullptr;
         if (packed) {
-            if (L->K <= 16) readout_bwd2_kernel<16><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u);
-            else if (L->K <= 24) readout_bwd2_kernel<24><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u);
-            else readout_bwd2_kernel<32><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u);
+            // 8 rows in flight per thread, next group prefetched: 128 registers, 2 CTAs per SM (4 rows at 3 CTAs per SM was slower)
+#define RB2(KM) readout_bwd2_kernel<KM, 8, 2><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u)
+            if (L->K <= 16) { RB2(16); }
+            else if (L->K <= 24) { RB2(24); }
+            else { RB2(32); }
+#undef RB2
         } else if (L->K <= 16)
             RB_LAUNCH(16, false, grid, b_per, nf, nf, nf, nf, nf, nf, nf, nf, 0, sc);
         else if (L->K <= 24)
