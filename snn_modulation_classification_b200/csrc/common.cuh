@@ -50,6 +50,30 @@ struct ProfScope {
         }                                                                                            \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------------
+// Every launch goes through launch_k (cudaLaunchKernelEx + programmaticStreamSerialization) and every kernel starts with
+// pdl_entry() = griddepcontrol.wait: the next kernel of the stream is scheduled while the CTAs of the previous one are still
+// retiring (implicit trigger at CTA exit), and blocks until that grid has completed and its writes are visible.  Nothing is
+// read or written before the wait, so only launch latency and CTA scheduling overlap the previous grid's tail; the dependency
+// chain of the stream is unchanged.  The instruction is a no-op for a kernel launched without the attribute (DCLL_PDL=0).
+// Measured (B200, profiles/r01_pdl_ab.txt): 16x16 B = 64 training +25 %, B = 1024 +7.6 %, 128x128 B = 64 +1 %.  An explicit
+// early trigger (griddepcontrol.launch_dependents at kernel entry) was worse: +16 % at 16x16 B = 64 but -7 % at 128x128,
+// where CTAs of up to two later grids sat resident and blocked beside the running one.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_entry() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);   // the error is picked up by DCLL_LAUNCH_OK
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -51,6 +51,7 @@ __host__ __device__ constexpr int pitch_for(int tw, int kw) {
 
 template <int KH, int KW, int TH, int SEGS, int CI_T, int PH, int PW>
 __global__ void __launch_bounds__(TH *SEGS * 4, 512 / (TH * SEGS * 4)) conv_fwd_kernel(const FwdP p) {
+    pdl_entry();
     constexpr int TW = 8 * SEGS;
     constexpr int POS_T = TH * SEGS;
     constexpr int HALO_H = TH + KH - 1, HALO_W = TW + KW - 1;
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(TH *SEGS * 4, 512 / (TH * SEGS * 4)) conv_fwd_
 // [Cout,Cin,KH,KW] -> [Cin,KH*KW,CoutPad] (zero padded)
 __global__ void weight_transpose_kernel(const float *__restrict__ w, float *__restrict__ wt, int Cout, int CoutPad,
                                         int CinKK) {
+    pdl_entry();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= CinKK * CoutPad) return;
     int co = i % CoutPad, r = i / CoutPad;
@@ -333,6 +335,7 @@ __global__ void weight_transpose_kernel(const float *__restrict__ w, float *__re
 // `deq`, a dense [Cout, Cin*KH*KW] copy that feeds the tensor-core weight split).
 __global__ void __launch_bounds__(256) weight_fakequant_transpose_kernel(const float *__restrict__ w, float *__restrict__ wt,
                                                                          float *__restrict__ deq, int CoutPad, int CinKK) {
+    pdl_entry();
     __shared__ float red[8];
     __shared__ float s_scale;
     const int co = blockIdx.x;
@@ -362,7 +365,7 @@ template <int KH, int KW, int TH, int SEGS, int CI_T, int PH, int PW>
 static int launch_inst(const FwdP &p, int B, cudaStream_t st) {
     int ncog = min(4, ceil_div(p.Cout, 8));
     dim3 grid((unsigned)(p.tiles_h * p.tiles_w * B), ceil_div(p.Cout, 32));
-    conv_fwd_kernel<KH, KW, TH, SEGS, CI_T, PH, PW><<<grid, TH * SEGS * ncog, 0, st>>>(p);
+    launch_k(conv_fwd_kernel<KH, KW, TH, SEGS, CI_T, PH, PW>, grid, TH * SEGS * ncog, 0, st, p);
     DCLL_LAUNCH_OK("conv_fwd_kernel");
     return DCLL_OK;
 }
@@ -400,13 +403,13 @@ int sync_kernel_weights(const dcll_conv_layer *L, cudaStream_t st) {
         // the dequantised dense copy for the tensor-core split lives at the tail of weight_t's allocation
         float *deq = L->weight_mma ? L->weight_t + (size_t)cinkk * g.CoutPad : nullptr;
         if (g.CoutPad > L->Cout) DCLL_CUDA_OK(cudaMemsetAsync(L->weight_t, 0, sizeof(float) * (size_t)cinkk * g.CoutPad, st));
-        weight_fakequant_transpose_kernel<<<L->Cout, 256, 0, st>>>(L->weight, L->weight_t, deq, g.CoutPad, cinkk);
+        launch_k(weight_fakequant_transpose_kernel, L->Cout, 256, 0, st, L->weight, L->weight_t, deq, g.CoutPad, cinkk);
         DCLL_LAUNCH_OK("weight_fakequant_transpose_kernel");
         if (L->weight_mma) return launch_weight_mma(L, deq, st);
         return DCLL_OK;
     }
     const int n = cinkk * g.CoutPad;
-    weight_transpose_kernel<<<ceil_div(n, 256), 256, 0, st>>>(L->weight, L->weight_t, L->Cout, g.CoutPad, cinkk);
+    launch_k(weight_transpose_kernel, ceil_div(n, 256), 256, 0, st, L->weight, L->weight_t, L->Cout, g.CoutPad, cinkk);
     DCLL_LAUNCH_OK("weight_transpose_kernel");
     if (L->weight_mma) return launch_weight_mma(L, L->weight, st);
     return DCLL_OK;

@@ -14,6 +14,7 @@ __global__ void dense_trace_kernel(const float *__restrict__ x, float *__restric
                                    const float *__restrict__ alpha, const float *__restrict__ alphas,
                                    const float *__restrict__ tau_m, const float *__restrict__ tau_s, int per_feature,
                                    int In, size_t n) {
+    pdl_entry();
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     int k = per_feature ? (int)(i % In) : 0;
@@ -39,6 +40,7 @@ struct GemmP {
 
 template <int EPI>
 __global__ void __launch_bounds__(256) sgemm_kernel(const GemmP p) {
+    pdl_entry();
     constexpr int BT = 32, BKK = 16;
     __shared__ float As[BKK][BT + 1], Bs[BKK][BT + 1];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 2 x 2 outputs each
@@ -89,12 +91,13 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmP p) {
 template <int EPI>
 static int gemm(const GemmP &p, cudaStream_t st) {
     dim3 grid(ceil_div(p.N, 32), ceil_div(p.M, 32));
-    sgemm_kernel<EPI><<<grid, 256, 0, st>>>(p);
+    launch_k(sgemm_kernel<EPI>, grid, 256, 0, st, p);
     DCLL_LAUNCH_OK("sgemm_kernel");
     return DCLL_OK;
 }
 
 __global__ void dense_finish_kernel(const float *__restrict__ pvoutput, int B, int K, int32_t *__restrict__ clout) {
+    pdl_entry();
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     int best = 0;
@@ -108,11 +111,13 @@ __global__ void dense_finish_kernel(const float *__restrict__ pvoutput, int B, i
 
 __global__ void dense_loss_grad_kernel(const float *__restrict__ pvoutput, const float *__restrict__ target, int n,
                                        int loss_kind, float *__restrict__ g_o) {
+    pdl_entry();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) g_o[i] = loss_grad_elem(pvoutput[i] - target[i], loss_kind, n);
 }
 
 __global__ void colsum_kernel(const float *__restrict__ g, int B, int N, float *__restrict__ out) {
+    pdl_entry();
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float s = 0.f;
@@ -144,7 +149,7 @@ extern "C" __attribute__((visibility("default"))) int dcll_dense_step_fwd(dcll_d
     DCLL_REQUIRE(x, DCLL_EINVAL, "dcll_dense_step_fwd: null input");
     cudaStream_t st = (cudaStream_t)stream;
     size_t n = (size_t)L->B * L->In;
-    dense_trace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, L->eps0, L->eps1, L->alpha, L->alphas, L->tau_m,
+    launch_k(dense_trace_kernel, (unsigned)((n + 255) / 256), 256, 0, st, x, L->eps0, L->eps1, L->alpha, L->alphas, L->tau_m,
                                                                     L->tau_s, L->coef_mode == DCLL_COEF_CHANNEL, L->In, n);
     DCLL_LAUNCH_OK("dense_trace_kernel");
     GemmP p = {};
@@ -161,7 +166,7 @@ extern "C" __attribute__((visibility("default"))) int dcll_dense_step_fwd(dcll_d
     rc = gemm<EPI_BIAS>(q, st);
     if (rc != DCLL_OK) return rc;
     if (clout) {
-        dense_finish_kernel<<<ceil_div(L->B, 128), 128, 0, st>>>(L->pvoutput, L->B, L->K, clout);
+        launch_k(dense_finish_kernel, ceil_div(L->B, 128), 128, 0, st, L->pvoutput, L->B, L->K, clout);
         DCLL_LAUNCH_OK("dense_finish_kernel");
     }
     return DCLL_OK;
@@ -179,7 +184,7 @@ extern "C" __attribute__((visibility("default"))) int dcll_dense_step_bwd_update
         DCLL_CUDA_OK(cudaMemcpyAsync(L->g_o, a->g_o_ext, sizeof(float) * nk, cudaMemcpyDeviceToDevice, st));
     } else {
         DCLL_REQUIRE(a->target, DCLL_EINVAL, "dcll_dense_step_bwd_update: null target");
-        dense_loss_grad_kernel<<<ceil_div(nk, 256), 256, 0, st>>>(L->pvoutput, a->target, nk, a->loss_kind, L->g_o);
+        launch_k(dense_loss_grad_kernel, ceil_div(nk, 256), 256, 0, st, L->pvoutput, a->target, nk, a->loss_kind, L->g_o);
         DCLL_LAUNCH_OK("dense_loss_grad_kernel");
     }
     GemmP p = {};                                      // g_u[b,o] = (sum_k g_o[b,k] Wo[k,o]) * pv (1-pv)
@@ -194,7 +199,7 @@ extern "C" __attribute__((visibility("default"))) int dcll_dense_step_bwd_update
     q.M = L->Out, q.N = L->In, q.Kd = L->B, q.C = L->grad_w;
     rc = gemm<EPI_BIAS>(q, st);
     if (rc != DCLL_OK) return rc;
-    colsum_kernel<<<ceil_div(L->Out, 128), 128, 0, st>>>(L->g_u, L->B, L->Out, L->grad_b);
+    launch_k(colsum_kernel, ceil_div(L->Out, 128), 128, 0, st, L->g_u, L->B, L->Out, L->grad_b);
     DCLL_LAUNCH_OK("colsum_kernel");
     if (a->apply_update) {
         DCLL_REQUIRE(a->adam_i2h.m_w && a->adam_i2h.v_w && a->adam_i2h.m_b && a->adam_i2h.v_b, DCLL_EINVAL,

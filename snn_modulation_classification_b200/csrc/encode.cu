@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256) iq_encode_kernel(const float *__restrict_
                                                         float span_I, float lo_Q, float span_Q, int out_w,
                                                         int out_h, int t_start, int T, int do_gamma,
                                                         int2 *__restrict__ cells) {
+    pdl_entry();
     __shared__ int2 tile[32][33];
     const int t0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(256) iq_encode_kernel(const float *__restrict_
 template <int VEC>
 __global__ void __launch_bounds__(256) cells_to_frames_kernel(const int2 *__restrict__ cells, size_t n_frames, int HW,
                                                               int W, float *__restrict__ frames) {
+    pdl_entry();
     const int per_frame = HW / VEC;
     size_t total = n_frames * (size_t)per_frame;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -84,7 +86,7 @@ extern "C" __attribute__((visibility("default"))) int dcll_iq_encode(const float
     DCLL_REQUIRE(t_start >= 0 && t_start + T <= N, DCLL_EINVAL,
                  "dcll_iq_encode: window [%d,%d) exceeds the %d samples of the record", t_start, t_start + T, N);
     dim3 grid(ceil_div(T, 32), ceil_div(B, 32));
-    iq_encode_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, N, (float)min_I, (float)(max_I - min_I), (float)min_Q,
+    launch_k(iq_encode_kernel, grid, 256, 0, (cudaStream_t)stream, x, B, N, (float)min_I, (float)(max_I - min_I), (float)min_Q,
                                                              (float)(max_Q - min_Q), out_w, out_h, t_start, T, do_gamma,
                                                              reinterpret_cast<int2 *>(cells));
     DCLL_LAUNCH_OK("iq_encode_kernel");
@@ -99,10 +101,10 @@ extern "C" __attribute__((visibility("default"))) int dcll_cells_to_frames(const
     size_t total = n_frames * (size_t)(vec ? HW / 4 : HW);
     int blocks = (int)((total + 255) / 256 < (size_t)148 * 16 ? (total + 255) / 256 : (size_t)148 * 16);
     if (vec)
-        cells_to_frames_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int2 *>(cells),
+        launch_k(cells_to_frames_kernel<4>, blocks, 256, 0, (cudaStream_t)stream, reinterpret_cast<const int2 *>(cells),
                                                                             n_frames, HW, W, frames);
     else
-        cells_to_frames_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int2 *>(cells),
+        launch_k(cells_to_frames_kernel<1>, blocks, 256, 0, (cudaStream_t)stream, reinterpret_cast<const int2 *>(cells),
                                                                             n_frames, HW, W, frames);
     DCLL_LAUNCH_OK("cells_to_frames_kernel");
     return DCLL_OK;

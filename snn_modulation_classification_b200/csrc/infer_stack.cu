@@ -55,6 +55,7 @@ constexpr int SMEM = OFF_BAR + 256;
 }  // namespace st16
 
 __global__ void __launch_bounds__(st16::NT, 1) infer_stack16_kernel(const StackP p) {
+    pdl_entry();
     using namespace st16;
     using namespace tc;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -365,7 +366,7 @@ extern "C" __attribute__((visibility("default"))) int dcll_infer_stack16(const d
         DCLL_CUDA_OK(cudaFuncSetAttribute(infer_stack16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st16::SMEM));
         configured = true;
     }
-    infer_stack16_kernel<<<p.B, st16::NT, st16::SMEM, (cudaStream_t)stream>>>(p);
+    launch_k(infer_stack16_kernel, p.B, st16::NT, st16::SMEM, (cudaStream_t)stream, p);
     DCLL_LAUNCH_OK("infer_stack16_kernel");
     return DCLL_OK;
 }

@@ -2,6 +2,7 @@
 // whole-window driver that replaces the Python T-loop of train.py:249-251 / test_radio_ml.py:144-145.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -15,6 +16,16 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// programmatic dependent launch is on unless DCLL_PDL=0 (read once)
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("DCLL_PDL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
 }
 
 // ---- launch counter + sampled CUDA-event profile ------------------------------------------------
@@ -172,6 +183,7 @@ static int check_train(const dcll_conv_layer *L, const dcll_train_args *a, const
 }
 
 __global__ void vote_kernel(const int32_t *__restrict__ clout, int T, int t_stride, int B, int K, int32_t *__restrict__ pred) {
+    pdl_entry();
     // Counter(...).most_common(1): highest count, first-seen wins ties (dcll/pytorch_libdcll.py:51)
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -192,6 +204,7 @@ __global__ void vote_kernel(const int32_t *__restrict__ clout, int T, int t_stri
 
 __global__ void quantize_kernel(const float *__restrict__ w, int rows, int cols, int8_t *__restrict__ codes,
                                 float *__restrict__ scales) {
+    pdl_entry();
     // one CTA per output channel: s = max|w| / 127 (1 if the row is all zero), q = clamp(rint(w / s), -127, 127)
     __shared__ float red[32];
     __shared__ float s_scale;
@@ -221,6 +234,7 @@ __global__ void quantize_kernel(const float *__restrict__ w, int rows, int cols,
 
 __global__ void dequantize_kernel(const int8_t *__restrict__ codes, const float *__restrict__ scales, int rows, int cols,
                                   float *__restrict__ w) {
+    pdl_entry();
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= (size_t)rows * cols) return;
     w[i] = __fmul_rn((float)codes[i], scales[i / cols]);
@@ -334,6 +348,7 @@ extern "C" __attribute__((visibility("default"))) int dcll_conv_apply_update(dcl
 
 // 19 equal bins over [0,1], last bin closed on the right (numpy.histogram with bins = linspace(0,1,20))
 __global__ void __launch_bounds__(256) activity_hist_kernel(const float *__restrict__ pv, size_t n, int32_t *__restrict__ hist) {
+    pdl_entry();
     __shared__ int sh[19];
     if (threadIdx.x < 19) sh[threadIdx.x] = 0;
     __syncthreads();
@@ -405,7 +420,7 @@ extern "C" __attribute__((visibility("default"))) int dcll_net_window_stats(dcll
                 const size_t n = (size_t)L->B * g.F;
                 int32_t *dst = hist + ((size_t)l * hist_cap + hist_n[l]++) * 19;
                 const int blocks = (int)(n / 256 / 8 + 1 < 296 ? n / 256 / 8 + 1 : 296);
-                activity_hist_kernel<<<blocks, 256, 0, st>>>(L->pv, n, dst);
+                launch_k(activity_hist_kernel, blocks, 256, 0, st, L->pv, n, dst);
                 DCLL_LAUNCH_OK("activity_hist_kernel");
             }
             if (do_train) {
@@ -419,14 +434,14 @@ extern "C" __attribute__((visibility("default"))) int dcll_net_window_stats(dcll
 
 extern "C" __attribute__((visibility("default"))) int dcll_vote(const int32_t *clout, int T, int t_stride, int B, int K, int32_t *pred, void *stream) {
     DCLL_REQUIRE(clout && pred && T > 0 && B > 0 && K > 0 && K <= 64, DCLL_EINVAL, "dcll_vote: bad arguments (K <= 64)");
-    vote_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(clout, T, t_stride, B, K, pred);
+    launch_k(vote_kernel, ceil_div(B, 128), 128, 0, (cudaStream_t)stream, clout, T, t_stride, B, K, pred);
     DCLL_LAUNCH_OK("vote_kernel");
     return DCLL_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int dcll_quantize(const float *w, int rows, int cols, int8_t *codes, float *scales, void *stream) {
     DCLL_REQUIRE(w && codes && scales && rows > 0 && cols > 0, DCLL_EINVAL, "dcll_quantize: bad arguments");
-    quantize_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(w, rows, cols, codes, scales);
+    launch_k(quantize_kernel, rows, 256, 0, (cudaStream_t)stream, w, rows, cols, codes, scales);
     DCLL_LAUNCH_OK("quantize_kernel");
     return DCLL_OK;
 }
@@ -434,7 +449,7 @@ extern "C" __attribute__((visibility("default"))) int dcll_quantize(const float 
 extern "C" __attribute__((visibility("default"))) int dcll_dequantize(const int8_t *codes, const float *scales, int rows, int cols, float *w, void *stream) {
     DCLL_REQUIRE(w && codes && scales && rows > 0 && cols > 0, DCLL_EINVAL, "dcll_dequantize: bad arguments");
     size_t n = (size_t)rows * cols;
-    dequantize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(codes, scales, rows, cols, w);
+    launch_k(dequantize_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, codes, scales, rows, cols, w);
     DCLL_LAUNCH_OK("dequantize_kernel");
     return DCLL_OK;
 }

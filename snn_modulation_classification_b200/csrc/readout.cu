@@ -35,6 +35,7 @@ template <int KJ, bool VEC>
 __global__ void __launch_bounds__(256, 3) readout_fwd_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
                                                              const float *__restrict__ wout, int B, int F, int K, int Ktot,
                                                              float *__restrict__ partial) {
+    pdl_entry();
     extern __shared__ __align__(16) float ro_smem[];
     constexpr int ROWS = RO_BM + 16 * KJ;                 // pv rows followed by read-out rows
     constexpr int STAGE = ROWS * RO_PITCH;
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(1024) readout_finish_kernel(const float *__res
                                                              float *__restrict__ output, float *__restrict__ g_o,
                                                              float *__restrict__ g_o2, int32_t *__restrict__ clout,
                                                              float *__restrict__ loss_out) {
+    pdl_entry();
     __shared__ float red[16][64];
     __shared__ float vals[64];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -203,6 +205,7 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(const float *__restric
                                                           float *__restrict__ m_b, float *__restrict__ v_b,
                                                           float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
                                                           AdamScalars sc) {
+    pdl_entry();
     // rows are read back as float4 (one broadcast LDS.128 per 4 FMAs; scalar LDS made the sweep LDS-issue bound)
     __shared__ __align__(16) float gs[64][KMAX];
     __shared__ __align__(16) float gs2[WOUT ? 64 : 1][KMAX];
@@ -309,6 +312,7 @@ template <int KMAX, int UB, int MINB>
 __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
                                                               const float *__restrict__ g_o, int B, int F, int K, int b_per_blk,
                                                               float *__restrict__ g_u) {
+    pdl_entry();
     // g rows are read back as broadcast LDS.128 (4 k per load) and enter the FFMA2 as a scalar-broadcast operand: ptxas folds
     // the {g,g} pair into `FFMA2 Rd, Rg.F32, Rw.F32x2, Rs.F32x2`.  (Storing the rows duplicated {g,g} doubled the LDS traffic
     // and made the sweep L1TEX-bound: ncu l1tex throughput 74 %, short-scoreboard stalls above the DRAM ones.)
@@ -393,6 +397,7 @@ __global__ void __launch_bounds__(256) wout_grad_adam_kernel(const float *__rest
                                                              float *__restrict__ m_b, float *__restrict__ v_b,
                                                              float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
                                                              AdamScalars sc) {
+    pdl_entry();
     __shared__ float red[8][KG][33];
     __shared__ float bred[8][KG];
     const int fx = threadIdx.x & 31, bs = threadIdx.x >> 5;
@@ -467,6 +472,7 @@ __global__ void __launch_bounds__(256, 2) wout_grad_adam2_kernel(const float *__
                                                                  float *__restrict__ m_b, float *__restrict__ v_b,
                                                                  float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
                                                                  AdamScalars sc) {
+    pdl_entry();
     __shared__ __align__(16) float gd[64][KMAX];                  // broadcast LDS.128 rows, see readout_bwd2_kernel
     __shared__ __align__(16) float2 red[KMAX][128];
     static_assert(KMAX % 8 == 0, "the Adam tail walks each half's k range in groups of 4 or 6");
@@ -578,6 +584,7 @@ __global__ void __launch_bounds__(256, 2) wout_grad_adam2_kernel(const float *__
 __global__ void loss_grad_kernel(const float *__restrict__ pvoutput, const float *__restrict__ output,
                                  const float *__restrict__ target, int B, int K, int loss_kind, float *__restrict__ g_o,
                                  float *__restrict__ g_o2, float *__restrict__ loss_out) {
+    pdl_entry();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     float lsum = 0.f;
     if (i < B * K) {
@@ -601,6 +608,7 @@ __global__ void loss_grad_kernel(const float *__restrict__ pvoutput, const float
 // generic Adam over a flat parameter (data-parallel path: gradients arrive from the allreduce)
 __global__ void adam_flat_kernel(float *__restrict__ w, const float *__restrict__ g, float *__restrict__ m,
                                  float *__restrict__ v, size_t n, AdamScalars sc) {
+    pdl_entry();
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     float wv = w[i], mv = m[i], vv = v[i];
@@ -618,7 +626,7 @@ int launch_readout_fwd(const dcll_conv_layer *L, const float *target, int loss_k
     if (readout_tc_supported(L)) {
         int rc = launch_readout_tc(L, partial, st);
         if (rc != DCLL_OK) return rc;
-        readout_finish_kernel<<<L->B, ws.n_ro_tc > 16 ? 1024 : 256, 0, st>>>(partial, ws.n_ro_tc, L->B, L->K, g.Ktot, L->bo, L->bout, target, loss_kind,
+        launch_k(readout_finish_kernel, L->B, ws.n_ro_tc > 16 ? 1024 : 256, 0, st, partial, ws.n_ro_tc, L->B, L->K, g.Ktot, L->bo, L->bout, target, loss_kind,
                                                       L->pvoutput, L->output, g_o, g_o2, clout, loss_out);
         DCLL_LAUNCH_OK("readout_finish_kernel");
         return DCLL_OK;
@@ -643,14 +651,14 @@ int launch_readout_fwd(const dcll_conv_layer *L, const float *target, int loss_k
 #define RO_CASE(J)                                                                                                        \
     case J: {                                                                                                             \
         size_t sm = 2 * (RO_BM + 16 * J) * RO_PITCH * sizeof(float);                                                      \
-        if (vec) readout_fwd_kernel<J, true><<<grid, 256, sm, st>>>(L->pv, L->wo, L->wout, L->B, g.F, L->K, g.Ktot, partial); \
-        else readout_fwd_kernel<J, false><<<grid, 256, sm, st>>>(L->pv, L->wo, L->wout, L->B, g.F, L->K, g.Ktot, partial);    \
+        if (vec) launch_k(readout_fwd_kernel<J, true>, grid, 256, sm, st, L->pv, L->wo, L->wout, L->B, g.F, L->K, g.Ktot, partial); \
+        else launch_k(readout_fwd_kernel<J, false>, grid, 256, sm, st, L->pv, L->wo, L->wout, L->B, g.F, L->K, g.Ktot, partial);    \
         break;                                                                                                            \
     }
     switch (kj) { RO_CASE(1) RO_CASE(2) RO_CASE(3) RO_CASE(4) }
 #undef RO_CASE
     DCLL_LAUNCH_OK("readout_fwd_kernel");
-    readout_finish_kernel<<<L->B, 256, 0, st>>>(partial, ws.n_ro, L->B, L->K, g.Ktot, L->bo, L->bout, target, loss_kind,
+    launch_k(readout_finish_kernel, L->B, 256, 0, st, partial, ws.n_ro, L->B, L->K, g.Ktot, L->bo, L->bout, target, loss_kind,
                                                  L->pvoutput, L->output, g_o, g_o2, clout, loss_out);
     DCLL_LAUNCH_OK("readout_finish_kernel");
     return DCLL_OK;
@@ -661,7 +669,7 @@ int launch_loss_grad(const dcll_conv_layer *L, const float *target, int loss_kin
     char *base = (char *)L->workspace;
     float *g_o = (float *)(base + ws.off_go), *g_o2 = (float *)(base + ws.off_go2);
     int n = L->B * L->K;
-    loss_grad_kernel<<<ceil_div(n, 256), 256, 0, st>>>(L->pvoutput, L->output_layer ? L->output : nullptr, target, L->B, L->K,
+    launch_k(loss_grad_kernel, ceil_div(n, 256), 256, 0, st, L->pvoutput, L->output_layer ? L->output : nullptr, target, L->B, L->K,
                                                         loss_kind, g_o, g_o2, loss_out);
     DCLL_LAUNCH_OK("loss_grad_kernel");
     return DCLL_OK;
@@ -689,7 +697,7 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
         dcll_adam &o = a->adam_out;
         const int grid = ceil_div(g.F, 256);
 #define WG2(KM)                                                                                                           \
-    wout_grad_adam2_kernel<KM><<<grid, 256, 0, st>>>(L->pv, g_o2, L->B, g.F, L->K, L->wout, L->bout, o.m_w, o.v_w, o.m_b, \
+    launch_k(wout_grad_adam2_kernel<KM>, grid, 256, 0, st, L->pv, g_o2, L->B, g.F, L->K, L->wout, L->bout, o.m_w, o.v_w, o.m_b, \
                                                      o.v_b, a->grad_wout, a->grad_bout, a->apply_update, sc)
         if (L->K <= 16) WG2(16);
         else if (L->K <= 24) WG2(24);
@@ -701,12 +709,12 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
         sc = adam_scalars(a->adam_out, a->adam_out.step + 1);
         dcll_adam &o = a->adam_out;
         dim3 grid(ceil_div(g.F, 32), ceil_div(L->K, 8));
-        wout_grad_adam_kernel<8><<<grid, 256, 0, st>>>(L->pv, g_o2, L->B, g.F, L->K, L->wout, L->bout, o.m_w, o.v_w, o.m_b, o.v_b,
+        launch_k(wout_grad_adam_kernel<8>, grid, 256, 0, st, L->pv, g_o2, L->B, g.F, L->K, L->wout, L->bout, o.m_w, o.v_w, o.m_b, o.v_b,
                                                       a->grad_wout, a->grad_bout, a->apply_update, sc);
         DCLL_LAUNCH_OK("wout_grad_adam_kernel");
     }
 #define RB_LAUNCH(KM, WO, GRID, BPER, ...) \
-    readout_bwd_kernel<KM, WO><<<GRID, 256, 0, st>>>(L->pv, L->wo, g_o, WO ? g_o2 : nullptr, L->B, g.F, L->K, BPER, L->g_u, __VA_ARGS__)
+    launch_k(readout_bwd_kernel<KM, WO>, GRID, 256, 0, st, L->pv, L->wo, g_o, WO ? g_o2 : nullptr, L->B, g.F, L->K, BPER, L->g_u, __VA_ARGS__)
     if (fused_out) {
         // the output_ gradient reduces over the whole batch inside one thread: no batch slicing
         sc = adam_scalars(a->adam_out, a->adam_out.step + 1);
@@ -727,7 +735,7 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
         float *nf = nullptr;
         if (packed) {
             // 8 rows in flight per thread, next group prefetched: 128 registers, 2 CTAs per SM (4 rows at 3 CTAs per SM was slower)
-#define RB2(KM) readout_bwd2_kernel<KM, 8, 2><<<grid, 256, 0, st>>>(L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u)
+#define RB2(KM) launch_k(readout_bwd2_kernel<KM, 8, 2>, grid, 256, 0, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u)
             if (L->K <= 16) { RB2(16); }
             else if (L->K <= 24) { RB2(24); }
             else { RB2(32); }
@@ -745,7 +753,7 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
 }
 
 int launch_adam_flat(float *w, const float *g, float *m, float *v, size_t n, const AdamScalars &sc, cudaStream_t st) {
-    adam_flat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, g, m, v, n, sc);
+    launch_k(adam_flat_kernel, (unsigned)((n + 255) / 256), 256, 0, st, w, g, m, v, n, sc);
     DCLL_LAUNCH_OK("adam_flat_kernel");
     return DCLL_OK;
 }

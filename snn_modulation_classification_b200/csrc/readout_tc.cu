@@ -80,6 +80,7 @@ __device__ __forceinline__ void cp_async_wait() {
 
 template <int NPAD>
 __global__ void __launch_bounds__(rotc::NT, 1) readout_tc_kernel(const RoTcP p) {
+    pdl_entry();
     using namespace rotc;
     using namespace tc;
     using G = Lay<NPAD>;
@@ -249,7 +250,7 @@ static int launch_rotc(const RoTcP &p, dim3 grid, cudaStream_t st) {
         DCLL_CUDA_OK(cudaFuncSetAttribute(readout_tc_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, rotc::Lay<NPAD>::SMEM));
         configured = true;
     }
-    readout_tc_kernel<NPAD><<<grid, rotc::NT, rotc::Lay<NPAD>::SMEM, st>>>(p);
+    launch_k(readout_tc_kernel<NPAD>, grid, rotc::NT, rotc::Lay<NPAD>::SMEM, st, p);
     DCLL_LAUNCH_OK("readout_tc_kernel");
     return DCLL_OK;
 }

@@ -36,6 +36,7 @@ __host__ __device__ constexpr int wg_plane(int halo_h, int pitch) {
 
 template <int KH, int KW, int PH, int PW>
 __global__ void __launch_bounds__(8 * wg_ci_t(KH) * KH) wgrad_kernel(const WgP p) {
+    pdl_entry();
     constexpr int TH = 16, SEGS = 2, TW = 16;
     constexpr int CI_T = wg_ci_t(KH);
     constexpr int NT = 8 * CI_T * KH;
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(256) reduce_adam_kernel(const float *__restric
                                                           float *__restrict__ m_b, float *__restrict__ v_b,
                                                           float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
                                                           AdamScalars sc, __nv_bfloat16 *__restrict__ w_mma, int Cin, int KHKW, int KW) {
+    pdl_entry();
     // CTA = 64 elements x 4 slices of the partial blocks (a single serial walk over ~150 blocks was pure load latency);
     // the slices are combined in a fixed order, so the result stays bit-reproducible
     __shared__ float red[4][64];
@@ -261,7 +263,7 @@ static int launch_wg_inst(const WgP &p, dim3 grid, cudaStream_t st) {
                                           (int)smem));
         configured = true;
     }
-    wgrad_kernel<KH, KW, PH, PW><<<grid, NT, smem, st>>>(p);
+    launch_k(wgrad_kernel<KH, KW, PH, PW>, grid, NT, smem, st, p);
     DCLL_LAUNCH_OK("wgrad_kernel");
     return DCLL_OK;
 }
@@ -305,7 +307,7 @@ int launch_wgrad(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st) 
     AdamScalars sc = adam_scalars(a->adam_i2h, a->adam_i2h.step + 1);
     dcll_adam &o = a->adam_i2h;
     ProfScope ps(KC_ADAM, 0, st);
-    reduce_adam_kernel<<<ceil_div(p.n_tot, 64), 256, 0, st>>>(p.partial, p.S, p.n_tot, p.nW, L->Cout, g.CoutPad,
+    launch_k(reduce_adam_kernel, ceil_div(p.n_tot, 64), 256, 0, st, p.partial, p.S, p.n_tot, p.nW, L->Cout, g.CoutPad,
                                                                L->Cin * L->KH * L->KW, L->weight, L->weight_t, L->bias,
                                                                o.m_w, o.v_w, o.m_b, o.v_b, a->grad_w, a->grad_b,
                                                                a->apply_update, sc,

@@ -70,6 +70,7 @@ struct WgTcGeoT {
 // while the elected lane of warp 0 issues the MMAs of unit i; tcgen05.commit hands buffers back to the loaders.
 template <int CIN_>
 __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
+    pdl_entry();
     using G = WgTcGeoT<CIN_>;
     using namespace tc;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -378,8 +379,8 @@ int launch_wgrad_tc(const dcll_conv_layer *L, float *partial, int S, cudaStream_
         DCLL_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgTcGeoT<1>::SMEM));
         configured = true;
     }
-    if (L->Cin == 32) wgrad_tc_kernel<32><<<2 * S, 512, WgTcGeoT<32>::SMEM, st>>>(p);
-    else wgrad_tc_kernel<1><<<S, 512, WgTcGeoT<1>::SMEM, st>>>(p);
+    if (L->Cin == 32) launch_k(wgrad_tc_kernel<32>, 2 * S, 512, WgTcGeoT<32>::SMEM, st, p);
+    else launch_k(wgrad_tc_kernel<1>, S, 512, WgTcGeoT<1>::SMEM, st, p);
     DCLL_LAUNCH_OK("wgrad_tc_kernel");
     return DCLL_OK;
 }
