@@ -462,26 +462,29 @@ __global__ void __launch_bounds__(256) wout_grad_adam_kernel(const float *__rest
 // the output layer.  The fused scalar sweep (readout_bwd_kernel<., true>) keeps the whole batch serial in one thread with
 // 48 scalar FMAs per sample-feature and a 2.3-wave grid (0.27 ms against a 0.09 ms HBM floor); splitting it into the packed
 // g_u sweep plus this kernel re-reads pv once (134 MB, 0.02 ms) but both halves run packed and with >= 4 waves.
-// CTA = 128 feature PAIRS x 2 batch halves: a thread accumulates gWout[k][f, f+1] over its half of every 64-sample chunk
-// (FFMA2, g rows duplicated {g,g} in shared memory), the halves are combined in fixed order (first half + second half)
-// through shared memory, and the Adam tail is split over the two halves by k.
+// CTA = 128 feature PAIRS x 2 halves of the OUTPUT index k: a thread accumulates gWout[k][f, f+1] for its KMAX/2 outputs over
+// the whole batch in order (FFMA2 with the g_o2 value as broadcast operand, rows prefetched one group ahead) and then applies
+// Adam to exactly those elements -- no cross-thread reduction.  The two halves read the same pv rows (second read: L1/L2).
+// (First version: halves of the BATCH, all KMAX outputs per thread -- 128 registers, 2 CTAs per SM, 0.104 ms.)
 template <int KMAX>
-__global__ void __launch_bounds__(256, 2) wout_grad_adam2_kernel(const float *__restrict__ pv, const float *__restrict__ g_o2, int B,
+__global__ void __launch_bounds__(256, 3) wout_grad_adam2_kernel(const float *__restrict__ pv, const float *__restrict__ g_o2, int B,
                                                                  int F, int K, float *__restrict__ wout, float *__restrict__ bout,
                                                                  float *__restrict__ m_w, float *__restrict__ v_w,
                                                                  float *__restrict__ m_b, float *__restrict__ v_b,
                                                                  float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
                                                                  AdamScalars sc) {
     pdl_entry();
+    constexpr int KH = KMAX / 2, UB = 8;
+    static_assert(KH % 4 == 0, "float4 rows per half");
     __shared__ __align__(16) float gd[64][KMAX];                  // broadcast LDS.128 rows, see readout_bwd2_kernel
-    __shared__ __align__(16) float2 red[KMAX][128];
-    static_assert(KMAX % 8 == 0, "the Adam tail walks each half's k range in groups of 4 or 6");
     const int tid = threadIdx.x, pair = tid & 127, half = tid >> 7;
     const int f = 2 * (blockIdx.x * 128 + pair);
     const bool fok = f < F;
-    float2 acc[KMAX];
+    const int kbase = half * KH;
+    const size_t rowF = (size_t)F;
+    float2 acc[KH];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) acc[k] = make_float2(0.f, 0.f);
+    for (int k = 0; k < KH; ++k) acc[k] = make_float2(0.f, 0.f);
     for (int b0 = 0; b0 < B; b0 += 64) {
         const int nb = min(64, B - b0);
         __syncthreads();
@@ -491,14 +494,11 @@ __global__ void __launch_bounds__(256, 2) wout_grad_adam2_kernel(const float *__
         }
         __syncthreads();
         if (fok) {
-            constexpr int UB = 8;
-            const int lo = half * 32, hi = min(nb, lo + 32);
-            const size_t rowF = (size_t)F;
-            const float *pvp = pv + (size_t)(b0 + lo) * F + f;
+            const float *pvp = pv + (size_t)b0 * F + f;
             auto sample = [&](int bb, float2 p) {
-                const float4 *g4 = reinterpret_cast<const float4 *>(gd[bb]);
+                const float4 *g4 = reinterpret_cast<const float4 *>(&gd[bb][kbase]);
 #pragma unroll
-                for (int k = 0; k < KMAX; k += 4) {
+                for (int k = 0; k < KH; k += 4) {
                     const float4 g = g4[k >> 2];
                     acc[k] = ffma2(make_float2(g.x, g.x), p, acc[k]);
                     acc[k + 1] = ffma2(make_float2(g.y, g.y), p, acc[k + 1]);
@@ -506,47 +506,43 @@ __global__ void __launch_bounds__(256, 2) wout_grad_adam2_kernel(const float *__
                     acc[k + 3] = ffma2(make_float2(g.w, g.w), p, acc[k + 3]);
                 }
             };
-            int bb = lo;
-            for (; bb + UB <= hi; bb += UB) {                      // full groups: unpredicated loads, pointer increments
-                float2 pvv[UB];
+            int bb = 0;
+            if (nb >= UB) {
+                float2 cur[UB], nxt[UB];
                 const float *p = pvp;
 #pragma unroll
-                for (int u = 0; u < UB; ++u, p += rowF) pvv[u] = __ldg(reinterpret_cast<const float2 *>(p));
+                for (int u = 0; u < UB; ++u, p += rowF) cur[u] = __ldg(reinterpret_cast<const float2 *>(p));
                 pvp = p;
+                for (; bb + UB <= nb; bb += UB) {
+                    const bool more = bb + 2 * UB <= nb;
+                    if (more) {
+                        p = pvp;
 #pragma unroll
-                for (int u = 0; u < UB; ++u) sample(bb + u, pvv[u]);
+                        for (int u = 0; u < UB; ++u, p += rowF) nxt[u] = __ldg(reinterpret_cast<const float2 *>(p));
+                        pvp = p;
+                    }
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) sample(bb + u, cur[u]);
+                    if (more) {
+#pragma unroll
+                        for (int u = 0; u < UB; ++u) cur[u] = nxt[u];
+                    }
+                }
             }
-            for (; bb < hi; ++bb, pvp += rowF) sample(bb, __ldg(reinterpret_cast<const float2 *>(pvp)));
+            for (; bb < nb; ++bb, pvp += rowF) sample(bb, __ldg(reinterpret_cast<const float2 *>(pvp)));
         }
     }
-    // combine the halves in fixed order; afterwards red[k][pair] holds the gradient of features (f, f+1)
-    if (half == 1) {
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) red[k][pair] = acc[k];
-    }
-    __syncthreads();
-    if (half == 0) {
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-            const float2 o = red[k][pair];
-            red[k][pair] = make_float2(__fadd_rn(acc[k].x, o.x), __fadd_rn(acc[k].y, o.y));
-        }
-    }
-    __syncthreads();
     if (fok) {
-        // Adam tail: this half's k range in groups of TB rows, every load of a group issued before its first store (the
-        // accumulators are dead by now, so TB * 3 float2 of state fit the registers)
-        constexpr int KH = KMAX / 2, TB = (KH % 6 == 0) ? 6 : 4;
+        // Adam tail on this thread's own outputs, TB rows at a time with every load issued before the first store
+        constexpr int TB = (KH % 3 == 0) ? 3 : 4;
         static_assert(KH % TB == 0, "tail groups");
-#pragma unroll 1
+#pragma unroll
         for (int kk = 0; kk < KH; kk += TB) {
-            const int k0 = half * KH + kk;
-            float2 g[TB], w[TB], m[TB], v[TB];
+            float2 w[TB], m[TB], v[TB];
 #pragma unroll
             for (int j = 0; j < TB; ++j) {
-                const size_t o = (size_t)(k0 + j) * F + f;
-                g[j] = red[k0 + j][pair];
-                if (apply && k0 + j < K) {
+                const size_t o = (size_t)(kbase + kk + j) * F + f;
+                if (apply && kbase + kk + j < K) {
                     w[j] = *reinterpret_cast<const float2 *>(wout + o);
                     m[j] = *reinterpret_cast<const float2 *>(m_w + o);
                     v[j] = *reinterpret_cast<const float2 *>(v_w + o);
@@ -554,12 +550,13 @@ __global__ void __launch_bounds__(256, 2) wout_grad_adam2_kernel(const float *__
             }
 #pragma unroll
             for (int j = 0; j < TB; ++j) {
-                if (k0 + j < K) {
-                    const size_t o = (size_t)(k0 + j) * F + f;
-                    if (grad_w) *reinterpret_cast<float2 *>(grad_w + o) = g[j];
+                if (kbase + kk + j < K) {
+                    const size_t o = (size_t)(kbase + kk + j) * F + f;
+                    const float2 g = acc[kk + j];
+                    if (grad_w) *reinterpret_cast<float2 *>(grad_w + o) = g;
                     if (apply) {
-                        adam_elem(w[j].x, g[j].x, m[j].x, v[j].x, sc);
-                        adam_elem(w[j].y, g[j].y, m[j].y, v[j].y, sc);
+                        adam_elem(w[j].x, g.x, m[j].x, v[j].x, sc);
+                        adam_elem(w[j].y, g.y, m[j].y, v[j].y, sc);
                         *reinterpret_cast<float2 *>(wout + o) = w[j];
                         *reinterpret_cast<float2 *>(m_w + o) = m[j];
                         *reinterpret_cast<float2 *>(v_w + o) = v[j];
