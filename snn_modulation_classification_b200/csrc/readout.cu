@@ -684,7 +684,7 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
     const bool packed = (g.F % 2 == 0) && (((uintptr_t)L->pv | (uintptr_t)L->wo | (uintptr_t)L->g_u) % 8 == 0);
     AdamScalars sc = {};
     const bool big_out = L->output_layer && ceil_div(g.F, 256) >= 2 * 148;
-    const bool packed_out = big_out && packed && a->adam_out.m_w && a->adam_out.v_w &&
+    const bool packed_out = big_out && packed && (!a->apply_update || (a->adam_out.m_w && a->adam_out.v_w)) &&
                             (((uintptr_t)L->wout | (uintptr_t)a->adam_out.m_w | (uintptr_t)a->adam_out.v_w | (uintptr_t)a->grad_wout) % 8 == 0);
     const bool fused_out = big_out && !packed_out;                 // odd F / unaligned rows: the scalar fused sweep
     const int fblk = ceil_div(g.F, (packed && !fused_out) ? 512 : 256);

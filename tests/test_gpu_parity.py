@@ -97,6 +97,9 @@ CONFIGS = [
     ("radio128", "radio_ml_conv", (1, 128, 128), 2, 24, 0.0),
     ("radio40x24_arp", "radio_ml_conv", (1, 40, 24), 3, 24, 1.0),       # ragged tiles
     ("mnist", "mnist_conv", (1, 28, 28), 5, 10, 0.0),                   # pooling 2, odd sizes
+    # F = 32*56*56 = 100 352: the large-F output layer (packed g_u sweep + wout_grad_adam2_kernel); B = 21 = two full
+    # groups of 8 prefetched rows + a remainder of 5
+    ("radio56_b21", "radio_ml_conv", (1, 56, 56), 21, 24, 0.0),
     ("radioref", "radio_ml_conv_ref", (1, 4, 128), 2, 24, 0.0),         # (1,3) kernels, (1,2) pooling, 64 ch
 ]
 
@@ -162,7 +165,7 @@ def test_layer_steps_teacher_forced(name, spec, im_dims, B, K, arp):
         assert len(s.clout) == steps - burnin + 1
 
 
-@pytest.mark.parametrize("name,spec,im_dims,B,K,arp", CONFIGS[:5], ids=[c[0] for c in CONFIGS[:5]])
+@pytest.mark.parametrize("name,spec,im_dims,B,K,arp", CONFIGS[:6], ids=[c[0] for c in CONFIGS[:6]])
 def test_raw_gradients_match_closed_form(name, spec, im_dims, B, K, arp):
     """g_u / gW / gb / gWout straight from the kernels (apply_update = 0 path, optimizer = SGD lr 0)."""
     from snn_modulation_classification_b200 import networks as N
