@@ -80,7 +80,6 @@ __device__ __forceinline__ void cp_async_wait() {
 
 template <int NPAD>
 __global__ void __launch_bounds__(rotc::NT, 1) readout_tc_kernel(const RoTcP p) {
-    pdl_entry();
     using namespace rotc;
     using namespace tc;
     using G = Lay<NPAD>;
@@ -105,6 +104,7 @@ __global__ void __launch_bounds__(rotc::NT, 1) readout_tc_kernel(const RoTcP p) 
     __syncthreads();
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_entry();   // barrier init and the TMEM allocation above overlap the previous grid's tail; no global access before here
 
     if (warp == MMA_WARP) {
         // ================= MMA issuer =================

@@ -70,7 +70,6 @@ struct WgTcGeoT {
 // while the elected lane of warp 0 issues the MMAs of unit i; tcgen05.commit hands buffers back to the loaders.
 template <int CIN_>
 __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
-    pdl_entry();
     using G = WgTcGeoT<CIN_>;
     using namespace tc;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -92,6 +91,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
     __syncthreads();
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_entry();   // barrier init and the TMEM allocation above overlap the previous grid's tail; no global access before here
 
     const int tiles = p.tiles_h * p.tiles_w;
     // CTA pairs (2k, 2k+1) walk the same units; each CTA accumulates one kernel-row group
