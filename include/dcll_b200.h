@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DCLL_ABI_VERSION 8
+#define DCLL_ABI_VERSION 9
 
 enum { DCLL_OK = 0, DCLL_EINVAL = -1, DCLL_ECUDA = -2, DCLL_EUNSUPPORTED = -3 };
 
@@ -149,6 +149,14 @@ int dcll_conv_sync_weights(const dcll_conv_layer *L, void *stream);
  * clout (device int32 [B], optional): argmax of pvoutput (or of output on the output layer),
  * DCLLClassification.forward :724-728.  Flips L->cur.                                        */
 int dcll_conv_step_fwd(dcll_conv_layer *L, const void *x, int32_t *clout, void *stream);
+/* The same step for a caller that walks the layers itself (data-parallel training: an allreduce sits between a
+ * layer's backward and its next forward) but still wants what dcll_net_window does between two tensor-core layers of equal
+ * geometry: with next != NULL, L's convolution epilogue also applies NEXT's trace recurrences (:415-416 of the next layer,
+ * its input being L's spikes) and writes its operand image; the following call for that layer then passes trace_done = 1
+ * and skips its own trace pass.  dcll_conv_chain_fusable(L, next) says whether a pair qualifies (1) or not (0). */
+int dcll_conv_chain_fusable(const dcll_conv_layer *L, const dcll_conv_layer *next);
+int dcll_conv_step_fwd_chain(dcll_conv_layer *L, const dcll_conv_layer *next, int trace_done, const void *x, int32_t *clout,
+                             void *stream);
 /* i2h.forward alone (ContinuousConv2D.forward :407-426): like the above without pooling-independent
  * read-outs; L->poolH/poolW must be 1 so that spikes/pv are the un-pooled tensors.  Flips L->cur. */
 int dcll_conv_core_fwd(dcll_conv_layer *L, const void *x, void *stream);

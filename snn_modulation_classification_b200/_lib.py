@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdcll_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 OK, EINVAL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3
 COEF_SCALAR, COEF_CHANNEL, COEF_ELEMENT = 0, 1, 2
@@ -80,6 +80,8 @@ def _load():
         "dcll_cells_to_frames": [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp],
         "dcll_conv_sync_weights": [P(ConvLayer), _fp],
         "dcll_conv_step_fwd": [P(ConvLayer), _fp, _fp, _fp],
+        "dcll_conv_step_fwd_chain": [P(ConvLayer), P(ConvLayer), C.c_int, _fp, _fp, _fp],
+        "dcll_conv_chain_fusable": [P(ConvLayer), P(ConvLayer)],
         "dcll_conv_core_fwd": [P(ConvLayer), _fp, _fp],
         "dcll_conv_step_bwd_update": [P(ConvLayer), P(TrainArgs), _fp],
         "dcll_conv_apply_update": [P(ConvLayer), P(TrainArgs), _fp],
@@ -131,7 +133,8 @@ EXPORTS = ["dcll_launch_count", "dcll_profile_enable", "dcll_profile_read", "dcl
            "dcll_cells_to_frames", "dcll_conv_workspace_bytes", "dcll_conv_sync_weights", "dcll_conv_step_fwd",
            "dcll_conv_core_fwd", "dcll_conv_step_bwd_update", "dcll_conv_apply_update", "dcll_net_window", "dcll_vote",
            "dcll_quantize", "dcll_dequantize", "dcll_sizeof_dense_layer", "dcll_dense_step_fwd",
-           "dcll_dense_step_bwd_update", "dcll_net_window_stats", "dcll_infer_stack16", "dcll_conv_readout_rows"]
+           "dcll_dense_step_bwd_update", "dcll_net_window_stats", "dcll_infer_stack16", "dcll_conv_readout_rows", "dcll_conv_step_fwd_chain",
+           "dcll_conv_chain_fusable"]
 
 
 def check(rc):

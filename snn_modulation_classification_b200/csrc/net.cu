@@ -289,6 +289,24 @@ extern "C" __attribute__((visibility("default"))) int dcll_conv_step_fwd(dcll_co
     return step_fwd(L, x, nullptr, 0, clout, nullptr, (cudaStream_t)stream);
 }
 
+// bool tc_trace_fusable(L, next) is defined in conv_fwd_tc.cu
+extern "C" __attribute__((visibility("default"))) int dcll_conv_chain_fusable(const dcll_conv_layer *L, const dcll_conv_layer *next) {
+    return tc_trace_fusable(L, next) ? 1 : 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int dcll_conv_step_fwd_chain(dcll_conv_layer *L, const dcll_conv_layer *next, int trace_done,
+                                                                                const void *x, int32_t *clout, void *stream) {
+    int rc = check_layer(L, "dcll_conv_step_fwd_chain");
+    if (rc != DCLL_OK) return rc;
+    DCLL_REQUIRE(x, DCLL_EINVAL, "dcll_conv_step_fwd_chain: null input");
+    if (next) {
+        rc = check_layer(const_cast<dcll_conv_layer *>(next), "dcll_conv_step_fwd_chain (next)");
+        if (rc != DCLL_OK) return rc;
+        DCLL_REQUIRE(tc_trace_fusable(L, next), DCLL_EINVAL, "dcll_conv_step_fwd_chain: the two layers are not fusable (dcll_conv_chain_fusable)");
+    }
+    return step_fwd(L, x, nullptr, 0, clout, nullptr, (cudaStream_t)stream, next, trace_done != 0);
+}
+
 extern "C" __attribute__((visibility("default"))) int dcll_conv_core_fwd(dcll_conv_layer *L, const void *x, void *stream) {
     DCLL_REQUIRE(L && x, DCLL_EINVAL, "dcll_conv_core_fwd: null argument");
     DCLL_REQUIRE(L->poolH == 1 && L->poolW == 1, DCLL_EINVAL, "dcll_conv_core_fwd: the i2h core has no pooling");

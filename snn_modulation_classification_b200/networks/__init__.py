@@ -274,11 +274,17 @@ class ConvNetwork(torch.nn.Module):
                 _lib.check(apply(ctypes.byref(layers[i]), ctypes.byref(trains[i]), stream))
                 pending[i] = None
 
+        # between two tensor-core layers of equal geometry the next layer's trace update rides in this layer's convolution
+        # epilogue, as in dcll_net_window (it depends on this layer's spikes only, not on the weights being reduced)
+        chain = _lib.lib.dcll_conv_step_fwd_chain
+        fuse = [i + 1 < n and bool(_lib.lib.dcll_conv_chain_fusable(ctypes.byref(layers[i]), ctypes.byref(layers[i + 1])))
+                for i in range(n)]
         for t in range(T):
             for i in range(n):
                 finish(i)
                 xin = x_base + t * x_stride if i == 0 else layers[i - 1].spikes
-                _lib.check(step_fwd(ctypes.byref(layers[i]), xin, clout[t, i].data_ptr(), stream))
+                _lib.check(chain(ctypes.byref(layers[i]), ctypes.byref(layers[i + 1]) if fuse[i] else None,
+                                 1 if i > 0 and fuse[i - 1] else 0, xin, clout[t, i].data_ptr(), stream))
                 iters[i] += 1
                 if iters[i] >= burnin:
                     _lib.check(step_bwd(ctypes.byref(layers[i]), ctypes.byref(trains[i]), stream))
