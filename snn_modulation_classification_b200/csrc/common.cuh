@@ -103,6 +103,7 @@ struct WsLayout {
     size_t off_go;       // float [B][K]   dL/dpvoutput
     size_t off_go2;      // float [B][K]   dL/doutput (output layer)
     size_t off_wg_part;  // float [n_split][nW + Cout]
+    size_t off_wimg2;    // bf16 weight image of conv_mma2_kernel (7x7, 32->32 tensor-core layers), else unused
     size_t total;
 };
 WsLayout ws_layout(const dcll_conv_layer *L);
@@ -119,6 +120,7 @@ bool tc_trace_fusable(const dcll_conv_layer *L, const dcll_conv_layer *next);
 int launch_weight_mma(const dcll_conv_layer *L, const float *w, cudaStream_t st);
 int sync_kernel_weights(const dcll_conv_layer *L, cudaStream_t st);   // weight -> weight_t / weight_mma (quantised or not)
 bool tc_supported(const dcll_conv_layer *L);
+size_t conv_mma2_image_bytes(const dcll_conv_layer *L);   // 0 when the layer has no conv_mma2 path
 int launch_readout_fwd(const dcll_conv_layer *L, const float *target, int loss_kind, int32_t *clout,
                        float *loss_out, cudaStream_t st);
 bool readout_tc_supported(const dcll_conv_layer *L);

@@ -76,6 +76,8 @@ WsLayout ws_layout(const dcll_conv_layer *L) {
     off = align_up(off + sizeof(float) * (size_t)L->B * L->K, 256);
     w.off_wg_part = off;
     off = align_up(off + sizeof(float) * (size_t)w.n_split * (g.nW + L->Cout), 256);
+    w.off_wimg2 = off;
+    off = align_up(off + conv_mma2_image_bytes(L), 256);
     w.total = off;
     return w;
 }
