@@ -184,10 +184,13 @@ def make_args(arp=0.0):
 NCU_SUMMARY = "r01_ncu_final_top_kernels.txt"
 
 
-def ncu_traffic(kernel_substr):
+NCU_SUMMARY_MMA2 = "r01_ncu_conv_mma2.txt"
+
+
+def ncu_traffic(kernel_substr, summary=None):
     """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed `ncu --set full`
     summary of this round (profiles/); None when the capture is absent."""
-    path = os.path.join(ROOT, "profiles", NCU_SUMMARY)
+    path = os.path.join(ROOT, "profiles", summary or NCU_SUMMARY)
     if not os.path.exists(path):
         return None
     cur, vals = None, {}
@@ -326,13 +329,23 @@ def run_b200(a):
     # SS-mode M=128 MMA with N <= 64 (A-operand read; tools/mma_bench.cu), tiles spread over 148 SMs
     n_tiles = batch * ((res + 15) // 16) ** 2
     floor_ms = (n_tiles + 147) // 148 * 392 * 44 / (sm_mhz * 1e3)
-    roofline = {"kernel": ("conv_mma_kernel<7,7,32,32> (layer 2: 32->32 ch, tcgen05 split-bf16 x3, TMEM accumulators)" if tc
-                           else "conv_fwd_kernel<7,7,...> (layer 2: 32->32 ch, FP32 FMA path)"), "bound": "tensor",
+    # The last layer takes conv_mma2_kernel (row-interleaved N-concatenation, conv_fwd_tc.cu) when its 32 x 8 tiles waste
+    # <= 15 % of the plane: per tile 14 ring stages of 6 x (N=128: 64 + N=64: 49) + 2 x (N=64: 49 + N=32: 45) cycles.
+    # Its conv_fwd bracket also holds the ~3 us weight re-layout launch that precedes it.
+    t32, t8 = (res + 31) // 32, (res + 7) // 8
+    mma2 = tc and os.environ.get("DCLL_CONV_MMA2", "1") != "0" and (t32 * 32) * (t8 * 8) <= 1.15 * res * res
+    if mma2:
+        floor_ms = (batch * t32 * t8 + 147) // 148 * 14 * (6 * (64 + 49) + 2 * (49 + 45)) / (sm_mhz * 1e3)
+    summary = NCU_SUMMARY_MMA2 if mma2 else NCU_SUMMARY
+    kname = ("conv_mma2_kernel (layer 2: 32->32 ch, tcgen05 split-bf16 x3, N = 128/64 row-interleaved MMAs, TMEM accumulators)"
+             if mma2 else "conv_mma_kernel<7,7,32,32> (layer 2: 32->32 ch, tcgen05 split-bf16 x3, TMEM accumulators)")
+    roofline = {"kernel": (kname if tc else "conv_fwd_kernel<7,7,...> (layer 2: 32->32 ch, FP32 FMA path)"), "bound": "tensor",
                 "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tensor"] if achieved else None,
-                "traffic": ncu_traffic("conv_mma_kernel") if (tc and res == 128 and batch == 64) else None,
+                "traffic": (ncu_traffic("conv_mma2_kernel" if mma2 else "conv_mma_kernel", summary)
+                            if (tc and res == 128 and batch == 64) else None),
                 "traffic_unit": "bytes per launch (dram read + write, ncu --set full, profiles/%s); algorithmic: 0.40e9 "
-                                "(operand image in, spikes + pv out)" % NCU_SUMMARY,
+                                "(operand image in, spikes + pv out)" % summary,
                 "peak_source": "%s bf16 dense sustained (MEASURED_PEAKS.json)" % pk["src"],
                 "avg_launch_ms": avg_ms, "launches_sampled": c_n, "algorithmic_flops_per_launch": conv_flops,
                 "fp32_fma_peak_tflops_at_clock": fp32_peak, "frac_of_fp32_fma_peak": achieved / fp32_peak if achieved else None,
@@ -341,9 +354,10 @@ def run_b200(a):
                 "mma_issue_floor_ms": floor_ms if tc else None,
                 "frac_of_issue_floor": (floor_ms / avg_ms) if (tc and avg_ms) else None,
                 "note": ("achieved counts ALGORITHMIC conv FLOPs; the split-bf16 mode executes 3 bf16 products per FLOP "
-                         "(frac_executed = tensor-pipe share actually used). With Cout = 32 the MMAs are N = 64 / 32 and "
-                         "bound by the A-operand read (~44 cycles each, measured), not by math: mma_issue_floor_ms is the "
-                         "floor of this decomposition." if tc else
+                         "(frac_executed = tensor-pipe share actually used). With Cout = 32 the MMAs are short (N = 128 / 64 "
+                         "in conv_mma2_kernel, N = 64 / 32 in conv_mma_kernel) and bound by the shared-memory operand reads "
+                         "(4 KB of A per MMA; 64 / 49 / 45 cycles for N = 128 / 64 / 32, measured), not by math: "
+                         "mma_issue_floor_ms is the floor of the decomposition in use." if tc else
                          "FP32-exact parity mode runs on the CUDA-core FMA pipe")}
     per_class = {}
     for (name, layer), (tms, n) in sorted(prof.items()):
