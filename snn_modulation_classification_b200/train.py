@@ -75,10 +75,11 @@ def parse_args(argv=None):
 
 
 def get_loader(batch_size, train, **kw):
+    """The RadioML HDF5 reader (data/load_radio_ml.py, needs h5py) when ``data_dir`` exists, else the synthetic stand-in."""
     data_dir = kw.get('data_dir')
     if data_dir and os.path.isdir(data_dir):
-        raise NotImplementedError('the RadioML HDF5 reader (ref data/load_radio_ml.py) is out of scope here; '
-                                  'omit --radio_ml_data_dir to use the synthetic loader')
+        from .data.load_radio_ml import get_radio_ml_loader
+        return get_radio_ml_loader(batch_size, train, **kw)
     from .data.synthetic import get_radio_ml_loader
     return get_radio_ml_loader(batch_size, train, **kw)
 
