@@ -137,3 +137,41 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libdcll_b200.so"))
     with pytest.raises(ImportError, match="no CPU fallback"):
         _lib._load()
+
+
+def test_every_kernel_waits_for_its_predecessor_and_every_launch_is_chained():
+    """Programmatic dependent launch is only safe if EVERY kernel executes griddepcontrol.wait before touching
+    global memory and every launch goes through launch_k: a static check over the CUDA sources."""
+    import glob
+    import re
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "snn_modulation_classification_b200", "csrc")
+    n_kernels = 0
+    for path in sorted(glob.glob(os.path.join(csrc, "*.cu"))):
+        src = open(path).read()
+        assert "<<<" not in src, "%s launches a kernel without launch_k" % os.path.basename(path)
+        for m in re.finditer(r"__global__", src):
+            # body = from the first '{' after the parameter list to the matching '}'
+            i = src.index("(", m.end())
+            depth, j = 0, i
+            while True:                                   # skip __launch_bounds__(...) and the parameter list
+                if src[j] == "(":
+                    depth += 1
+                elif src[j] == ")":
+                    depth -= 1
+                    if depth == 0 and src[j + 1:].lstrip().startswith("{"):
+                        break
+                j += 1
+            b0 = src.index("{", j)
+            depth, k = 0, b0
+            while True:
+                if src[k] == "{":
+                    depth += 1
+                elif src[k] == "}":
+                    depth -= 1
+                    if depth == 0:
+                        break
+                k += 1
+            body = src[b0:k]
+            assert "pdl_entry();" in body, "kernel near %s:%d has no pdl_entry()" % (os.path.basename(path), src[:m.start()].count("\n") + 1)
+            n_kernels += 1
+    assert n_kernels >= 30
