@@ -74,6 +74,19 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
     (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);   // the error is picked up by DCLL_LAUNCH_OK
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: set it once per (call site, device), keyed by the
+// current device, so that a process which moves on to a second GPU does not get launch failures there.
+#define DCLL_SMEM_ATTR(kern, bytes)                                                                              \
+    do {                                                                                                         \
+        static unsigned long long done_mask_ = 0ull;                                                             \
+        int dev_ = 0;                                                                                            \
+        DCLL_CUDA_OK(cudaGetDevice(&dev_));                                                                      \
+        if (dev_ >= 64 || !((done_mask_ >> dev_) & 1ull)) {                                                      \
+            DCLL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            if (dev_ < 64) done_mask_ |= 1ull << dev_;                                                           \
+        }                                                                                                        \
+    } while (0)
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

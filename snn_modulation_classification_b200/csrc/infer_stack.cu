@@ -361,11 +361,7 @@ extern "C" __attribute__((visibility("default"))) int dcll_infer_stack16(const d
         p.bias[l] = L.bias, p.alpharp[l] = L.alpharp, p.wrp[l] = L.wrp, p.pv[l] = pv_out[l];
     }
     p.w0t = layers[0].weight_t;   // [49][32] since CoutPad == 32
-    static bool configured = false;
-    if (!configured) {
-        DCLL_CUDA_OK(cudaFuncSetAttribute(infer_stack16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st16::SMEM));
-        configured = true;
-    }
+    DCLL_SMEM_ATTR(infer_stack16_kernel, st16::SMEM);
     launch_k(infer_stack16_kernel, p.B, st16::NT, st16::SMEM, (cudaStream_t)stream, p);
     DCLL_LAUNCH_OK("infer_stack16_kernel");
     return DCLL_OK;

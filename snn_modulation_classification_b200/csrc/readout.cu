@@ -631,17 +631,11 @@ int launch_readout_fwd(const dcll_conv_layer *L, const float *target, int loss_k
     const int kj = ceil_div(g.Ktot, 16);
     DCLL_REQUIRE(kj >= 1 && kj <= 4, DCLL_EUNSUPPORTED, "read-out width %d > 64 unsupported", g.Ktot);
     const bool vec = (g.F % 4 == 0) && (((uintptr_t)L->pv | (uintptr_t)L->wo | (uintptr_t)L->wout) % 16 == 0);
-    static bool configured = false;
-    if (!configured) {
-#define RO_CFG(J)                                                                                                         \
-    DCLL_CUDA_OK(cudaFuncSetAttribute(readout_fwd_kernel<J, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                      (int)(2 * (RO_BM + 16 * J) * RO_PITCH * sizeof(float))));                           \
-    DCLL_CUDA_OK(cudaFuncSetAttribute(readout_fwd_kernel<J, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
-                                      (int)(2 * (RO_BM + 16 * J) * RO_PITCH * sizeof(float))));
-        RO_CFG(1) RO_CFG(2) RO_CFG(3) RO_CFG(4)
+#define RO_CFG(J)                                                                                            \
+    DCLL_SMEM_ATTR((readout_fwd_kernel<J, true>), 2 * (RO_BM + 16 * J) * RO_PITCH * sizeof(float));          \
+    DCLL_SMEM_ATTR((readout_fwd_kernel<J, false>), 2 * (RO_BM + 16 * J) * RO_PITCH * sizeof(float));
+    RO_CFG(1) RO_CFG(2) RO_CFG(3) RO_CFG(4)
 #undef RO_CFG
-        configured = true;
-    }
     // batch tiles in grid.y until the grid holds ~4 CTAs per SM
     const int b_tiles = ceil_div(L->B, RO_BM);
     dim3 grid(ws.n_ro, max(1, min(b_tiles, ceil_div(4 * 148, ws.n_ro))));

@@ -245,11 +245,7 @@ int readout_tc_blocks(const dcll_conv_layer *L) {
 
 template <int NPAD>
 static int launch_rotc(const RoTcP &p, dim3 grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        DCLL_CUDA_OK(cudaFuncSetAttribute(readout_tc_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, rotc::Lay<NPAD>::SMEM));
-        configured = true;
-    }
+    DCLL_SMEM_ATTR(readout_tc_kernel<NPAD>, rotc::Lay<NPAD>::SMEM);
     launch_k(readout_tc_kernel<NPAD>, grid, rotc::NT, rotc::Lay<NPAD>::SMEM, st, p);
     DCLL_LAUNCH_OK("readout_tc_kernel");
     return DCLL_OK;

@@ -257,12 +257,7 @@ template <int KH, int KW, int PH, int PW>
 static int launch_wg_inst(const WgP &p, dim3 grid, cudaStream_t st) {
     constexpr int NT = 8 * wg_ci_t(KH) * KH;
     constexpr size_t smem = wg_smem_bytes<KH, KW>();
-    static bool configured = false;
-    if (!configured) {
-        DCLL_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<KH, KW, PH, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
-        configured = true;
-    }
+    DCLL_SMEM_ATTR((wgrad_kernel<KH, KW, PH, PW>), smem);
     launch_k(wgrad_kernel<KH, KW, PH, PW>, grid, NT, smem, st, p);
     DCLL_LAUNCH_OK("wgrad_kernel");
     return DCLL_OK;

@@ -368,17 +368,13 @@ int launch_wgrad_tc(const dcll_conv_layer *L, float *partial, int S, cudaStream_
     Geo g = geo_of(L);
     WgTcP p;
     p.g_u = L->g_u, p.eps1 = L->eps1[L->cur & 1], p.partial = partial;
-    p.img = (tc_supported(L) && L->padW == 3) ? reinterpret_cast<const uint4 *>(L->eps1_mma) : nullptr;
+    p.img = tc_supported(L) ? reinterpret_cast<const uint4 *>(L->eps1_mma) : nullptr;
     p.B = L->B, p.H = L->H, p.W = L->W, p.padH = L->padH, p.padW = L->padW, p.Hc = g.Hc, p.Wc = g.Wc;
     p.tiles_h = ceil_div(g.Hc, 16), p.tiles_w = ceil_div(g.Wc, 16);
     p.n_units = L->B * p.tiles_h * p.tiles_w;
     p.nW = g.nW, p.n_tot = g.nW + L->Cout;
-    static bool configured = false;
-    if (!configured) {
-        DCLL_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgTcGeoT<32>::SMEM));
-        DCLL_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgTcGeoT<1>::SMEM));
-        configured = true;
-    }
+    DCLL_SMEM_ATTR(wgrad_tc_kernel<32>, WgTcGeoT<32>::SMEM);
+    DCLL_SMEM_ATTR(wgrad_tc_kernel<1>, WgTcGeoT<1>::SMEM);
     if (L->Cin == 32) launch_k(wgrad_tc_kernel<32>, 2 * S, 512, WgTcGeoT<32>::SMEM, st, p);
     else launch_k(wgrad_tc_kernel<1>, S, 512, WgTcGeoT<1>::SMEM, st, p);
     DCLL_LAUNCH_OK("wgrad_tc_kernel");

@@ -339,8 +339,11 @@ class ContinuousConv2D(nn.Module):
         """True when this core runs on the tcgen05 split-bf16 kernels (precision 'bf16x3' and an instantiated
         shape: 7x7, {1, 32} -> 32 channels; the layer additionally needs pooling 1, checked by the library).
         Other shapes stay on the FP32 FMA kernel."""
-        return (self.precision == 'bf16x3' and self.kernel_size == (7, 7) and self.in_channels in (1, 32)
-                and self.out_channels == 32)
+        if not (self.precision == 'bf16x3' and self.kernel_size == (7, 7) and self.out_channels == 32):
+            return False
+        # single input channel: the operand pieces hold the column shifts x-padW .. x-padW+7 of the W input columns,
+        # which covers every tap only while the output is not wider than the input (tc_supported, conv_fwd_tc.cu)
+        return self.in_channels == 32 or (self.in_channels == 1 and 0 <= self.padding[1] <= 3)
 
     def _fill_core(self, desc, batch, height, width, x_mode):
         """Geometry, parameters and state pointers of the i2h core."""

@@ -70,9 +70,9 @@ def allreduce_mean(flat, group=None, async_op=False):
     import torch.distributed as dist
     if dist.get_backend(group) == 'nccl':
         return dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
-    work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=False)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=False)   # completed when it returns
     flat.div_(dist.get_world_size(group))
-    return work
+    return None
 
 
 class ConvNetwork(torch.nn.Module):
@@ -194,9 +194,18 @@ class ConvNetwork(torch.nn.Module):
         if labels is not None:
             target = _as_cuda_f32(labels)
             if target.dim() == 3:
-                t_stride = target.shape[1] * target.shape[2]
-                if target.shape[0] > 1 and bool((target[0] == target[-1]).all()) and target.shape[0] != T:
-                    raise ValueError('labels [T,B,K] must cover the window')
+                # [T,B,K] time-varying labels, or [1,B,K] = one row for the whole window; anything else would make the
+                # driver read past the end of the buffer.  No device->host comparison here (no host sync in the window).
+                if target.shape[0] == 1:
+                    t_stride = 0
+                elif target.shape[0] == T:
+                    t_stride = target.shape[1] * target.shape[2]
+                else:
+                    raise ValueError('labels [T,B,K] must cover the window: got %d rows for T = %d'
+                                     % (target.shape[0], T))
+            if tuple(target.shape[-2:]) != (batch, int(self.dcll_slices[0].dclllayer.target_size)):
+                raise ValueError('labels must be [B,K] or [T,B,K] with B = %d, K = %d; got %s'
+                                 % (batch, int(self.dcll_slices[0].dclllayer.target_size), tuple(target.shape)))
         iter0 = (ctypes.c_int32 * n)(*[int(s.iter) for s in self.dcll_slices])
         clout = torch.empty((T, n, batch), dtype=torch.int32, device=x_t.device)
         burnin = int(self.dcll_slices[0].burnin)
@@ -240,7 +249,18 @@ class ConvNetwork(torch.nn.Module):
         win = self._window_buffers(batch)
         Layers, Trains = _lib.ConvLayer * n, _lib.TrainArgs * n
         layers, trains = Layers(), Trains()
-        olds, states, buckets, pending = [], [], [], [None] * n
+        olds, states, buckets, pending, needs_apply = [], [], [], [None] * n, [False] * n
+        for s in self.dcll_slices:
+            lay = s.dclllayer
+            if lay.i2h.state.eps0.shape[0] != batch:
+                import logging
+                logging.warning("Batch size changed from {} to {} since last iteration. Reallocating states."
+                                .format(lay.i2h.state.eps0.shape[0], batch))
+                lay.i2h.init_state(batch, lay.im_dims)
+            if not (_is_plain_adam(s.optimizer) and (not lay.output_layer or _is_plain_adam(s.optimizer2))):
+                raise NotImplementedError('learn_window_dp needs torch.optim.Adam slices')
+            if _loss_kind(s.crit) == _lib.LOSS_EXTERNAL:
+                raise NotImplementedError('learn_window_dp implements SmoothL1Loss / MSELoss / L1Loss')
         target = _as_cuda_f32(labels)
         if target.dim() == 3:
             target = target[0].contiguous()
@@ -269,10 +289,14 @@ class ConvNetwork(torch.nn.Module):
         iters = [int(s.iter) for s in self.dcll_slices]
 
         def finish(i):
-            if pending[i] is not None:
-                pending[i].wait()
+            # a backward ran for layer i: wait for its collective (a completed blocking one returns no handle) and
+            # apply the identical Adam step on every rank
+            if needs_apply[i]:
+                if pending[i] is not None:
+                    pending[i].wait()
+                    pending[i] = None
                 _lib.check(apply(ctypes.byref(layers[i]), ctypes.byref(trains[i]), stream))
-                pending[i] = None
+                needs_apply[i] = False
 
         # between two tensor-core layers of equal geometry the next layer's trace update rides in this layer's convolution
         # epilogue, as in dcll_net_window (it depends on this layer's spikes only, not on the weights being reduced)
@@ -289,6 +313,7 @@ class ConvNetwork(torch.nn.Module):
                 if iters[i] >= burnin:
                     _lib.check(step_bwd(ctypes.byref(layers[i]), ctypes.byref(trains[i]), stream))
                     pending[i] = allreduce_mean(buckets[i], group=group, async_op=True)
+                    needs_apply[i] = True
         for i in range(n):
             finish(i)
         for i, s in enumerate(self.dcll_slices):

@@ -55,6 +55,7 @@ def main(argv=None, snrs=None):
         start = time.time()
         gen_test = iter(get_loader(args.batch_size_test, train=False, data_dir=args.radio_ml_data_dir, min_snr=int(snr),
                                    max_snr=int(snr), per_h5_frac=args.per_h5_frac, train_frac=args.train_frac,
+                                   synthetic=args.synthetic,
                                    n=n_test * args.batch_size_test))
         data = [next(gen_test) for _ in range(n_test)]
         data = [(x, to_one_hot(y, target_size)) for x, y in data]

@@ -2,8 +2,8 @@
 
 Differences from the reference, all outside the hot path: the conventional baseline CNN
 (``ReferenceConvNetwork``, ref train.py:199-202,256-260) is out of scope and not trained; without the RadioML
-HDF5 file (``--radio_ml_data_dir`` missing) a synthetic loader with the same batch layout is used; tensorboardX
-is optional.  The hot loop (ref :249-251, :279-280) is one ``learn_window`` / ``test_window`` call.
+HDF5 file a synthetic loader with the same batch layout can be selected EXPLICITLY with ``--synthetic`` (a missing
+``--radio_ml_data_dir`` is otherwise an error, as in the reference); tensorboardX is optional.  The hot loop (ref :249-251, :279-280) is one ``learn_window`` / ``test_window`` call.
 """
 import argparse
 import datetime
@@ -35,6 +35,9 @@ def parse_args(argv=None):
     p = argparse.ArgumentParser(description='DCLL')
     p.add_argument('--data', type=str, default='RadioML', choices=['RadioML'], help='which data to use')
     p.add_argument('--radio_ml_data_dir', type=str, default='2018.01')
+    p.add_argument('--synthetic', action='store_true',
+                   help='use the synthetic RadioML-shaped stand-in loader (no data set needed); without this flag a '
+                        'missing --radio_ml_data_dir is an error, as in the reference')
     p.add_argument('--min_snr', type=int, default=6)
     p.add_argument('--max_snr', type=int, default=30)
     p.add_argument('--per_h5_frac', type=float, default=0.5)
@@ -74,13 +77,18 @@ def parse_args(argv=None):
     return p.parse_args(argv)
 
 
-def get_loader(batch_size, train, **kw):
-    """The RadioML HDF5 reader (data/load_radio_ml.py, needs h5py) when ``data_dir`` exists, else the synthetic stand-in."""
-    data_dir = kw.get('data_dir')
-    if data_dir and os.path.isdir(data_dir):
-        from .data.load_radio_ml import get_radio_ml_loader
+def get_loader(batch_size, train, synthetic=False, **kw):
+    """The RadioML HDF5 reader (data/load_radio_ml.py) on ``data_dir``; the synthetic stand-in ONLY when asked for with
+    ``--synthetic``.  A wrong path fails loudly (the reference does, data/load_radio_ml.py:69-71) instead of silently
+    training and writing checkpoints on synthetic data."""
+    if synthetic:
+        from .data.synthetic import get_radio_ml_loader
         return get_radio_ml_loader(batch_size, train, **kw)
-    from .data.synthetic import get_radio_ml_loader
+    data_dir = kw.get('data_dir')
+    if not (data_dir and os.path.isdir(data_dir)):
+        raise FileNotFoundError('--radio_ml_data_dir %r is not a directory (pass --synthetic for the synthetic '
+                                'RadioML-shaped loader)' % (data_dir,))
+    from .data.load_radio_ml import get_radio_ml_loader
     return get_radio_ml_loader(batch_size, train, **kw)
 
 
@@ -101,7 +109,7 @@ def main(argv=None):
     im_dims = (1, args.Q_resolution, args.I_resolution)                 # ref :133
     target_size = 24
     loader_kw = dict(data_dir=args.radio_ml_data_dir, min_snr=args.min_snr, max_snr=args.max_snr,
-                     per_h5_frac=args.per_h5_frac, train_frac=args.train_frac)
+                     per_h5_frac=args.per_h5_frac, train_frac=args.train_frac, synthetic=args.synthetic)
     st_kw = dict(out_w=args.I_resolution, out_h=args.Q_resolution, min_I=args.I_bounds[0], max_I=args.I_bounds[1],
                  min_Q=args.Q_bounds[0], max_Q=args.Q_bounds[1], gs_stdev=0, as_cells=True)
     n_test = int(np.ceil(float(args.n_test_samples) / args.batch_size_test))

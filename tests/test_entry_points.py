@@ -25,7 +25,7 @@ def test_train_save_restore_evaluate(tmp_path):
     from snn_modulation_classification_b200 import test_radio_ml, train
     common = ['--I_resolution', '16', '--Q_resolution', '16', '--burnin', '4', '--batch_size', '8', '--batch_size_test', '8',
               '--n_test_samples', '8', '--n_iters', '12', '--n_iters_test', '12', '--arp', '1.0', '--radio_ml_data_dir',
-              str(tmp_path / 'no_such_dir'), '--output', str(tmp_path / 'results')]
+              str(tmp_path / 'no_such_dir'), '--synthetic', '--output', str(tmp_path / 'results')]
     os.chdir(tmp_path)
     r = train.main(common + ['--n_steps', '3', '--n_test_interval', '2'])
     saved = sorted(f for f in os.listdir(r['out_dir']) if f.endswith('.pth'))
@@ -45,3 +45,13 @@ def test_train_save_restore_evaluate(tmp_path):
     s = r['net'].dcll_slices[0]
     s.optimizer.param_groups[-1]['lr'] /= 2
     assert s.optimizer.param_groups[-1]['lr'] == 0.5e-6
+
+
+def test_missing_data_dir_fails_loudly(tmp_path):
+    """A wrong --radio_ml_data_dir must not silently fall back to synthetic data (the reference fails loudly)."""
+    from snn_modulation_classification_b200.train import get_loader, parse_args
+    with pytest.raises(FileNotFoundError):
+        get_loader(8, train=True, data_dir=str(tmp_path / 'no_such_dir'))
+    assert parse_args([]).synthetic is False and parse_args(['--synthetic']).synthetic is True
+    x, y = next(iter(get_loader(8, train=True, synthetic=True, data_dir=str(tmp_path / 'no_such_dir'))))
+    assert x.shape == (8, 2, 1, 1024)
