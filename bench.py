@@ -10,12 +10,15 @@ and Adam step per layer per timestep), or of inference for the infer workloads. 
   value        windows/s with the IQ records already resident in HBM (encode + T timesteps timed)
   e2e          the same through the public API with HOST buffers: pinned-host IQ -> H2D -> iq2spiketrain ->
                ConvNetwork.learn_window -> device vote -> D2H of the per-sample predictions, all timed
-  roofline     dominant kernel (convolution of a 32->32 layer) from CUDA events sampled inside the timed region
-  cpu_baseline the oracle port (same operator sequence as the reference: F.conv2d / autograd / torch.optim.Adam)
-               on the box's host cores, on a bounded sample of the same workload
+  roofline     the kernel class with the largest share of the step (CUDA events sampled inside the timed region on the
+               launching stream), plus the other big kernels under roofline.kernels
+  fp32_mode    the same workload in the FP32-exact parity mode (BASELINE.json configs[0] says FP32), short run
+  other_workloads   the other BASELINE.json configs (mnist_conv, quantised radio_ml_conv_ref, 16x16 script geometry,
+               inference sweep points), short runs through the same public API
+  cpu_baseline the reference's own classes (oracle/_ref, vendored unmodified by oracle/make_ref.py) on the box's host
+               cores, on a bounded sample of the same workload; the oracle port when oracle/_ref is absent
 
---impl reference times that CPU port alone (the reference is pure Python/PyTorch and is not shipped to the GPU
-box; oracle/ restates it operator for operator and is pinned bit-exactly against it, tests/test_oracle_vs_reference.py).
+--impl reference times that CPU arm alone, on the same `config`.
 """
 import argparse
 import json
@@ -37,6 +40,10 @@ WORKLOADS = {
     "radio_ml_conv_infer_16x16_B4096": ("radio_ml_conv", 16, 4096, False, 1.0, 20),
     "radio_ml_conv_infer_128x128_B64": ("radio_ml_conv", 128, 64, False, 0.0, 50),
     "radio_ml_conv_train_16x16_B1024": ("radio_ml_conv", 16, 1024, True, 0.0, 50),   # config 5 shard (8192 / 8)
+    # BASELINE.json configs[4]: data-parallel training at GLOBAL batch 8192 (per-GPU batch = 8192 / N: strong scaling).
+    # 16x16 (script geometry) fits any N; 128x128 needs ~50 GB of state per 1024 samples, i.e. N = 8.
+    "radio_ml_conv_train_dp_global8192_16x16": ("radio_ml_conv", 16, -8192, True, 0.0, 50),
+    "radio_ml_conv_train_dp_global8192_128x128": ("radio_ml_conv", 128, -8192, True, 0.0, 50),
 }
 DEFAULT = "radio_ml_conv_train_128x128_B64"
 K_CLASSES, N_IQ = 24, 1024
@@ -99,15 +106,95 @@ def synth(batch, seed):
 
 
 # --------------------------------------------------------------------------------------------------------
-# CPU port (reference arm / cpu_baseline)
+# workload helpers shared by both arms
 # --------------------------------------------------------------------------------------------------------
+def workload(name, world=1):
+    """(spec, resolution, per-GPU batch, train, arp, burnin, scaling).  A negative batch in WORKLOADS is a GLOBAL batch
+    split over the ranks (BASELINE.json configs[4]: strong scaling)."""
+    spec, res, batch, train, arp, burnin = WORKLOADS[name]
+    scaling = "weak"
+    if batch < 0:
+        if (-batch) % world:
+            raise SystemExit("global batch %d does not divide over %d GPUs" % (-batch, world))
+        batch, scaling = (-batch) // world, "strong"
+    return spec, res, batch, train, arp, burnin, scaling
+
+
+def config_dict(a, world):
+    """`config` of the JSON line -- built by ONE function for both arms so that the driver's same_config check compares
+    like with like.  At N > 1 the global batch is batch_per_gpu * N for both arms: the CPU arm has one host, which works
+    through the N per-GPU chunks one after another (its windows/s is that of one chunk; see cpu_baseline.sample)."""
+    spec, res, batch, train, arp, burnin, scaling = workload(a.workload, world)
+    hw = res * res
+    return {"workload": a.workload, "network": spec + ".yaml", "timesteps": a.timesteps, "batch_per_gpu": batch,
+            "global_batch": batch * world, "resolution": "%dx%d" % (res, res), "arp": arp, "burnin": burnin,
+            "parallelism": ("dp%d (batch-sharded, NCCL allreduce of local-layer grads per timestep)" % world) if world > 1
+            else "single GPU",
+            "l2": "256 MiB flush buffer written between timed steps; per-step working set (state ping-pong "
+                  "%.0f MB/layer) %s L2" % (2 * 2 * 4 * 32 * hw * batch / 1e6, ">" if 2 * 2 * 4 * 32 * hw * batch > 126e6 else "<")}
+
+
+# --------------------------------------------------------------------------------------------------------
+# CPU arm (reference arm / cpu_baseline): the reference's own classes from oracle/_ref, else the oracle port
+# --------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(wl, T, n_fwd=1, n_train=2):
+    """Times the UNMODIFIED reference (train.py:238-251 / test_radio_ml.py:140-145: iq2spiketrain -> torch.Tensor ->
+    net.reset(); net.train(); net.learn(x[t], y[t]) per timestep) on a bounded sample and extrapolates linearly in T
+    (BASELINE.md section 4).  Returns (windows_per_s, description, seconds, extra) or None when oracle/_ref is absent."""
+    import numpy as np
+    import torch
+    from oracle import refshim
+    if not refshim.reference_available():
+        return None
+    spec, res, batch, train, arp, burnin, _ = workload(wl)
+    torch.set_num_threads(os.cpu_count() or 1)
+    _, _, U = refshim.load_reference()
+    # sample layout: 1 warm-up + n_fwd forward-only timesteps, then (training) 1 untimed first training step (builds the
+    # Adam state) + n_train timed ones; the reference trains from iter >= burnin (dcll/pytorch_libdcll.py:692)
+    n_s = 1 + n_fwd + ((1 + n_train) if train else 0)
+    net = refshim.build_reference_net(spec, (1, res, res), batch, K_CLASSES, arp=arp, burnin=(2 + n_fwd) if train else burnin,
+                                      train=train, seed=1)
+    x, y = synth(batch, 1)
+    spent0 = time.perf_counter()
+    np.random.seed(1)
+    t0 = time.perf_counter()
+    with refshim.quiet():
+        frames, targets = U.iq2spiketrain(x, y.numpy(), out_w=res, out_h=res, min_I=-1, max_I=1, min_Q=-1, max_Q=1,
+                                          max_duration=n_s)
+    inp, lab = torch.Tensor(frames), torch.Tensor(targets)                 # train.py:243-244
+    enc_per_t = (time.perf_counter() - t0) / n_s
+    net.reset()
+    net.train() if train else net.eval()
+    ts = []
+    for t in range(n_s):
+        t0 = time.perf_counter()
+        if train:
+            net.learn(x=inp[t], labels=lab[t])
+        else:
+            with torch.no_grad():
+                net.test(x=inp[t])
+        ts.append(time.perf_counter() - t0)
+    t_fw = sum(ts[1:1 + n_fwd]) / n_fwd
+    t_tr = sum(ts[2 + n_fwd:]) / n_train if train else 0.0
+    who = "UNMODIFIED reference classes (oracle/_ref: ConvNetwork.learn/.test, data.utils.iq2spiketrain), torch %s CPU, %d threads" \
+        % (torch.__version__, torch.get_num_threads())
+    if train:
+        window_s = enc_per_t * T + (burnin - 1) * t_fw + (T - burnin + 1) * t_tr
+        desc = ("%s: %d fwd-only + %d training timesteps of %s at B=%d timed, extrapolated linearly to T=%d "
+                "(%d burn-in + %d training timesteps) + encode" % (who, n_fwd, n_train, wl, batch, T, burnin - 1, T - burnin + 1))
+    else:
+        window_s = enc_per_t * T + T * t_fw
+        desc = "%s: %d inference timesteps of %s at B=%d timed, extrapolated linearly to T=%d + encode" % (who, n_fwd, wl, batch, T)
+    return batch / window_s, desc, time.perf_counter() - spent0, dict(ms_fwd_timestep=1e3 * t_fw, ms_train_timestep=1e3 * t_tr,
+                                                                      ms_encode_timestep=1e3 * enc_per_t)
+
+
 def cpu_port_sample(wl, T, n_fwd=1, n_train=2, reps=1):
-    """Times the oracle port on a bounded sample and extrapolates linearly in T.
-    Returns (windows_per_s, description, seconds_spent)."""
+    """Fallback when oracle/_ref is absent: the oracle port (same operator sequence: F.conv2d / autograd / torch.optim.Adam)."""
     import numpy as np
     import torch
     from oracle import dcll_oracle as O
-    spec, res, batch, train, arp, burnin = WORKLOADS[wl]
+    spec, res, batch, train, arp, burnin, _ = workload(wl)
     torch.set_num_threads(os.cpu_count() or 1)
     specs = O.make_specs(O.BUILTIN_SPECS[spec], (1, res, res), K_CLASSES, wrp=arp)
     params = O.random_params(specs, seed=1)
@@ -148,26 +235,38 @@ def cpu_port_sample(wl, T, n_fwd=1, n_train=2, reps=1):
     return batch / window_s, desc, time.perf_counter() - spent0, dict(ms_fwd_timestep=1e3 * t_fw, ms_train_timestep=1e3 * t_tr)
 
 
+def cpu_sample(wl, T, n_fwd, n_train):
+    """(value, description, seconds, extra, kind): the reference classes when vendored, else the port."""
+    r = cpu_reference_sample(wl, T, n_fwd=n_fwd, n_train=n_train)
+    if r is not None:
+        return r + ("reference",)
+    return cpu_port_sample(wl, T, n_fwd=n_fwd, n_train=n_train) + ("port",)
+
+
 def run_reference(a):
     import torch
-    rank = int(os.environ.get("RANK", "0"))
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    spec, res, batch, train, arp, burnin = WORKLOADS[a.workload]
+    spec, res, batch, train, arp, burnin, scaling = workload(a.workload, world)
     vals = []
     big = res >= 64
+    # per-GPU chunk of the workload; the single host works through the `world` chunks one after another, so its
+    # windows/s is the chunk's (samples are independent; only the batch mean couples them)
     for i in range(a.warmup + a.steps):
-        v, desc, _, extra = cpu_port_sample(a.workload, a.timesteps, n_fwd=2 if big else 8, n_train=6 if big else 64)
+        v, desc, _, extra, kind = cpu_sample(a.workload, a.timesteps, n_fwd=2 if big else 8, n_train=6 if big else 64)
         if i >= a.warmup:
             vals.append(v)
     v = sum(vals) / len(vals)
     unit = "windows/s"
+    if world > 1:
+        desc += "; N = %d: ONE host, the %d per-GPU chunks of the global batch %d are processed one after another at this rate" \
+            % (world, world, batch * world)
     out = {"impl": "reference", "metric": "RadioML IQ windows/sec (DCLL %s)" % ("train" if train else "infer"),
            "value": v, "unit": unit, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-           "ms_per_step": 1e3 * batch / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic",
-           "config": {"workload": a.workload, "timesteps": a.timesteps, "batch_per_gpu": batch, "resolution": res},
-           "cpu_baseline": {"value": v, "unit": unit, "cores": torch.get_num_threads(), "kind": "port", "sample": desc},
+           "ms_per_step": 1e3 * batch * world / v, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": config_dict(a, world),
+           "cpu_baseline": {"value": v, "unit": unit, "cores": torch.get_num_threads(), "kind": kind, "sample": desc, **extra},
            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit_json(out)
 
@@ -181,40 +280,11 @@ def make_args(arp=0.0):
     return types.SimpleNamespace(netscale=1.0, alpha=0.92, alphas=0.85, alpharp=0.65, arp=arp, lc_ampl=0.5, random_tau=True)
 
 
-NCU_SUMMARY = "r01_ncu_final_top_kernels.txt"
-
-
-NCU_SUMMARY_MMA2 = "r01_ncu_conv_mma2.txt"
-
-
-def ncu_traffic(kernel_substr, summary=None):
-    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed `ncu --set full`
-    summary of this round (profiles/); None when the capture is absent."""
-    path = os.path.join(ROOT, "profiles", summary or NCU_SUMMARY)
-    if not os.path.exists(path):
-        return None
-    cur, vals = None, {}
-    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
-    for line in open(path):
-        parts = line.split()
-        if line.startswith("Kernel Name"):
-            cur = line
-            if kernel_substr in cur and vals.get("done"):
-                break
-        elif cur and kernel_substr in cur and parts and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            vals[parts[0]] = float(parts[1]) * scale.get(parts[2], 1.0)
-            if len(vals) == 2:
-                vals["done"] = True
-    if "dram__bytes_read.sum" in vals and "dram__bytes_write.sum" in vals:
-        return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
-    return None
-
-
-def build_net(wl):
+def build_net(wl, world=1):
     import numpy as np
     import torch
     from snn_modulation_classification_b200 import networks as N
-    spec, res, batch, train, arp, burnin = WORKLOADS[wl]
+    spec, res, batch, train, arp, burnin, _ = workload(wl, world)
     torch.manual_seed(1)
     np.random.seed(1)
     kw = dict(loss=torch.nn.SmoothL1Loss, opt=torch.optim.Adam, opt_param={"betas": [0.0, 0.95], "weight_decay": 10.0},
@@ -223,6 +293,105 @@ def build_net(wl):
                         act=torch.nn.Sigmoid(), burnin=burnin, **kw)
     net.reset(True)
     return net
+
+
+def _event_timed(fn, steps, flush=None):
+    import torch
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(steps):
+        if flush is not None:
+            flush.zero_()
+        fn()
+    ev1.record()
+    torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1) / steps
+
+
+def other_workloads(flush):
+    """Short runs of the other BASELINE.json configs through the same public API (driver-visible; each entry names its
+    configuration).  1 warm-up + 2 timed windows each, CUDA events, L2 flushed between windows."""
+    import numpy as np
+    import torch
+    from snn_modulation_classification_b200 import networks as N
+    from snn_modulation_classification_b200.data.utils import iq2spiketrain
+    from snn_modulation_classification_b200.quant import enable_quantized_weights
+    res_out = []
+
+    def train_net(spec, im, batch, K, burnin, arp=0.0):
+        torch.manual_seed(1)
+        np.random.seed(1)
+        net = N.ConvNetwork(make_args(arp), im, batch, N.load_network_spec(spec), K, act=torch.nn.Sigmoid(),
+                            loss=torch.nn.SmoothL1Loss, opt=torch.optim.Adam,
+                            opt_param={"betas": [0.0, 0.95], "weight_decay": 10.0}, learning_rates=[1e-6], burnin=burnin)
+        net.reset(True)
+        return net.set_precision("bf16x3")
+
+    def record(name, cfg, B, T, ms, **extra):
+        res_out.append(dict(name=name, config=cfg, windows_per_s=B / (ms / 1e3), ms_per_window_batch=ms,
+                            sample_timesteps_per_s=B * T / (ms / 1e3), **extra))
+
+    # configs[1]: mnist_conv.yaml on synthetic 28x28 Bernoulli spike trains (data/utils.py:23-31: rate = gain*pixel/1000)
+    B, T = 128, 500
+    net = train_net("mnist_conv", (1, 28, 28), B, 10, 50)
+    g = torch.Generator().manual_seed(1)
+    img = torch.rand(B, 1, 28, 28, generator=g)
+    frames = (torch.rand(T, B, 1, 28, 28, generator=g) < img * (100.0 / 1000.0)).float().cuda()
+    y10 = torch.zeros(B, 10).scatter_(1, torch.randint(0, 10, (B,), generator=g).unsqueeze(-1), 1).cuda()
+
+    def step_mnist():
+        net.reset()
+        net.learn_window(frames, y10)
+    step_mnist()
+    record("mnist_conv_train_28x28_B128", "BASELINE configs[1]: mnist_conv.yaml train, B=128, T=500, dense Bernoulli frames, K=10",
+           B, T, _event_timed(step_mnist, 2, flush), tensor_core_layers=[bool(s.dclllayer.i2h.tensor_core_ok()) for s in net.dcll_slices])
+    del net, frames
+
+    # configs[2]: radio_ml_conv_ref.yaml as a 7-layer DCLL spec with int8-quantised weights
+    B, T = 32, 64
+    net = train_net("radio_ml_conv_ref", (1, 128, 128), B, K_CLASSES, 16)
+    enable_quantized_weights(net)
+    x, y = synth(B, 1)
+    x, y = x.cuda(), y.cuda()
+    enc = dict(out_w=128, out_h=128, min_I=-1, max_I=1, min_Q=-1, max_Q=1, max_duration=T, as_cells=True)
+
+    def step_q():
+        cells, _ = iq2spiketrain(x, y, **enc)
+        net.reset()
+        net.learn_window(cells, y)
+    step_q()
+    record("radio_ml_conv_ref_quant_train_128x128_B32", "BASELINE configs[2]: radio_ml_conv_ref.yaml (7 layers, 1x3 kernels, 64 ch), "
+           "int8-quantised weights, train, B=32, T=64, 128x128", B, T, _event_timed(step_q, 2, flush),
+           tensor_core_layers=[bool(s.dclllayer.i2h.tensor_core_ok()) for s in net.dcll_slices])
+    del net
+
+    # script geometry (scripts/train_radio_ml.sh): 16x16, B=512, arp=1, burnin=20
+    for name, B, T, train, arp, burnin in (("radio_ml_conv_train_16x16_B512_arp", 512, 256, True, 1.0, 20),
+                                           ("radio_ml_conv_infer_16x16_B4096", 4096, 256, False, 1.0, 20),
+                                           ("radio_ml_conv_infer_16x16_B65536", 65536, 64, False, 1.0, 20),
+                                           ("radio_ml_conv_infer_16x16_B256", 256, 512, False, 1.0, 20)):
+        WORKLOADS["_tmp"] = ("radio_ml_conv", 16, B, train, arp, burnin)
+        net = build_net("_tmp").set_precision("bf16x3")
+        x, y = synth(B, 1)
+        x, y = x.cuda(), y.cuda()
+        enc = dict(out_w=16, out_h=16, min_I=-1, max_I=1, min_Q=-1, max_Q=1, max_duration=T, as_cells=True)
+
+        def step_s():
+            cells, _ = iq2spiketrain(x, y, **enc)
+            net.reset()
+            if train:
+                net.learn_window(cells, y)
+            else:
+                net.test_window(cells)
+                net.dcll_slices[-1].clout.vote_device(K_CLASSES)
+        step_s()
+        what = "train (scripts/train_radio_ml.sh geometry)" if train else "BASELINE configs[3] inference sweep point (multi-timestep kernel + device vote)"
+        record(name, "radio_ml_conv.yaml %s, 16x16, B=%d, T=%d, arp=%g" % (what, B, T, arp), B, T, _event_timed(step_s, 2, flush))
+        del net
+    WORKLOADS.pop("_tmp", None)
+    torch.cuda.empty_cache()
+    return res_out
 
 
 def run_b200(a):
@@ -237,9 +406,9 @@ def run_b200(a):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    spec, res, batch, train, arp, burnin = WORKLOADS[a.workload]
+    spec, res, batch, train, arp, burnin, scaling = workload(a.workload, world)
     T = a.timesteps
-    net = build_net(a.workload)
+    net = build_net(a.workload, world)
     net.set_precision(a.precision)
     tc = any(sl.dclllayer.i2h.tensor_core_ok() for sl in net.dcll_slices)
     if world > 1:                                   # identical replicas: broadcast rank 0's parameters
@@ -312,80 +481,119 @@ def run_b200(a):
     value = world * batch * a.steps / (ms / 1e3)
     e2e = world * batch * a.steps / (ms_e2e / 1e3)
     pk = peaks()
-    # ---- roofline of the dominant kernel: the convolution of a 32->32 layer (layers 1 and 2 are identical).
-    # In bf16x3 mode the conv_fwd bracket holds trace_image_kernel + conv_mma_kernel and the trace bracket the former alone.
     hw = res * res
-    conv_flops = 2.0 * 32 * 49 * 32 * hw * batch                     # algorithmic FLOPs per launch
-    # Quoted on the LAST layer: in the window driver layer 1's launch also carries layer 2's trace update (fused epilogue), and
-    # layer 2's own trace pass is gone, so its conv_fwd bracket is the pure MMA kernel.
-    lr = len(net.dcll_slices) - 1
-    c_ms, c_n = prof.get(("conv_fwd", lr), (0.0, 0))
-    t_ms, t_n = prof.get(("trace", lr), (0.0, 0))
-    avg_ms = (c_ms / c_n - (t_ms / t_n if t_n else 0.0)) if c_n else None
-    achieved = conv_flops / (avg_ms * 1e-3) / 1e12 if avg_ms else None
-    sm_mhz = (clocks or {}).get("sm_mhz") or 1965
-    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    # issue floor of this decomposition: 2 M-tiles x 49 taps x 2 k-chunks x 2 MMAs per 16x16-position tile, ~44 cycles per
-    # SS-mode M=128 MMA with N <= 64 (A-operand read; tools/mma_bench.cu), tiles spread over 148 SMs
-    n_tiles = batch * ((res + 15) // 16) ** 2
-    floor_ms = (n_tiles + 147) // 148 * 392 * 44 / (sm_mhz * 1e3)
-    # The last layer takes conv_mma2_kernel (row-interleaved N-concatenation, conv_fwd_tc.cu) when its 32 x 8 tiles waste
-    # <= 15 % of the plane: per tile 14 ring stages of 6 x (N=128: 64 + N=64: 49) + 2 x (N=64: 49 + N=32: 45) cycles.
-    # Its conv_fwd bracket also holds the ~3 us weight re-layout launch that precedes it.
-    t32, t8 = (res + 31) // 32, (res + 7) // 8
-    mma2 = tc and os.environ.get("DCLL_CONV_MMA2", "1") != "0" and (t32 * 32) * (t8 * 8) <= 1.15 * res * res
-    if mma2:
-        floor_ms = (batch * t32 * t8 + 147) // 148 * 14 * (6 * (64 + 49) + 2 * (49 + 45)) / (sm_mhz * 1e3)
-    summary = NCU_SUMMARY_MMA2 if mma2 else NCU_SUMMARY
-    kname = ("conv_mma2_kernel (layer 2: 32->32 ch, tcgen05 split-bf16 x3, N = 128/64 row-interleaved MMAs, TMEM accumulators)"
-             if mma2 else "conv_mma_kernel<7,7,32,32> (layer 2: 32->32 ch, tcgen05 split-bf16 x3, TMEM accumulators)")
-    roofline = {"kernel": (kname if tc else "conv_fwd_kernel<7,7,...> (layer 2: 32->32 ch, FP32 FMA path)"), "bound": "tensor",
-                "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tensor"] if achieved else None,
-                "traffic": (ncu_traffic("conv_mma2_kernel" if mma2 else "conv_mma_kernel", summary)
-                            if (tc and res == 128 and batch == 64) else None),
-                "traffic_unit": "bytes per launch (dram read + write, ncu --set full, profiles/%s); algorithmic: 0.40e9 "
-                                "(operand image in, spikes + pv out)" % summary,
-                "peak_source": "%s bf16 dense sustained (MEASURED_PEAKS.json)" % pk["src"],
-                "avg_launch_ms": avg_ms, "launches_sampled": c_n, "algorithmic_flops_per_launch": conv_flops,
-                "fp32_fma_peak_tflops_at_clock": fp32_peak, "frac_of_fp32_fma_peak": achieved / fp32_peak if achieved else None,
-                "executed_tensor_flops_per_launch": conv_flops * (3 if tc else 0),
-                "frac_executed": (3 * achieved / pk["tensor"]) if (achieved and tc) else None,
-                "mma_issue_floor_ms": floor_ms if tc else None,
-                "frac_of_issue_floor": (floor_ms / avg_ms) if (tc and avg_ms) else None,
-                "note": ("achieved counts ALGORITHMIC conv FLOPs; the split-bf16 mode executes 3 bf16 products per FLOP "
-                         "(frac_executed = tensor-pipe share actually used). With Cout = 32 the MMAs are short (N = 128 / 64 "
-                         "in conv_mma2_kernel, N = 64 / 32 in conv_mma_kernel) and bound by the shared-memory operand reads "
-                         "(4 KB of A per MMA; 64 / 49 / 45 cycles for N = 128 / 64 / 32, measured), not by math: "
-                         "mma_issue_floor_ms is the floor of the decomposition in use." if tc else
-                         "FP32-exact parity mode runs on the CUDA-core FMA pipe")}
+    n_layers = len(net.dcll_slices)
     per_class = {}
     for (name, layer), (tms, n) in sorted(prof.items()):
         per_class["%s[l%d]" % (name, layer)] = {"avg_ms": tms / n, "samples": n}
 
+    def avg(name, layer):
+        tms, n = prof.get((name, layer), (0.0, 0))
+        return (tms / n if n else None), n
+
+    # ---- roofline.  Kernel classes and their algorithmic work per launch:
+    #   wgrad[l]       wgrad_tc_kernel (bracket minus the reduce_adam launch inside it)   2*Cin*49*Cout*H'W'*B FLOP   tensor
+    #   conv_fwd[l]    conv_mma(2)_kernel (bracket minus the trace pass inside it)        the same FLOP              tensor
+    #   trace[l]       trace_image_kernel                                                  24 B per state element     hbm
+    #   readout_fwd[l] readout_tc + finish    pv (4 B/elem) + Wo (4*Ktot*F)               hbm
+    #   readout_bwd[l] g_u sweep (+ output_ gradient/Adam on the last layer)              hbm
+    # `roofline` is quoted on the class with the LARGEST share of the sampled step; the others follow in roofline.kernels.
+    adam_ms, _ = avg("adam", 0)
+    kernels = []
+    conv_flops = lambda cin: 2.0 * cin * 49 * 32 * hw * batch
+    for l in range(n_layers):
+        cin = 1 if l == 0 else 32
+        elems_in, elems_out = cin * hw * batch, 32 * hw * batch
+        ktot = K_CLASSES * (2 if l == n_layers - 1 else 1)
+        c_ms, c_n = avg("conv_fwd", l)
+        t_ms, _ = avg("trace", l)
+        if c_ms:
+            k_ms = c_ms - (t_ms or 0.0)
+            kernels.append(dict(kernel="conv_fwd[l%d] (%s)" % (l, "tcgen05 conv_mma/conv_mma2" if tc else "FP32 FMA conv_fwd_kernel"),
+                                bound="tensor", ms=k_ms, samples=c_n, work=conv_flops(cin), unit="TFLOP/s",
+                                achieved=conv_flops(cin) / (k_ms * 1e-3) / 1e12, peak=pk["tensor"]))
+        if t_ms:
+            # bytes: x in (4 B dense; one cell per sample when fed cells), eps0/eps1 read + written, operand image written
+            img = 4 * (8 if cin == 1 else cin) / cin            # single channel: 8 column shifts per position, hi + lo
+            byt = elems_in * ((0 if l == 0 else 4) + 16 + img)
+            kernels.append(dict(kernel="trace[l%d] (trace_image_kernel)" % l, bound="hbm", ms=t_ms, samples=c_n, work=byt,
+                                unit="GB/s", achieved=byt / (t_ms * 1e-3) / 1e9, peak=pk["hbm"]))
+        w_ms, w_n = avg("wgrad", l)
+        if w_ms:
+            k_ms = w_ms - (adam_ms or 0.0)
+            kernels.append(dict(kernel="wgrad[l%d] (%s)" % (l, "tcgen05 wgrad_tc_kernel" if tc else "FP32 FMA wgrad_kernel"), bound="tensor",
+                                ms=k_ms, samples=w_n, work=conv_flops(cin), unit="TFLOP/s",
+                                achieved=conv_flops(cin) / (k_ms * 1e-3) / 1e12, peak=pk["tensor"]))
+        r_ms, r_n = avg("readout_fwd", l)
+        if r_ms:
+            byt = 4.0 * elems_out + 4.0 * ktot * 32 * hw
+            kernels.append(dict(kernel="readout_fwd[l%d] (readout_tc + finish)" % l, bound="hbm", ms=r_ms, samples=r_n, work=byt,
+                                unit="GB/s", achieved=byt / (r_ms * 1e-3) / 1e9, peak=pk["hbm"]))
+        b_ms, b_n = avg("readout_bwd", l)
+        if b_ms:
+            byt = 8.0 * elems_out + 4.0 * K_CLASSES * 32 * hw            # pv in, g_u out, Wo once
+            if l == n_layers - 1:
+                byt += 4.0 * elems_out + 6 * 4.0 * K_CLASSES * 32 * hw   # pv again, Wout/m/v read + written
+            kernels.append(dict(kernel="readout_bwd[l%d]" % l, bound="hbm", ms=b_ms, samples=b_n, work=byt, unit="GB/s",
+                                achieved=byt / (b_ms * 1e-3) / 1e9, peak=pk["hbm"]))
+    for k in kernels:
+        k["frac"] = k["achieved"] / k["peak"]
+        if k["bound"] == "tensor" and tc:
+            k["frac_executed"] = 3 * k["frac"]          # split-bf16: three bf16 products per algorithmic MAC
+    # share per kernel CLASS (layers of the same shape summed): the dominant class is the one the step spends most time in
+    cls = {}
+    for k in kernels:
+        name = k["kernel"].split("[")[0]
+        cls.setdefault(name, []).append(k)
+    step_ms = sum(k["ms"] for k in kernels) or 1.0
+    dom_name = max(cls, key=lambda n_: sum(k["ms"] for k in cls[n_])) if cls else None
+    roofline = None
+    if dom_name:
+        grp = [k for k in cls[dom_name]]
+        big = max(grp, key=lambda k: k["ms"])           # quoted on the largest launch of the class (a 32->32 layer)
+        roofline = {"kernel": big["kernel"], "bound": big["bound"], "achieved": big["achieved"], "peak": big["peak"],
+                    "unit": big["unit"], "frac": big["frac"],
+                    # dram bytes per launch are an ncu quantity; they are not measured inside this run (profiles/*ncu*.txt
+                    # of the round hold the `ncu --set full` capture of this kernel)
+                    "traffic": None,
+                    "peak_source": "%s %s (MEASURED_PEAKS.json)" % (pk["src"], "bf16 dense sustained" if big["bound"] == "tensor" else "HBM copy bandwidth"),
+                    "avg_launch_ms": big["ms"], "launches_sampled": big["samples"],
+                    "algorithmic_work_per_launch": big["work"],
+                    "class_share_of_step": sum(k["ms"] for k in grp) / step_ms,
+                    "frac_executed": big.get("frac_executed"),
+                    "note": ("achieved counts ALGORITHMIC conv FLOPs (one product per MAC); the split-bf16 mode executes 3 bf16 "
+                             "products per MAC (frac_executed = share of the bf16 tensor peak actually issued)" if tc and big["bound"] == "tensor"
+                             else None),
+                    "kernels": [{kk: (round(v, 6) if isinstance(v, float) else v) for kk, v in k.items()} for k in
+                                sorted(kernels, key=lambda k: -k["ms"])]}
+
     out = {"metric": "RadioML IQ windows/sec (DCLL %s)" % ("train" if train else "infer"), "value": value,
            "unit": "windows/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
            "dtype": "bf16x3 (split-bf16 operands on tcgen05, fp32 accumulate; traces/neuron/update fp32)" if tc else "f32",
-           "data": "synthetic",
-           "config": {"workload": a.workload, "precision": a.precision, "network": spec + ".yaml", "timesteps": T, "batch_per_gpu": batch,
-                      "global_batch": batch * world, "resolution": "%dx%d" % (res, res), "arp": arp, "burnin": burnin,
-                      "parallelism": "dp%d (batch-sharded, NCCL allreduce of local-layer grads per timestep)" % world
-                      if world > 1 else "single GPU",
-                      "l2": "256 MiB flush buffer written between timed steps; per-step working set (state ping-pong "
-                            "%.0f MB/layer) %s L2" % (2 * 2 * 4 * 32 * hw * batch / 1e6, ">" if res >= 64 else "<")},
+           "precision": a.precision, "data": "synthetic", "config": config_dict(a, world),
            "sample_timesteps_per_s": value * T,
            "model_tflops": value * T * flops_per_sample_timestep(res, train) / 1e12,
            "e2e": {"value": e2e, "unit": "windows/s", "ms_per_step": ms_e2e / a.steps,
                    "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4),
                    "d2h_bytes_per_step": int(pred_pin.numel() * 4)},
            "gpu_launches": launches, "roofline": roofline, "kernel_ms": per_class, "clocks": clocks}
+    if world == 1 and a.precision != "fp32" and not a.no_extras:
+        # BASELINE.json configs[0] says FP32: the same workload in the FP32-exact parity mode (CUDA-core FMA kernels), whole
+        # windows at the full T, 1 warm-up + 2 timed
+        net.set_precision("fp32")
+        step_device()
+        ms32 = _event_timed(step_device, 2, flush)
+        out["fp32_mode"] = {"value": batch / (ms32 / 1e3), "unit": "windows/s", "ms_per_step": ms32, "steps": 2, "timesteps": T,
+                            "note": "FP32-exact parity mode (every tolerance of DESIGN.md section 2 holds), same workload"}
+        net = None                                   # free the 128x128 state before the other workloads allocate theirs
+        torch.cuda.empty_cache()
+        out["other_workloads"] = other_workloads(flush)
     if world == 1 and not a.no_cpu:
         big = res >= 64
-        # ~10-20 s of CPU work on the bounded sample (16 host cores: ~0.45 s / 0.67 s per 128x128 timestep)
-        v, desc, spent, extra = cpu_port_sample(a.workload, T, n_fwd=4 if big else 16, n_train=12 if big else 256,
-                                                reps=1 if big else 3)
-        out["cpu_baseline"] = {"value": v, "unit": "windows/s", "cores": torch.get_num_threads(), "kind": "port",
+        # ~10-25 s of CPU work on the bounded sample (16 host cores: ~0.5 s / 0.7 s per 128x128 timestep)
+        v, desc, spent, extra, kind = cpu_sample(a.workload, T, n_fwd=4 if big else 16, n_train=12 if big else 256)
+        out["cpu_baseline"] = {"value": v, "unit": "windows/s", "cores": torch.get_num_threads(), "kind": kind,
                                "sample": desc, "seconds": spent, **extra}
     emit_json(out)
     if world > 1:
@@ -434,6 +642,8 @@ def main():
     ap.add_argument("--timesteps", type=int, default=1024)
     ap.add_argument("--profile-every", type=int, default=31, dest="profile_every")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--no-extras", action="store_true", dest="no_extras",
+                    help="skip the fp32_mode and other_workloads legs (quick profiling runs)")
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3"],
                     help="fp32: FP32-exact parity mode on the FMA pipe; bf16x3: tcgen05 split-bf16 (headline mode)")
     ap.add_argument("--burnin", type=int, default=None, help="override the workload's burn-in (profiling runs)")

@@ -1,9 +1,10 @@
-"""Import the UNMODIFIED reference from /root/reference on CPU (build container only).
+"""Import the UNMODIFIED reference on CPU: from /root/reference (build container) or from its vendored copy oracle/_ref/
+(written by oracle/make_ref.py; git-ignored, travels to the GPU box).
 
-TEST INFRASTRUCTURE.  /root/reference does not exist on the GPU box, so nothing
-that runs there may call into this module; it is used by
-``tests/golden/make_golden.py`` (fixture generation) and by
-``tests/test_oracle_vs_reference.py`` (skipped when the reference is absent).
+TEST / BASELINE INFRASTRUCTURE.  Used by ``tests/golden/make_golden.py`` (fixture generation),
+``tests/test_oracle_vs_reference.py`` (skipped when no reference is present) and by ``bench.py``'s reference arm and
+``cpu_baseline`` leg, which time the reference classes themselves on the host cores.  Nothing in the product package
+imports this module.
 
 Four shims, none touching arithmetic:
   1. ``apex`` is not installed; the reference imports ``apex.amp`` but every use
@@ -19,11 +20,36 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("DCLL_REFERENCE_ROOT", "/root/reference")
+VENDORED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _pick_root():
+    env = os.environ.get("DCLL_REFERENCE_ROOT")
+    for cand in ([env] if env else []) + ["/root/reference", VENDORED_ROOT]:
+        if cand and os.path.isfile(os.path.join(cand, "dcll", "pytorch_libdcll.py")):
+            return cand
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "dcll", "pytorch_libdcll.py"))
+
+
+def _check_manifest(root):
+    """The vendored copy must be byte-identical to what make_ref.py copied (sha256 manifest)."""
+    import hashlib
+    import json
+    mf = os.path.join(root, "MANIFEST.json")
+    if not os.path.isfile(mf):
+        return
+    for rel, want in json.load(open(mf))["sha256"].items():
+        with open(os.path.join(root, rel), "rb") as f:
+            got = hashlib.sha256(f.read()).hexdigest()
+        if got != want:
+            raise RuntimeError("oracle/_ref/%s was modified after vendoring (sha256 mismatch): rerun oracle/make_ref.py" % rel)
 
 
 _cached = None
@@ -36,6 +62,7 @@ def load_reference():
         return _cached
     if not reference_available():
         raise RuntimeError("reference not present at %s" % REFERENCE_ROOT)
+    _check_manifest(REFERENCE_ROOT)
     if "apex" not in sys.modules:
         apex = types.ModuleType("apex")
         apex.amp = types.ModuleType("apex.amp")

@@ -193,3 +193,39 @@ def test_multi_timestep_stack_kernel_matches_per_step_path(arp):
     # layer 0 in isolation is bit-exact in its traces (same FP32 recurrences, one rounding per op)
     assert torch.equal(a.dcll_slices[0].dclllayer.i2h.state.eps1, b.dcll_slices[0].dclllayer.i2h.state.eps1)
     assert a.accuracy(tgt) == b.accuracy(tgt)
+
+
+@pytest.mark.parametrize("pad", [2, 1])
+def test_tc_layer0_other_padding(pad):
+    """Advisor finding (round 1): the single-input-channel tensor-core path hard-coded padW == 3.  A 7x7, 1 -> 32 layer with
+    another padding now runs the same kernels (operand pieces hold the shifts x-padW .. x-padW+7); forward and weight
+    gradient against the oracle, teacher-forced."""
+    from snn_modulation_classification_b200 import networks as N
+    name = "tc_pad%d" % pad
+    spec = [dict(out_channels=32, kernel_size=7, padding=pad, pooling=1), dict(out_channels=32, kernel_size=7, padding=3, pooling=1)]
+    O.BUILTIN_SPECS[name] = spec
+    N.BUILTIN_SPECS[name] = spec
+    try:
+        B, K, lr, burnin = 3, 24, 1e-6, 1
+        net, onet = build_pair(name, (1, 40, 24), B, K, arp=0.0, burnin=burnin, lr=lr)
+        net.set_precision("bf16x3")
+        assert [s.dclllayer.i2h.tensor_core_ok() for s in net.dcll_slices] == [True, True]
+        g = torch.Generator().manual_seed(5)
+        x = (torch.rand(4, B, 1, 40, 24, generator=g) < 0.1).float()
+        y = O.to_one_hot(torch.randint(0, K, (B,), generator=g), K)
+        net.reset()
+        onet.reset()
+        for t in range(4):
+            force_state(net, onet)
+            onet.learn(x[t], y)
+            for i, s in enumerate(net.dcll_slices):
+                inp = x[t].cuda() if i == 0 else onet.last[i - 1].output.cuda()
+                out, pvo, pv, pvmem, _ = s.train_dcll(inp, y.cuda(), regularize=False)
+                fo, st = onet.last[i], s.dclllayer.i2h.state
+                assert torch.equal(st.eps0.cpu(), fo.state.eps0) and torch.equal(st.eps1.cpu(), fo.state.eps1), (t, i)
+                assert rel_err(pvmem, fo.pvmem) <= TC_MEM_TOL, (t, i, rel_err(pvmem, fo.pvmem))
+                dw = (s.dclllayer.i2h.weight.detach().cpu() - onet.params[i].weight).abs()
+                assert float(dw.max()) <= 0.5 * lr and float(dw.mean()) <= 2e-3 * lr, (t, i, float(dw.max()) / lr)
+    finally:
+        O.BUILTIN_SPECS.pop(name, None)
+        N.BUILTIN_SPECS.pop(name, None)
