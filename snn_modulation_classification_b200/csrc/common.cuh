@@ -146,6 +146,11 @@ int wgrad_splits(const dcll_conv_layer *L);
 bool wgrad_tc_supported(const dcll_conv_layer *L);
 int wgrad_tc_splits(const dcll_conv_layer *L);
 int launch_wgrad_tc(const dcll_conv_layer *L, float *partial, int S, cudaStream_t st);
+// row-pair N-concatenation kernel (wgrad_tc2.cu): operands from the eps1 image and from g_u left as bf16 {hi,lo} planes by
+// the packed backward read-out; one compact partial block per CTA, reduced by reduce_adam_rp_kernel
+bool wgrad_tc2_supported(const dcll_conv_layer *L);
+size_t wgrad_tc2_partial_floats();
+int launch_wgrad_tc2(const dcll_conv_layer *L, float *partial, int *nA, int *nB, cudaStream_t st);
 struct AdamScalars;
 int launch_adam_flat(float *w, const float *g, float *m, float *v, size_t n, const AdamScalars &sc, cudaStream_t st);
 

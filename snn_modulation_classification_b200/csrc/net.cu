@@ -75,7 +75,9 @@ WsLayout ws_layout(const dcll_conv_layer *L) {
     w.off_go2 = off;
     off = align_up(off + sizeof(float) * (size_t)L->B * L->K, 256);
     w.off_wg_part = off;
-    off = align_up(off + sizeof(float) * (size_t)w.n_split * (g.nW + L->Cout), 256);
+    size_t wg_floats = (size_t)w.n_split * (g.nW + L->Cout);
+    if (wgrad_tc2_supported(L)) wg_floats = max(wg_floats, wgrad_tc2_partial_floats());   // one compact block per CTA
+    off = align_up(off + sizeof(float) * wg_floats, 256);
     w.off_wimg2 = off;
     off = align_up(off + conv_mma2_image_bytes(L), 256);
     w.total = off;

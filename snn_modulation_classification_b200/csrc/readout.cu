@@ -13,6 +13,8 @@
 // epilogue of the convolution: every CTA keeps a 32-wide slice of Wo in shared memory and sweeps it
 // over all samples.  Partials are reduced in a fixed order (no float atomics): results are
 // deterministic run to run.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace dcll {
@@ -308,7 +310,17 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
     return *reinterpret_cast<float2 *>(&rd);
 }
 
-template <int KMAX, int UB, int MINB>
+// IMG: g_u leaves the kernel as bf16 {hi,lo} NCHW planes in the same buffer -- sample b occupies the same F*4 bytes,
+// [part 2][F] bf16 -- which is the operand form wgrad_tc2_kernel stages with plain 16-byte copies (no conversion there).
+// q32 = 32-bit address of the bf16 pair (f, f+1) in the hi plane of the sample; the lo plane starts F/2 words later.
+__device__ __forceinline__ void store_gu_img(uint32_t *q32, int half_f, float2 v) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
+    q32[0] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    q32[half_f] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
+
+template <int KMAX, int UB, int MINB, bool IMG>
 __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
                                                               const float *__restrict__ g_o, int B, int F, int K, int b_per_blk,
                                                               float *__restrict__ g_u) {
@@ -372,7 +384,11 @@ __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__
                     }
                     float *q = gup;
 #pragma unroll
-                    for (int u = 0; u < UB; ++u, q += rowF) *reinterpret_cast<float2 *>(q) = sample(bb + u, cur[u]);
+                    for (int u = 0; u < UB; ++u, q += rowF) {
+                        const float2 v = sample(bb + u, cur[u]);
+                        if (IMG) store_gu_img(reinterpret_cast<uint32_t *>(q - f) + (f >> 1), F >> 1, v);
+                        else *reinterpret_cast<float2 *>(q) = v;
+                    }
                     gup = q;
                     if (more) {
 #pragma unroll
@@ -380,8 +396,11 @@ __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__
                     }
                 }
             }
-            for (; bb < nb; ++bb, pvp += rowF, gup += rowF)
-                *reinterpret_cast<float2 *>(gup) = sample(bb, __ldg(reinterpret_cast<const float2 *>(pvp)));
+            for (; bb < nb; ++bb, pvp += rowF, gup += rowF) {
+                const float2 v = sample(bb, __ldg(reinterpret_cast<const float2 *>(pvp)));
+                if (IMG) store_gu_img(reinterpret_cast<uint32_t *>(gup - f) + (f >> 1), F >> 1, v);
+                else *reinterpret_cast<float2 *>(gup) = v;
+            }
         }
     }
 }
@@ -680,7 +699,9 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
     const bool big_out = L->output_layer && ceil_div(g.F, 256) >= 2 * 148;
     const bool packed_out = big_out && packed && (!a->apply_update || (a->adam_out.m_w && a->adam_out.v_w)) &&
                             (((uintptr_t)L->wout | (uintptr_t)a->adam_out.m_w | (uintptr_t)a->adam_out.v_w | (uintptr_t)a->grad_wout) % 8 == 0);
-    const bool fused_out = big_out && !packed_out;                 // odd F / unaligned rows: the scalar fused sweep
+    // odd F / unaligned rows: the scalar fused sweep -- never when the weight-gradient kernel expects g_u in image form (then the
+    // packed g_u sweep below runs and the output_ gradient takes the generic kernel)
+    const bool fused_out = big_out && !packed_out && !wgrad_tc2_supported(L);
     const int fblk = ceil_div(g.F, (packed && !fused_out) ? 512 : 256);
     if (packed_out) {
         // large F: packed g_u sweep below + packed output_ gradient/Adam kernel (pv read twice, both at >= 4 waves)
@@ -726,7 +747,12 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
         float *nf = nullptr;
         if (packed) {
             // 8 rows in flight per thread, next group prefetched: 128 registers, 2 CTAs per SM (4 rows at 3 CTAs per SM was slower)
-#define RB2(KM) launch_k(readout_bwd2_kernel<KM, 8, 2>, grid, 256, 0, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u)
+            // image form of g_u (bf16 {hi,lo} planes in the same buffer) when the row-pair weight-gradient kernel consumes it
+#define RB2(KM)                                                                                                                    \
+    do {                                                                                                                           \
+        if (wgrad_tc2_supported(L)) launch_k(readout_bwd2_kernel<KM, 8, 2, true>, grid, 256, 0, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u); \
+        else launch_k(readout_bwd2_kernel<KM, 8, 2, false>, grid, 256, 0, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u);  \
+    } while (0)
             if (L->K <= 16) { RB2(16); }
             else if (L->K <= 24) { RB2(24); }
             else { RB2(32); }

@@ -228,6 +228,69 @@ __global__ void __launch_bounds__(256) reduce_adam_kernel(const float *__restric
     }
 }
 
+// Same reduction + Adam tail for the partial blocks of wgrad_tc2_kernel (wgrad_tc2.cu): one compact block per CTA,
+//   block[(co*32 + ci)*20 + a*5 + slot],  a = kernel column within the role (A: kw 0..3, B: kw 4..6), slot <-> kh = 4g - 1 + slot,
+//   + 32 bias sums (role B blocks).  CTA c: pair c >> 1 (pairs [0, nA) = role A), kernel-row group g = c & 1.
+// Element (kh, kw) lives in the role's CTAs with g = 0 when kh <= 3 (slot kh + 1) and with g = 1 when kh >= 3 (slot kh - 3);
+// kh = 3 is the sum of both.  Blocks are walked in a fixed order by 4 slices that are combined in a fixed order.
+__global__ void __launch_bounds__(256) reduce_adam_rp_kernel(const float *__restrict__ partial, int nA, int nB, int blk, int nw_blk,
+                                                             int n_tot, int nW, int Cout, int CoutPad, int CinKK, float *__restrict__ w,
+                                                             float *__restrict__ wt, float *__restrict__ bias,
+                                                             float *__restrict__ m_w, float *__restrict__ v_w,
+                                                             float *__restrict__ m_b, float *__restrict__ v_b,
+                                                             float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
+                                                             AdamScalars sc, __nv_bfloat16 *__restrict__ w_mma, int Cin, int KHKW, int KW) {
+    pdl_entry();
+    __shared__ float red[4][64];
+    const int e = threadIdx.x & 63, sl = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + e;
+    float g = 0.f;
+    if (i < nW) {
+        const int cc = i / KHKW, tap = i - cc * KHKW;            // cc = co * Cin + ci
+        const int kh = tap / KW, kw = tap - kh * KW;
+        const bool roleA = kw < 4;
+        const int a = roleA ? kw : kw - 4;
+        const int c_first = roleA ? 0 : 2 * nA, c_last = roleA ? 2 * nA : 2 * (nA + nB);
+        const size_t base = (size_t)cc * 20 + a * 5;
+        for (int c = c_first + sl; c < c_last; c += 4) {
+            const int grp = c & 1;
+            if (grp == 0 ? kh <= 3 : kh >= 3) g += __ldg(partial + (size_t)c * blk + base + (grp == 0 ? kh + 1 : kh - 3));
+        }
+    } else if (i < n_tot) {
+        for (int c = 2 * nA + sl; c < 2 * (nA + nB); c += 4) g += __ldg(partial + (size_t)c * blk + nw_blk + (i - nW));
+    }
+    red[sl][e] = g;
+    __syncthreads();
+    if (sl != 0 || i >= n_tot) return;
+    g = ((red[0][e] + red[1][e]) + red[2][e]) + red[3][e];
+    if (i < nW) {
+        if (grad_w) grad_w[i] = g;
+        if (apply) {
+            float wv = w[i], m = m_w[i], v = v_w[i];
+            adam_elem(wv, g, m, v, sc);
+            w[i] = wv, m_w[i] = m, v_w[i] = v;
+            int co = i / CinKK, r = i - co * CinKK;
+            wt[(size_t)r * CoutPad + co] = wv;
+            if (w_mma) {
+                const int ci = r / KHKW, tap = r - ci * KHKW;
+                __nv_bfloat16 hi = __float2bfloat16_rn(wv);
+                __nv_bfloat16 lo = __float2bfloat16_rn(wv - __bfloat162float(hi));
+                size_t o = (size_t)tap * (2 * Cin * Cout) + ((size_t)(ci >> 3) * 2 * Cout + co) * 8 + (ci & 7);
+                w_mma[o] = hi;
+                w_mma[o + (size_t)Cout * 8] = lo;
+            }
+        }
+    } else {
+        int co = i - nW;
+        if (grad_b) grad_b[co] = g;
+        if (apply) {
+            float wv = bias[co], m = m_b[co], v = v_b[co];
+            adam_elem(wv, g, m, v, sc);
+            bias[co] = wv, m_b[co] = m, v_b[co] = v;
+        }
+    }
+}
+
 static int wg_n_ci_chunks(const dcll_conv_layer *L) {
     int ci_t = L->KH >= 7 ? 4 : (L->KH >= 5 ? 6 : (L->KH >= 3 ? 10 : 32));
     return ceil_div(L->Cin, ci_t);
@@ -287,6 +350,23 @@ int launch_wgrad(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st) 
     p.tiles_h = ceil_div(g.Hc, 16), p.tiles_w = ceil_div(g.Wc, 16);
     p.n_units = wgrad_units(L), p.nW = g.nW, p.n_tot = g.nW + L->Cout;
     int rc;
+    if (wgrad_tc2_supported(L)) {
+        // row-pair N-concatenation kernel: g_u arrives as bf16 planes (readout_bwd2_kernel<.., IMG>), compact per-CTA partials
+        int nA = 0, nB = 0;
+        rc = launch_wgrad_tc2(L, p.partial, &nA, &nB, st);
+        if (rc != DCLL_OK) return rc;
+        AdamScalars sc = adam_scalars(a->adam_i2h, a->adam_i2h.step + 1);
+        dcll_adam &o = a->adam_i2h;
+        ProfScope ps(KC_ADAM, 0, st);
+        const int blk = (int)(wgrad_tc2_partial_floats() / 148);
+        launch_k(reduce_adam_rp_kernel, ceil_div(p.n_tot, 64), 256, 0, st, p.partial, nA, nB, blk, blk - L->Cout, p.n_tot, p.nW, L->Cout,
+                 g.CoutPad, L->Cin * L->KH * L->KW, L->weight, L->weight_t, L->bias, o.m_w, o.v_w, o.m_b, o.v_b, a->grad_w, a->grad_b,
+                 a->apply_update, sc, L->quantized ? nullptr : reinterpret_cast<__nv_bfloat16 *>(L->weight_mma), L->Cin,
+                 L->KH * L->KW, L->KW);
+        DCLL_LAUNCH_OK("reduce_adam_rp_kernel");
+        if (a->apply_update && L->quantized) return sync_kernel_weights(L, st);
+        return DCLL_OK;
+    }
     if (wgrad_tc_supported(L)) {
         p.S = wgrad_tc_splits(L);
         rc = launch_wgrad_tc(L, p.partial, p.S, st);

@@ -1,0 +1,305 @@
+// Local weight gradient of a 7x7, 32 -> 32 Conv2dDCLLlayer on tcgen05 with ROW-PAIR N-CONCATENATION (split-bf16 x3).
+//
+//     gW[co,ci,kh,kw] = sum_{b,h,w} g_u[b,co,h,w] * eps1[b,ci,h+kh-pad,w+kw-pad]      (dcll/pytorch_libdcll.py:704, see wgrad.cu)
+//
+// wgrad_tc_kernel (wgrad_tc.cu) issues one N = 64 / N = 32 MMA pair per (output row, kernel column): an SS-mode MMA with
+// M = 128, K = 16 costs max(N/2, 32 + N/4) cycles (4 KB of A + 32 N bytes of B through the 128 B/cycle shared-memory operand
+// path; tools/mma_bench.cu), so those MMAs run at 49 + 45 cycles for 32 + 16 cycles of math.  Here N is doubled without more
+// output channels: the B operand holds TWO adjacent output rows,
+//
+//     B_main = [ G_hi(r) | G_hi(r+1) | G_lo(r) | G_lo(r+1) ]   N = 128        B_lo = its first half, N = 64
+//     A      = X[halo rows r + 4g + dy, dy = 0..3][cols c + kw][ci]            M = 128 = (dy, ci), read ONCE for both rows
+//
+// Column block j = 0 (row r) meets kernel row kh = 4g + dy, block j = 1 (row r+1) meets kh = 4g + dy - 1; with g in {0,1} both
+// row parities see every kh = 0..6 exactly once (kh = -1 and 7 are the padding each group already paid).  Stepping r by two
+// halves the MMAs over positions: 8 row pairs x (64 + 49) cycles per kernel column and tile instead of 16 x (49 + 45).
+// The accumulator of one kernel column is now 128 x 128 fp32, so a CTA holds at most four of them (512 TMEM columns):
+// FOUR CTA roles -- kernel-row group g in {0,1} x kernel columns {0..3} (role A) or {4..6} (role B).  Role B has a spare
+// accumulator, which takes the bias gradient as one more MMA per row pair: ones(128 x 16) x B_main = sum over positions of
+// G_hi and G_lo (alternate pairs on the g = 0 / g = 1 CTA).  nA : nB CTA pairs = 40 : 34 balances the two roles.
+//
+// Operands arrive without any conversion in this kernel:
+//   * eps1: the bf16 {hi,lo} operand image the forward wrote ([b][part][ci/8][H][W][8 ci]), staged [row][ci/8][col][8 ci] exactly as
+//     in wgrad_tc_kernel (MN-major A; (dy, ci/8) uniformly strided; kw = 16-byte start shift);
+//   * g_u: the packed backward read-out (readout_bwd2_kernel<.., IMG>) leaves it as bf16 {hi,lo} NCHW planes
+//     [b][part][co][Hc][Wc] in the g_u buffer (same bytes as fp32).  16-byte pieces (8 columns of one channel) are staged as the
+//     K-MAJOR B operand: core matrix = [co % 8][8 columns], N-group order (part, row parity, co/8), two K chunks per group.
+// All loads are cp.async (zero fill outside the picture); 12 loader warps fill one half of a double buffer while two issuer
+// warps work on the other; mbarriers both ways.  Each CTA leaves its accumulators as one compact partial block
+// [co][ci][kernel column a][slot = kh - (4g-1)] (+ 32 bias sums); reduce_adam_rp_kernel (wgrad.cu) adds the blocks that hold a
+// given element in a fixed order -- deterministic, no float atomics.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace dcll {
+
+struct Wg2P {
+    const uint4 *gimg;   // g_u as bf16 {hi,lo} NCHW planes, in 16-byte pieces
+    const uint4 *ximg;   // eps1 operand image
+    float *partial;      // [n_cta][WG2_BLK]
+    int B, H, W, padH, padW, Hc, Wc;
+    int tiles_h, tiles_w, n_units;
+    int nA, nB;          // CTA pairs of role A (kernel columns 0..3) and role B (4..6 + bias)
+};
+
+struct Wg2Geo {
+    static constexpr int KH = 7, KW = 7, CIN = 32, COUT = 32;
+    static constexpr int TH = 16, TW = 16, PAIRS = TH / 2;
+    static constexpr int CGR = 4, DY = 4;
+    static constexpr int XROWS = TH + DY - 2;               // halo rows 2*pair + dy of one kernel-row group: 18
+    static constexpr int XCOLS = TW + KW - 1;               // 22
+    static constexpr int X_CP = XCOLS * 16, X_RP = CGR * X_CP, X_PART = XROWS * X_RP, X_BYTES = 2 * X_PART;
+    static constexpr int G_GRP = 256;                        // one N-group: [k chunk 2][co % 8][8 columns] bf16
+    static constexpr int G_PAIR = 16 * G_GRP;                // (part 2, row parity 2, co/8 4) groups
+    static constexpr int G_BYTES = PAIRS * G_PAIR;
+    static constexpr int BUF = X_BYTES + G_BYTES;
+    static constexpr int OFF_ONES = 2 * BUF, OFF_BAR = OFF_ONES + 4096, SMEM = OFF_BAR + 128;
+    static constexpr int NT = 512, LOADER_WARPS = 12;
+    static constexpr int ACC_COLS = 128, TMEM_COLS = 512;
+    static constexpr int SLOTS = 5, NACC = 4, PER_CC = NACC * SLOTS;   // floats per (co, ci) in a partial block
+    static constexpr int PITCH = PER_CC + 1;                 // staging pitch (odd: conflict-free across ci)
+    static constexpr int NW_BLK = COUT * CIN * PER_CC;       // 20 480
+    static constexpr int BLK = NW_BLK + COUT;                // + bias sums
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+    static_assert(COUT * CIN * PITCH * 4 <= 2 * BUF, "staging fits the tile buffers");
+    static_assert(X_PART % 16 == 0 && BUF % 128 == 0, "alignment");
+};
+
+size_t wgrad_tc2_partial_floats() { return (size_t)148 * Wg2Geo::BLK; }
+
+__global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p) {
+    using G = Wg2Geo;
+    using namespace tc;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + G::OFF_BAR);
+    uint64_t *full = bars, *empty = bars + 2, *done = bars + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
+    uint32_t *ones_used = tmem_slot + 1;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) mbar_init(full + i, G::LOADER_WARPS), mbar_init(empty + i, 2);
+        mbar_init(done, 2);
+        *ones_used = 0u;
+        mbar_fence_init();
+    }
+    // the all-ones A tile of the bias-gradient MMA (any layout: every element is 1.0)
+    for (int i = tid; i < 4096 / 4; i += G::NT) reinterpret_cast<uint32_t *>(smem + G::OFF_ONES)[i] = 0x3f803f80u;
+    if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)G::TMEM_COLS);
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_entry();   // nothing global is touched before here
+
+    // role / group / unit walk of this CTA: CTAs (2k, 2k+1) form a pair (g = 0, 1) that walks the same units
+    const int pair_id = blockIdx.x >> 1, grp = blockIdx.x & 1;
+    const bool roleB = pair_id >= p.nA;
+    const int u_first = roleB ? pair_id - p.nA : pair_id, u_step = roleB ? p.nB : p.nA;
+    const int kw_base = roleB ? 4 : 0;
+    const int tiles = p.tiles_h * p.tiles_w;
+    const int row_off = G::DY * grp;
+
+    if (warp >= 4) {
+        // ================= loaders: 384 threads, everything by cp.async =================
+        const int l = (warp - 4) * 32 + lane;
+        const size_t hw = (size_t)p.H * p.W;
+        const size_t gplane = (size_t)p.Hc * p.Wc / 8;            // 16-byte pieces per (b, part, co) plane (Wc % 8 == 0)
+        const int wc8 = p.Wc >> 3;
+        int i = 0;
+        for (int u = u_first; u < p.n_units; u += u_step, ++i) {
+            const int buf = i & 1;
+            const uint32_t sX = smem_u32(smem + buf * G::BUF), sG = sX + G::X_BYTES;
+            const int b = u / tiles, tile = u - b * tiles;
+            const int th_i = tile / p.tiles_w, tw_i = tile - th_i * p.tiles_w;
+            const int h0 = th_i * G::TH, w0 = tw_i * G::TW;
+            if (i >= 2) mbar_wait(empty + buf, ((i >> 1) - 1) & 1);   // MMAs of unit i-2 have finished reading this half
+            {   // ---- eps1 halo tile: [row][cg][col][8 ci], bf16 hi | lo
+                const uint4 *src0 = p.ximg + (size_t)b * 2 * G::CGR * hw;
+                for (int idx = l; idx < 2 * G::XROWS * G::CGR * G::XCOLS; idx += G::LOADER_WARPS * 32) {
+                    const int c = idx % G::XCOLS;
+                    int t = idx / G::XCOLS;
+                    const int cg = t % G::CGR;
+                    t /= G::CGR;
+                    const int r = t % G::XROWS, part = t / G::XROWS;
+                    const int gh = h0 - p.padH + row_off + r, gw = w0 - p.padW + c;
+                    const bool in = gh >= 0 && gh < p.H && gw >= 0 && gw < p.W;
+                    const uint4 *src = in ? src0 + (size_t)(part * G::CGR + cg) * hw + (size_t)gh * p.W + gw : src0;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sX + part * G::X_PART + r * G::X_RP + cg * G::X_CP + c * 16),
+                                 "l"(src), "r"(in ? 16u : 0u)
+                                 : "memory");
+                }
+            }
+            {   // ---- g_u tile: piece = 8 columns of one channel; N-group (part, row parity, co/8), k chunk, co % 8
+                const uint4 *src0 = p.gimg + (size_t)b * 2 * G::COUT * gplane;
+                for (int idx = l; idx < 2 * G::COUT * G::TH * 2; idx += G::LOADER_WARPS * 32) {
+                    const int kc = idx & 1, row = (idx >> 1) & 15, co = (idx >> 5) & 31, part = idx >> 10;
+                    const int oh = h0 + row, ow = w0 + 8 * kc;
+                    const bool in = oh < p.Hc && ow < p.Wc;
+                    const uint4 *src = in ? src0 + (size_t)(part * G::COUT + co) * gplane + (size_t)oh * wc8 + (ow >> 3) : src0;
+                    const uint32_t dst = sG + (row >> 1) * G::G_PAIR + (part * 8 + (row & 1) * 4 + (co >> 3)) * G::G_GRP + kc * 128 + (co & 7) * 16;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(in ? 16u : 0u) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full + buf);
+        }
+    } else if (warp < 2) {
+        // ================= MMA issuers: warp 0 = first two kernel columns of the role, warp 1 = the rest (+ bias) =================
+        constexpr uint32_t IDESC_N128 = idesc_bf16(128, 128, true, false);   // A MN-major (M = (dy, ci) contiguous), B K-major
+        constexpr uint32_t IDESC_N64 = idesc_bf16(128, 64, true, false);
+        constexpr uint32_t A_HI = desc_hi(G::X_CP);          // SBO: next 8 rows of M = next (dy, cg) group
+        constexpr uint32_t B_HI = desc_hi(G::G_GRP);         // SBO: next 8 rows of N = next (part, parity, co/8) group
+        constexpr uint32_t ONES_HI = desc_hi(128);
+        const uint32_t elected = elect_one();
+        const int kw0 = kw_base + (warp == 0 ? 0 : 2), kw1 = roleB ? (warp == 0 ? 6 : 7) : (warp == 0 ? 2 : 4);
+        const bool do_ones = roleB && warp == 1;
+        const uint64_t ones_desc = desc(ONES_HI, desc_lo(smem_u32(smem + G::OFF_ONES), 2048));
+        uint32_t ones_acc = 0;
+        int i = 0;
+        for (int u = u_first; u < p.n_units; u += u_step, ++i) {
+            const int buf = i & 1;
+            const int tile = u % tiles;
+            const int h0 = (tile / p.tiles_w) * G::TH;
+            const int npair = (min(G::TH, p.Hc - h0) + 1) >> 1;
+            const uint32_t a_base = desc_lo(smem_u32(smem + buf * G::BUF), 128);                 // LBO: next 8 positions (K)
+            const uint32_t b_base = desc_lo(smem_u32(smem + buf * G::BUF + G::X_BYTES), 128);    // LBO: next 8 columns (K)
+            mbar_wait(full + buf, (i >> 1) & 1);
+            fence_after();
+            if (elected) {
+                for (int pr = 0; pr < npair; ++pr) {
+                    const uint64_t b = desc(B_HI, b_base + pr * (G::G_PAIR >> 4));
+                    const uint32_t acc = (i == 0 && pr == 0) ? 0u : 1u;
+                    const uint32_t a_row = a_base + ((2 * pr * G::X_RP) >> 4);
+#pragma unroll 2
+                    for (int kw = kw0; kw < kw1; ++kw) {
+                        const uint32_t d = tmem_base + (kw - kw_base) * G::ACC_COLS;
+                        mma_bf16(d, desc(A_HI, a_row + kw), b, IDESC_N128, acc);
+                        mma_bf16(d, desc(A_HI, a_row + kw + (G::X_PART >> 4)), b, IDESC_N64, 1);
+                    }
+                    if (do_ones && (pr & 1) == grp) {
+                        mma_bf16(tmem_base + 3 * G::ACC_COLS, ones_desc, b, IDESC_N128, ones_acc);
+                        ones_acc = 1;
+                    }
+                }
+                commit(empty + buf);
+            }
+            __syncwarp();
+        }
+        if (elected) {
+            if (do_ones) *ones_used = ones_acc;
+            commit(done);
+        }
+        __syncwarp();
+    }
+    // ---- drain.  Lane m = (dy, ci) of accumulator a holds, per output channel co:
+    //        j = 0 (even rows): D[co] + D[64 + co]        -> kernel row 4g + dy      -> slot dy + 1
+    //        j = 1 (odd rows) : D[32 + co] + D[96 + co]   -> kernel row 4g + dy - 1  -> slot dy
+    //      (slot s <-> kh = 4g - 1 + s).  Two phases through the idle tile buffers: j = 0 stores slots 1..4, then j = 1 stores
+    //      slot 0 and adds to slots 1..3; each (co, ci, a, slot) is touched by one thread per phase.
+    float *out = p.partial + (size_t)blockIdx.x * G::BLK;
+    mbar_wait(done, 0);
+    fence_after();
+    __syncthreads();
+    {
+        const int q = warp & 3;                                          // TMEM lane quarter of this warp = dy
+        const int ci = lane;
+        float *stg = reinterpret_cast<float *>(smem);
+        const int nacc = roleB ? 3 : 4;
+        for (int a = (warp >> 2); a < nacc; a += 4) {
+            uint32_t v[32], v2[32];
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS;
+            ld32(ta, v);
+            ld32(ta + 64, v2);
+#pragma unroll
+            for (int co = 0; co < 32; ++co)
+                stg[(co * G::CIN + ci) * G::PITCH + a * G::SLOTS + q + 1] = __uint_as_float(v[co]) + __uint_as_float(v2[co]);
+        }
+        __syncthreads();
+        for (int a = (warp >> 2); a < nacc; a += 4) {
+            uint32_t v[32], v2[32];
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS;
+            ld32(ta + 32, v);
+            ld32(ta + 96, v2);
+#pragma unroll
+            for (int co = 0; co < 32; ++co) {
+                float *s = stg + (co * G::CIN + ci) * G::PITCH + a * G::SLOTS + q;
+                const float val = __uint_as_float(v[co]) + __uint_as_float(v2[co]);
+                *s = q == 0 ? val : *s + val;
+            }
+        }
+        // bias gradient (role B): every lane of the spare accumulator holds [sum G_hi(even) | sum G_hi(odd) | sum G_lo(even) | sum G_lo(odd)]
+        if (warp == 0) {
+            float bsum = 0.f;
+            if (roleB && *ones_used) {
+                uint32_t c0[32], c1[32];
+                const uint32_t ta = tmem_base + 3 * G::ACC_COLS;
+                ld32(ta, c0);
+                ld32(ta + 32, c1);
+                float s01[32];
+#pragma unroll
+                for (int co = 0; co < 32; ++co) s01[co] = __uint_as_float(c0[co]) + __uint_as_float(c1[co]);
+                ld32(ta + 64, c0);
+                ld32(ta + 96, c1);
+#pragma unroll
+                for (int co = 0; co < 32; ++co)
+                    if (co == lane) bsum = s01[co] + (__uint_as_float(c0[co]) + __uint_as_float(c1[co]));
+            }
+            out[G::NW_BLK + lane] = bsum;
+        }
+        fence_before();
+        __syncthreads();
+        for (int e = tid; e < G::NW_BLK; e += G::NT) {
+            const int cc = e / G::PER_CC, r = e - cc * G::PER_CC;
+            out[e] = (r < nacc * G::SLOTS) ? stg[cc * G::PITCH + r] : 0.f;
+        }
+    }
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)G::TMEM_COLS);
+}
+
+// The row-pair kernel takes the layer when its operands exist in image form: the tensor-core forward wrote eps1_mma, and the
+// packed backward read-out can write g_u as bf16 planes (even F, 16-byte aligned rows of 8 columns).
+bool wgrad_tc2_supported(const dcll_conv_layer *L) {
+    static int on = -1;                                     // DCLL_WGRAD_TC2=0: keep wgrad_tc_kernel (A/B measurements)
+    if (on < 0) {
+        const char *e = getenv("DCLL_WGRAD_TC2");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (!on) return false;
+    Geo g = geo_of(L);
+    return wgrad_tc_supported(L) && tc_supported(L) && L->Cin == 32 && L->eps1_mma && (g.Wc % 8) == 0 && L->K <= 32 &&
+           (((uintptr_t)L->pv | (uintptr_t)L->wo | (uintptr_t)L->g_u) % 16) == 0;
+}
+
+void wgrad_tc2_roles(const dcll_conv_layer *L, int *nA, int *nB) {
+    Geo g = geo_of(L);
+    const int n_units = L->B * ceil_div(g.Hc, 16) * ceil_div(g.Wc, 16);
+    // 74 CTA pairs: role A does 4 kernel columns per tile (8 x 4 x 113 cycles), role B 3 + half of the bias MMAs (8 x 3 x 113 + 4 x 64)
+    if (n_units >= 40) *nA = 40, *nB = 34;
+    else *nA = *nB = n_units < 37 ? n_units : 37;
+}
+
+int launch_wgrad_tc2(const dcll_conv_layer *L, float *partial, int *nA_out, int *nB_out, cudaStream_t st) {
+    using G = Wg2Geo;
+    Geo g = geo_of(L);
+    Wg2P p;
+    p.gimg = reinterpret_cast<const uint4 *>(L->g_u), p.ximg = reinterpret_cast<const uint4 *>(L->eps1_mma), p.partial = partial;
+    p.B = L->B, p.H = L->H, p.W = L->W, p.padH = L->padH, p.padW = L->padW, p.Hc = g.Hc, p.Wc = g.Wc;
+    p.tiles_h = ceil_div(g.Hc, G::TH), p.tiles_w = ceil_div(g.Wc, G::TW);
+    p.n_units = L->B * p.tiles_h * p.tiles_w;
+    wgrad_tc2_roles(L, &p.nA, &p.nB);
+    *nA_out = p.nA, *nB_out = p.nB;
+    DCLL_SMEM_ATTR(wgrad_tc2_kernel, G::SMEM);
+    launch_k(wgrad_tc2_kernel, 2 * (p.nA + p.nB), G::NT, G::SMEM, st, p);
+    DCLL_LAUNCH_OK("wgrad_tc2_kernel");
+    return DCLL_OK;
+}
+
+}  // namespace dcll
