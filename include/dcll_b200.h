@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DCLL_ABI_VERSION 9
+#define DCLL_ABI_VERSION 10
 
 enum { DCLL_OK = 0, DCLL_EINVAL = -1, DCLL_ECUDA = -2, DCLL_EUNSUPPORTED = -3 };
 
@@ -205,6 +205,23 @@ int dcll_net_window(dcll_conv_layer *layers, dcll_train_args *train, int n_layer
 int dcll_net_window_stats(dcll_conv_layer *layers, dcll_train_args *train, int n_layers, const void *x0,
                           const float *target, int64_t target_t_stride, int T, int train_mode, int burnin,
                           const int32_t *iter0, int32_t *clout, int32_t *hist, int hist_every, int hist_cap, void *stream);
+
+/* -- data-parallel window (the reference has no multi-GPU code: train.py:249-251 over a batch shard) -- *
+ * One process per GPU, identical weights, each rank its own B/world samples.  dcll_net_window_dp is dcll_net_window in
+ * training mode with one raw ncclAllReduce (average) per layer and timestep of the layer's gradient bucket
+ * [gW | gb | gWout | gbout] on a side stream, waited for right before the layer's next forward, where the identical Adam
+ * step is applied on every rank.  NCCL is dlopen'ed from `nccl_lib` (the libnccl.so.2 torch has loaded; NULL = default
+ * search path) -- the library itself links cudart only.  Rendezvous: rank 0 calls dcll_dp_unique_id, the host broadcasts the
+ * 128 bytes (torch.distributed), every rank calls dcll_dp_create (collective).  max_ctas > 0 caps the CTAs NCCL may use, so
+ * that the collectives do not evict the one-CTA-per-SM persistent kernels they overlap with.
+ * train[l]: apply_update = 0 and grad_w, grad_b[, grad_wout, grad_bout] back to back in bucket[l] (bucket_floats[l] floats). */
+typedef struct dcll_dp dcll_dp;
+int dcll_dp_unique_id(const char *nccl_lib, void *id128);
+int dcll_dp_create(const char *nccl_lib, const void *id128, int rank, int world, int max_ctas, dcll_dp **out);
+int dcll_dp_destroy(dcll_dp *dp);
+int dcll_net_window_dp(dcll_dp *dp, dcll_conv_layer *layers, dcll_train_args *train, int n_layers, const void *x0,
+                       const float *target, int64_t target_t_stride, int T, int burnin, const int32_t *iter0, int32_t *clout,
+                       float *const *bucket, const size_t *bucket_floats, void *stream);
 
 /* -- multi-timestep inference of the radio_ml_conv stack on a 16x16 plane (test_radio_ml.py:144-145, script geometry) -- *
  * One launch runs Tc timesteps of the three conv cores (1->32, 32->32, 32->32; 7x7, padding 3, no pooling) with one CTA

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdcll_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 OK, EINVAL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3
 COEF_SCALAR, COEF_CHANNEL, COEF_ELEMENT = 0, 1, 2
@@ -94,6 +94,11 @@ def _load():
         "dcll_infer_stack16": [P(ConvLayer), C.c_int, _fp, C.c_int, P(_fp), _fp],
         "dcll_conv_readout_rows": [P(ConvLayer), _fp, _fp],
         "dcll_vote": [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp],
+        "dcll_dp_unique_id": [C.c_char_p, _fp],
+        "dcll_dp_create": [C.c_char_p, _fp, C.c_int, C.c_int, C.c_int, P(_fp)],
+        "dcll_dp_destroy": [_fp],
+        "dcll_net_window_dp": [_fp, P(ConvLayer), P(TrainArgs), C.c_int, _fp, _fp, C.c_int64, C.c_int, C.c_int, P(C.c_int32), _fp,
+                               P(_fp), P(C.c_size_t), _fp],
         "dcll_quantize": [_fp, C.c_int, C.c_int, _fp, _fp, _fp],
         "dcll_dequantize": [_fp, _fp, C.c_int, C.c_int, _fp, _fp],
     }
@@ -134,7 +139,7 @@ EXPORTS = ["dcll_launch_count", "dcll_profile_enable", "dcll_profile_read", "dcl
            "dcll_conv_core_fwd", "dcll_conv_step_bwd_update", "dcll_conv_apply_update", "dcll_net_window", "dcll_vote",
            "dcll_quantize", "dcll_dequantize", "dcll_sizeof_dense_layer", "dcll_dense_step_fwd",
            "dcll_dense_step_bwd_update", "dcll_net_window_stats", "dcll_infer_stack16", "dcll_conv_readout_rows", "dcll_conv_step_fwd_chain",
-           "dcll_conv_chain_fusable"]
+           "dcll_conv_chain_fusable", "dcll_dp_unique_id", "dcll_dp_create", "dcll_dp_destroy", "dcll_net_window_dp"]
 
 
 def check(rc):
@@ -164,3 +169,24 @@ def current_stream():
     import torch
 
     return torch.cuda.current_stream().cuda_stream
+
+
+def nccl_library_path():
+    """The libnccl.so.2 this process has loaded (torch's bundled copy once torch.distributed's NCCL backend is up), else the
+    one shipped in the nvidia.nccl wheel, else None (default search path).  dcll_dp_* dlopen it by this path."""
+    try:
+        for line in open("/proc/self/maps"):
+            if "libnccl.so" in line:
+                return line.split()[-1]
+    except OSError:
+        pass
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for loc in (spec.submodule_search_locations or []) if spec else []:
+            p = os.path.join(loc, "lib", "libnccl.so.2")
+            if os.path.isfile(p):
+                return p
+    except Exception:
+        pass
+    return None

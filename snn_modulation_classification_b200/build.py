@@ -22,6 +22,20 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
 
+def _nccl_include():
+    """nccl.h for dp.cu (types only: the library itself is dlopen'ed at run time): torch's bundled copy, else the system's."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for loc in (spec.submodule_search_locations or []) if spec else []:
+            inc = os.path.join(loc, "include")
+            if os.path.isfile(os.path.join(inc, "nccl.h")):
+                return ["-I", inc]
+    except Exception:
+        pass
+    return ["-I", "/usr/include"] if os.path.isfile("/usr/include/nccl.h") else []
+
+
 def _sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -37,7 +51,7 @@ def _compile(src, force):
     deps = [os.path.join(CSRC, src)] + _headers()
     if not force and os.path.exists(obj) and all(os.path.getmtime(obj) >= os.path.getmtime(d) for d in deps):
         return obj, False
-    cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [NVCC] + FLAGS + (_nccl_include() if src == "dp.cu" else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -50,7 +64,7 @@ def build(force=False, verbose=True):
         results = list(ex.map(lambda s: _compile(s, force), _sources()))
     objs = [o for o, _ in results]
     if any(c for _, c in results) or not os.path.exists(LIB) or force:
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

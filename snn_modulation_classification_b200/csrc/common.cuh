@@ -122,13 +122,15 @@ struct WsLayout {
 WsLayout ws_layout(const dcll_conv_layer *L);
 
 // Launchers implemented in the individual .cu files (all asynchronous on `st`).
+// write_spikes = false (window driver, tensor-core path): nobody reads this step's spike tensor -- the consumer is the trace
+// update fused into this launch's epilogue, or there is none (last layer) -- so the epilogue does not store it.
 int launch_conv_fwd(const dcll_conv_layer *L, const void *x, cudaStream_t st, const dcll_conv_layer *next = nullptr,
-                    bool trace_done = false);
+                    bool trace_done = false, bool write_spikes = true);
 // tcgen05, split-bf16 x3.  Window driver only: `next` != null makes the epilogue also apply the NEXT layer's trace update
 // (its input is exactly the spike the epilogue thread just produced) and write that layer's operand image;
 // `trace_done` says the previous layer already did so for this one.
 int launch_conv_fwd_tc(const dcll_conv_layer *L, const void *x, cudaStream_t st, const dcll_conv_layer *next = nullptr,
-                       bool trace_done = false);
+                       bool trace_done = false, bool write_spikes = true);
 bool tc_trace_fusable(const dcll_conv_layer *L, const dcll_conv_layer *next);
 int launch_weight_mma(const dcll_conv_layer *L, const float *w, cudaStream_t st);
 int sync_kernel_weights(const dcll_conv_layer *L, cudaStream_t st);   // weight -> weight_t / weight_mma (quantised or not)

@@ -135,12 +135,12 @@ static int g_layer = 0;  // layer index of the step being enqueued (profile key 
 int prof_layer() { return g_layer; }
 
 static int step_fwd(dcll_conv_layer *L, const void *x, const float *target, int loss_kind, int32_t *clout, float *loss_out,
-                    cudaStream_t st, const dcll_conv_layer *next = nullptr, bool trace_done = false) {
+                    cudaStream_t st, const dcll_conv_layer *next = nullptr, bool trace_done = false, bool write_spikes = true) {
     prof_begin_layer_step();
     int rc;
     {
         ProfScope ps(KC_CONV_FWD, g_layer, st);
-        rc = launch_conv_fwd(L, x, st, next, trace_done);
+        rc = launch_conv_fwd(L, x, st, next, trace_done, write_spikes);
     }
     if (rc != DCLL_OK) return rc;
     L->cur ^= 1;
@@ -182,6 +182,37 @@ static int check_train(const dcll_conv_layer *L, const dcll_train_args *a, const
         DCLL_REQUIRE(a->grad_w && a->grad_b, DCLL_EINVAL, "%s: apply_update == 0 needs gradient buffers", who);
         DCLL_REQUIRE(!L->output_layer || (a->grad_wout && a->grad_bout), DCLL_EINVAL, "%s: needs output_ gradient buffers",
                      who);
+    }
+    return DCLL_OK;
+}
+
+// entry points of the data-parallel driver (dp.cu) into the per-layer steps above
+int dp_step_fwd(dcll_conv_layer *L, const void *x, const float *target, int loss_kind, int32_t *clout, cudaStream_t st,
+                const dcll_conv_layer *next, bool trace_done, bool write_spikes, int layer) {
+    g_layer = layer;
+    return step_fwd(L, x, target, loss_kind, clout, nullptr, st, next, trace_done, write_spikes);
+}
+int dp_step_bwd(dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st, int layer) {
+    g_layer = layer;
+    return step_bwd(L, a, st);
+}
+int dp_check(const dcll_conv_layer *layers, const dcll_train_args *train, int n_layers) {
+    for (int l = 0; l < n_layers; ++l) {
+        int rc = check_layer(&layers[l], "dcll_net_window_dp");
+        if (rc != DCLL_OK) return rc;
+        rc = check_train(&layers[l], &train[l], "dcll_net_window_dp");
+        if (rc != DCLL_OK) return rc;
+        DCLL_REQUIRE(train[l].loss_kind != DCLL_LOSS_EXTERNAL, DCLL_EUNSUPPORTED, "dcll_net_window_dp: external loss gradients need the per-step API");
+        DCLL_REQUIRE(train[l].adam_i2h.m_w && train[l].adam_i2h.v_w && train[l].adam_i2h.m_b && train[l].adam_i2h.v_b, DCLL_EINVAL,
+                     "dcll_net_window_dp: null Adam state (i2h)");
+        DCLL_REQUIRE(!layers[l].output_layer || (train[l].adam_out.m_w && train[l].adam_out.v_w && train[l].adam_out.m_b && train[l].adam_out.v_b),
+                     DCLL_EINVAL, "dcll_net_window_dp: null Adam state (output_)");
+        if (l > 0) {
+            Geo gp = geo_of(&layers[l - 1]);
+            DCLL_REQUIRE(layers[l].x_mode == DCLL_X_DENSE && layers[l].Cin == layers[l - 1].Cout && layers[l].H == gp.Hp &&
+                             layers[l].W == gp.Wp && layers[l].B == layers[0].B,
+                         DCLL_EINVAL, "dcll_net_window_dp: layer %d does not chain onto layer %d", l, l - 1);
+        }
     }
     return DCLL_OK;
 }
@@ -454,8 +485,10 @@ extern "C" __attribute__((visibility("default"))) int dcll_net_window_stats(dcll
             // the trace update of layer l+1 rides in the epilogue of layer l's tensor-core convolution where that is free
             const bool fuse_next = l + 1 < n_layers && tc_trace_fusable(L, &layers[l + 1]);
             const bool trace_done = l > 0 && tc_trace_fusable(&layers[l - 1], L);
+            // the spike tensor of this step is stored only when somebody reads it: the next layer's own trace pass
+            const bool spikes_read = l + 1 < n_layers && !fuse_next;
             int rc = step_fwd(L, x, do_train ? tgt : nullptr, do_train ? train[l].loss_kind : 0, co, nullptr, st,
-                              fuse_next ? &layers[l + 1] : nullptr, trace_done);
+                              fuse_next ? &layers[l + 1] : nullptr, trace_done, spikes_read);
             if (rc != DCLL_OK) return rc;
             if (hist && (it % hist_every) == 0 && hist_n[l] < hist_cap) {          // DCLLBase.forward :658-661
                 Geo g = geo_of(L);

@@ -339,6 +339,39 @@ static int launch_wg(const WgP &p, const dcll_conv_layer *L, cudaStream_t st) {
     return DCLL_EUNSUPPORTED;
 }
 
+// Adam on an already averaged gradient bucket [gW | gb | gWout | gbout] (data-parallel driver, dp.cu): the conv parameters go
+// through reduce_adam_kernel with the bucket as its single partial block, so weight_t and the tensor-core weight image are
+// refreshed by the same launch, as on the single-GPU path; output_ takes the flat kernel.
+int launch_bucket_adam(const dcll_conv_layer *L, dcll_train_args *a, const float *bucket, cudaStream_t st) {
+    Geo g = geo_of(L);
+    const int n_tot = g.nW + L->Cout;
+    {
+        AdamScalars sc = adam_scalars(a->adam_i2h, a->adam_i2h.step + 1);
+        dcll_adam &o = a->adam_i2h;
+        ProfScope ps(KC_ADAM, 0, st);
+        launch_k(reduce_adam_kernel, ceil_div(n_tot, 64), 256, 0, st, bucket, 1, n_tot, g.nW, L->Cout, g.CoutPad, L->Cin * L->KH * L->KW,
+                 L->weight, L->weight_t, L->bias, o.m_w, o.v_w, o.m_b, o.v_b, (float *)nullptr, (float *)nullptr, 1, sc,
+                 L->quantized ? nullptr : reinterpret_cast<__nv_bfloat16 *>(L->weight_mma), L->Cin, L->KH * L->KW, L->KW);
+        DCLL_LAUNCH_OK("reduce_adam_kernel");
+        a->adam_i2h.step += 1;
+        if (L->quantized) {
+            int rc = sync_kernel_weights(L, st);
+            if (rc != DCLL_OK) return rc;
+        }
+    }
+    if (L->output_layer) {
+        AdamScalars so = adam_scalars(a->adam_out, a->adam_out.step + 1);
+        const float *gwout = bucket + n_tot, *gbout = gwout + (size_t)L->K * g.F;
+        ProfScope ps(KC_ADAM, 1, st);
+        int rc = launch_adam_flat(L->wout, gwout, a->adam_out.m_w, a->adam_out.v_w, (size_t)L->K * g.F, so, st);
+        if (rc != DCLL_OK) return rc;
+        rc = launch_adam_flat(L->bout, gbout, a->adam_out.m_b, a->adam_out.v_b, (size_t)L->K, so, st);
+        if (rc != DCLL_OK) return rc;
+        a->adam_out.step += 1;
+    }
+    return DCLL_OK;
+}
+
 int launch_wgrad(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st) {
     Geo g = geo_of(L);
     WsLayout ws = ws_layout(L);

@@ -24,14 +24,19 @@
 //   * g_u: the packed backward read-out (readout_bwd2_kernel<.., IMG>) leaves it as bf16 {hi,lo} NCHW planes
 //     [b][part][co][Hc][Wc] in the g_u buffer (same bytes as fp32).  16-byte pieces (8 columns of one channel) are staged as the
 //     K-MAJOR B operand: core matrix = [co % 8][8 columns], N-group order (part, row parity, co/8), two K chunks per group.
-// All loads are cp.async (zero fill outside the picture); 12 loader warps fill one half of a double buffer while two issuer
-// warps work on the other; mbarriers both ways.  Each CTA leaves its accumulators as one compact partial block
+// Tiles are moved by TMA: one thread issues three cp.async.bulk.tensor boxes per tile (tensor maps whose DIMENSION ORDER is chosen
+// so that the box lands in shared memory already in operand order; zero fill outside the picture) into one half of a double
+// buffer while two issuer warps work on the other; mbarriers both ways.  (The first version staged the same tiles with 5 216
+// 16-byte cp.async per tile: ncu showed 2.4 GB of L2 sector reads per launch for 1.37 GB of tile bytes -- nearly one 32-byte
+// sector per 16-byte piece -- and the kernel bound by that load path: 0.34 ms with the MMAs removed, 0.28 ms with the loads removed.)  Each CTA leaves its accumulators as one compact partial block
 // [co][ci][kernel column a][slot = kh - (4g-1)] (+ 32 bias sums); reduce_adam_rp_kernel (wgrad.cu) adds the blocks that hold a
 // given element in a fixed order -- deterministic, no float atomics.
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "tmap.cuh"
 
 namespace dcll {
 
@@ -42,6 +47,9 @@ struct Wg2P {
     int B, H, W, padH, padW, Hc, Wc;
     int tiles_h, tiles_w, n_units;
     int nA, nB;          // CTA pairs of role A (kernel columns 0..3) and role B (4..6 + bias)
+    int use_tma;         // tiles by cp.async.bulk.tensor (3 loads per tile) instead of 5216 16-byte cp.async
+    int dbg;             // DCLL_WG2_DEBUG (timing experiments only, results are garbage): bit 0 skip eps1 loads, bit 1 skip g_u loads,
+                         // bit 2 skip the MMAs
 };
 
 struct Wg2Geo {
@@ -51,9 +59,12 @@ struct Wg2Geo {
     static constexpr int XROWS = TH + DY - 2;               // halo rows 2*pair + dy of one kernel-row group: 18
     static constexpr int XCOLS = TW + KW - 1;               // 22
     static constexpr int X_CP = XCOLS * 16, X_RP = CGR * X_CP, X_PART = XROWS * X_RP, X_BYTES = 2 * X_PART;
-    static constexpr int G_GRP = 256;                        // one N-group: [k chunk 2][co % 8][8 columns] bf16
-    static constexpr int G_PAIR = 16 * G_GRP;                // (part 2, row parity 2, co/8 4) groups
-    static constexpr int G_BYTES = PAIRS * G_PAIR;
+    // g_u tile: [k chunk 2][pair 8][part 2][row parity 2][co 32][8 columns] bf16 -- exactly what ONE tensor-map box per k chunk
+    // delivers; an N-group (8 channels) is 128 bytes, 16 groups (part, parity, co/8) per pair, the k chunks G_KC apart
+    static constexpr int G_GRP = 128;
+    static constexpr int G_PAIR = 16 * G_GRP;
+    static constexpr int G_KC = PAIRS * G_PAIR;              // 16 KB
+    static constexpr int G_BYTES = 2 * G_KC;
     static constexpr int BUF = X_BYTES + G_BYTES;
     static constexpr int OFF_ONES = 2 * BUF, OFF_BAR = OFF_ONES + 4096, SMEM = OFF_BAR + 128;
     static constexpr int NT = 512, LOADER_WARPS = 12;
@@ -69,7 +80,8 @@ struct Wg2Geo {
 
 size_t wgrad_tc2_partial_floats() { return (size_t)148 * Wg2Geo::BLK; }
 
-__global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p) {
+__global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const __grid_constant__ TmapDesc tmx,
+                                                           const __grid_constant__ TmapDesc tmg) {
     using G = Wg2Geo;
     using namespace tc;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -80,7 +92,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) mbar_init(full + i, G::LOADER_WARPS), mbar_init(empty + i, 2);
+        for (int i = 0; i < 2; ++i) mbar_init(full + i, p.use_tma ? 1 : G::LOADER_WARPS), mbar_init(empty + i, 2);
         mbar_init(done, 2);
         *ones_used = 0u;
         mbar_fence_init();
@@ -103,8 +115,31 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p) {
     const int tiles = p.tiles_h * p.tiles_w;
     const int row_off = G::DY * grp;
 
-    if (warp >= 4) {
-        // ================= loaders: 384 threads, everything by cp.async =================
+    if (warp >= 4 && p.use_tma) {
+        // ================= tile producer, TMA: one thread, three tensor-map boxes per tile (UTMALDG), zero fill outside the picture:
+        //   eps1 image  dims (8 ci, W, ci/8, H, (b, part))          box (8, 22, 4, 18, 2)  -> [part][row][ci/8][col][8 ci]
+        //   g_u planes  dims (w, co, row parity, (b, part), row/2)  box (8, 32, 2, 2, 8)   -> [pair][part][parity][co][8 w], per k chunk
+        if (warp == 4 && lane == 0) {
+            tma_prefetch_desc(&tmx);
+            tma_prefetch_desc(&tmg);
+            int i = 0;
+            for (int u = u_first; u < p.n_units; u += u_step, ++i) {
+                const int buf = i & 1;
+                const uint32_t sX = smem_u32(smem + buf * G::BUF), sG = sX + G::X_BYTES, bar = smem_u32(full + buf);
+                const int b = u / tiles, tile = u - b * tiles;
+                const int th_i = tile / p.tiles_w, tw_i = tile - th_i * p.tiles_w;
+                const int h0 = th_i * G::TH, w0 = tw_i * G::TW;
+                if (i >= 2) mbar_wait(empty + buf, ((i >> 1) - 1) & 1);
+                mbar_expect_tx(full + buf, ((p.dbg & 1) ? 0 : G::X_BYTES) + ((p.dbg & 2) ? 0 : G::G_BYTES));
+                if (!(p.dbg & 1)) tma_load_5d(sX, &tmx, bar, 0, w0 - p.padW, 0, h0 - p.padH + row_off, 2 * b);
+                if (!(p.dbg & 2)) {
+                    tma_load_5d(sG, &tmg, bar, w0, 0, 0, 2 * b, h0 >> 1);
+                    tma_load_5d(sG + G::G_KC, &tmg, bar, w0 + 8, 0, 0, 2 * b, h0 >> 1);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= loaders (fallback when the driver refuses the tensor maps): 384 threads, everything by cp.async =================
         const int l = (warp - 4) * 32 + lane;
         const size_t hw = (size_t)p.H * p.W;
         const size_t gplane = (size_t)p.Hc * p.Wc / 8;            // 16-byte pieces per (b, part, co) plane (Wc % 8 == 0)
@@ -117,7 +152,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p) {
             const int th_i = tile / p.tiles_w, tw_i = tile - th_i * p.tiles_w;
             const int h0 = th_i * G::TH, w0 = tw_i * G::TW;
             if (i >= 2) mbar_wait(empty + buf, ((i >> 1) - 1) & 1);   // MMAs of unit i-2 have finished reading this half
-            {   // ---- eps1 halo tile: [row][cg][col][8 ci], bf16 hi | lo
+            if (!(p.dbg & 1)) {   // ---- eps1 halo tile: [row][cg][col][8 ci], bf16 hi | lo
                 const uint4 *src0 = p.ximg + (size_t)b * 2 * G::CGR * hw;
                 for (int idx = l; idx < 2 * G::XROWS * G::CGR * G::XCOLS; idx += G::LOADER_WARPS * 32) {
                     const int c = idx % G::XCOLS;
@@ -133,14 +168,14 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p) {
                                  : "memory");
                 }
             }
-            {   // ---- g_u tile: piece = 8 columns of one channel; N-group (part, row parity, co/8), k chunk, co % 8
+            if (!(p.dbg & 2)) {   // ---- g_u tile: piece = 8 columns of one channel; N-group (part, row parity, co/8), k chunk, co % 8
                 const uint4 *src0 = p.gimg + (size_t)b * 2 * G::COUT * gplane;
                 for (int idx = l; idx < 2 * G::COUT * G::TH * 2; idx += G::LOADER_WARPS * 32) {
                     const int kc = idx & 1, row = (idx >> 1) & 15, co = (idx >> 5) & 31, part = idx >> 10;
                     const int oh = h0 + row, ow = w0 + 8 * kc;
                     const bool in = oh < p.Hc && ow < p.Wc;
                     const uint4 *src = in ? src0 + (size_t)(part * G::COUT + co) * gplane + (size_t)oh * wc8 + (ow >> 3) : src0;
-                    const uint32_t dst = sG + (row >> 1) * G::G_PAIR + (part * 8 + (row & 1) * 4 + (co >> 3)) * G::G_GRP + kc * 128 + (co & 7) * 16;
+                    const uint32_t dst = sG + kc * G::G_KC + (row >> 1) * G::G_PAIR + (part * 8 + (row & 1) * 4 + (co >> 3)) * G::G_GRP + (co & 7) * 16;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(in ? 16u : 0u) : "memory");
                 }
             }
@@ -169,11 +204,11 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p) {
             const int h0 = (tile / p.tiles_w) * G::TH;
             const int npair = (min(G::TH, p.Hc - h0) + 1) >> 1;
             const uint32_t a_base = desc_lo(smem_u32(smem + buf * G::BUF), 128);                 // LBO: next 8 positions (K)
-            const uint32_t b_base = desc_lo(smem_u32(smem + buf * G::BUF + G::X_BYTES), 128);    // LBO: next 8 columns (K)
+            const uint32_t b_base = desc_lo(smem_u32(smem + buf * G::BUF + G::X_BYTES), G::G_KC);   // LBO: next 8 columns (K)
             mbar_wait(full + buf, (i >> 1) & 1);
             fence_after();
             if (elected) {
-                for (int pr = 0; pr < npair; ++pr) {
+                for (int pr = 0; pr < ((p.dbg & 4) ? (i == 0 ? 1 : 0) : npair); ++pr) {
                     const uint64_t b = desc(B_HI, b_base + pr * (G::G_PAIR >> 4));
                     const uint32_t acc = (i == 0 && pr == 0) ? 0u : 1u;
                     const uint32_t a_row = a_base + ((2 * pr * G::X_RP) >> 4);
@@ -296,8 +331,31 @@ int launch_wgrad_tc2(const dcll_conv_layer *L, float *partial, int *nA_out, int 
     p.n_units = L->B * p.tiles_h * p.tiles_w;
     wgrad_tc2_roles(L, &p.nA, &p.nB);
     *nA_out = p.nA, *nB_out = p.nB;
+    static int dbg = -1, tma = -1;
+    if (dbg < 0) {
+        const char *e = getenv("DCLL_WG2_DEBUG");
+        dbg = e ? atoi(e) : 0;
+        e = getenv("DCLL_WG2_TMA");                         // 0: cp.async loaders (A/B measurements)
+        tma = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.dbg = dbg;
+    // tensor maps (cached per buffer and geometry).  The row-parity / row-pair split of the g_u rows needs an even Hc; global
+    // strides must be multiples of 16 bytes (Wc % 8 == 0 is part of wgrad_tc2_supported).
+    TmapDesc tmx, tmg;
+    memset(&tmx, 0, sizeof(tmx)), memset(&tmg, 0, sizeof(tmg));
+    p.use_tma = 0;
+    if (tma && (g.Hc % 2) == 0) {
+        const uint64_t hw16 = (uint64_t)L->H * L->W * 16, plane = (uint64_t)g.Hc * g.Wc * 2;
+        const uint64_t xd[5] = {8, (uint64_t)L->W, 4, (uint64_t)L->H, (uint64_t)2 * L->B};
+        const uint64_t xs[4] = {16, hw16, (uint64_t)L->W * 16, 4 * hw16};
+        const uint32_t xb[5] = {8, (uint32_t)G::XCOLS, 4, (uint32_t)G::XROWS, 2};
+        const uint64_t gd[5] = {(uint64_t)g.Wc, 32, 2, (uint64_t)2 * L->B, (uint64_t)g.Hc / 2};
+        const uint64_t gs[4] = {plane, (uint64_t)g.Wc * 2, 32 * plane, (uint64_t)g.Wc * 4};
+        const uint32_t gb[5] = {8, 32, 2, 2, (uint32_t)G::PAIRS};
+        if (tmap_bf16(&tmx, L->eps1_mma, 5, xd, xs, xb) && tmap_bf16(&tmg, L->g_u, 5, gd, gs, gb)) p.use_tma = 1;
+    }
     DCLL_SMEM_ATTR(wgrad_tc2_kernel, G::SMEM);
-    launch_k(wgrad_tc2_kernel, 2 * (p.nA + p.nB), G::NT, G::SMEM, st, p);
+    launch_k(wgrad_tc2_kernel, 2 * (p.nA + p.nB), G::NT, G::SMEM, st, p, tmx, tmg);
     DCLL_LAUNCH_OK("wgrad_tc2_kernel");
     return DCLL_OK;
 }

@@ -234,22 +234,48 @@ class ConvNetwork(torch.nn.Module):
                     _store_steps(states[i][1], trains[i].adam_out.step)
         return clout
 
-    def learn_window_dp(self, x, labels, group=None):
+    def _dp_handle(self, group, max_ctas):
+        """The raw-NCCL communicator of the C driver for `group` (created once: rank 0 draws the unique id, the ranks receive
+        it through torch.distributed, every rank joins)."""
+        import torch.distributed as dist
+        key = (id(group), dist.get_rank(group), dist.get_world_size(group), int(max_ctas))
+        h = getattr(self, '_dp', None)
+        if h is not None and h['key'] == key:
+            return h['dp']
+        if h is not None:
+            _lib.check(_lib.lib.dcll_dp_destroy(h['dp']))
+        lib_path = _lib.nccl_library_path()
+        lib_c = lib_path.encode() if lib_path else None
+        dev = self.dcll_slices[0].dclllayer.i2h.weight.device
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if dist.get_rank(group) == 0:
+            buf = (ctypes.c_uint8 * 128)()
+            _lib.check(_lib.lib.dcll_dp_unique_id(lib_c, ctypes.cast(buf, ctypes.c_void_p)))
+            uid = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+        uid = uid.to(dev)
+        dist.broadcast(uid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        buf = (ctypes.c_uint8 * 128)(*uid.cpu().tolist())
+        dp = ctypes.c_void_p()
+        _lib.check(_lib.lib.dcll_dp_create(lib_c, ctypes.cast(buf, ctypes.c_void_p), dist.get_rank(group),
+                                           dist.get_world_size(group), int(max_ctas), ctypes.byref(dp)))
+        self._dp = dict(key=key, dp=dp)
+        return dp
+
+    def learn_window_dp(self, x, labels, group=None, max_ctas=None):
         """Data-parallel ``learn_window``: every rank holds identical weights and its own shard of the batch
         (samples are independent in the forward pass, the state and the read-outs; the only coupling is the
         mean over the batch in the local loss).  Each layer's local gradients (gW, gb and, on the output
         layer, gWout, gbout) live in one flat bucket that is averaged over ranks with a single NCCL
         all-reduce per layer per timestep; the collective of layer l overlaps the forward/backward of layers
         l+1.. and is only waited for right before layer l's next forward, where the identical Adam step is
-        applied on every rank.  Equals the single-process run at the global batch up to summation order."""
+        applied on every rank.  Equals the single-process run at the global batch up to summation order.
+
+        With the NCCL backend the whole window runs inside the C driver (``dcll_net_window_dp``: raw ncclAllReduce on a
+        side stream, no per-timestep Python); other backends (gloo in the CPU tests) take the per-layer Python loop."""
         import torch.distributed as dist
         n = self.num_layers
         x_t, x_mode = (x.cells, _lib.X_CELLS) if isinstance(x, SpikeCells) else (_as_cuda_f32(x), _lib.X_DENSE)
         T, batch = int(x_t.shape[0]), int(x_t.shape[1])
-        win = self._window_buffers(batch)
-        Layers, Trains = _lib.ConvLayer * n, _lib.TrainArgs * n
-        layers, trains = Layers(), Trains()
-        olds, states, buckets, pending, needs_apply = [], [], [], [None] * n, [False] * n
         for s in self.dcll_slices:
             lay = s.dclllayer
             if lay.i2h.state.eps0.shape[0] != batch:
@@ -261,9 +287,17 @@ class ConvNetwork(torch.nn.Module):
                 raise NotImplementedError('learn_window_dp needs torch.optim.Adam slices')
             if _loss_kind(s.crit) == _lib.LOSS_EXTERNAL:
                 raise NotImplementedError('learn_window_dp implements SmoothL1Loss / MSELoss / L1Loss')
+        win = self._window_buffers(batch)
+        Layers, Trains = _lib.ConvLayer * n, _lib.TrainArgs * n
+        layers, trains = Layers(), Trains()
+        olds, states, buckets = [], [], []
         target = _as_cuda_f32(labels)
+        t_stride = 0
         if target.dim() == 3:
-            target = target[0].contiguous()
+            if target.shape[0] == T and T > 1:
+                t_stride = target.shape[1] * target.shape[2]
+            elif target.shape[0] != 1 and target.shape[0] != T:
+                raise ValueError('labels [T,B,K] must cover the window: got %d rows for T = %d' % (target.shape[0], T))
         for i, s in enumerate(self.dcll_slices):
             lay = s.dclllayer
             old, _ = lay._fill_desc(layers[i], batch, x_mode if i == 0 else _lib.X_DENSE, win['outs'][i])
@@ -281,11 +315,38 @@ class ConvNetwork(torch.nn.Module):
             buckets.append(flat)
         clout = torch.empty((T, n, batch), dtype=torch.int32, device=x_t.device)
         stream = _lib.current_stream()
-        step_fwd, step_bwd, apply = _lib.lib.dcll_conv_step_fwd, _lib.lib.dcll_conv_step_bwd_update, \
-            _lib.lib.dcll_conv_apply_update
+        burnin = int(self.dcll_slices[0].burnin)
+        if dist.get_backend(group) == 'nccl':
+            if max_ctas is None:
+                max_ctas = int(os.environ.get('DCLL_DP_MAX_CTAS', '8'))
+            dp = self._dp_handle(group, max_ctas)
+            iter0 = (ctypes.c_int32 * n)(*[int(s.iter) for s in self.dcll_slices])
+            bptr = (ctypes.c_void_p * n)(*[_lib.ptr(b) for b in buckets])
+            bn = (ctypes.c_size_t * n)(*[b.numel() for b in buckets])
+            _lib.check(_lib.lib.dcll_net_window_dp(dp, layers, trains, n, _lib.ptr(x_t), _lib.ptr(target), t_stride, T, burnin,
+                                                   iter0, _lib.ptr(clout), bptr, bn, stream))
+            # the side stream's last collective was waited for by the main stream inside the driver: the buckets may be freed
+        else:
+            self._learn_window_dp_python(layers, trains, buckets, x_t, target, t_stride, T, clout, group, stream, burnin)
+        for i, s in enumerate(self.dcll_slices):
+            s.dclllayer.i2h._commit_state(*olds[i], flips=T)
+            s.dclllayer._ctx = None
+            first = max(0, int(s.burnin) - int(s.iter) - 1)
+            if first < T:
+                s.clout.extend(clout[first:, i, :])
+            s.iter += T
+            _store_steps(states[i][0], trains[i].adam_i2h.step)
+            if s.dclllayer.output_layer:
+                _store_steps(states[i][1], trains[i].adam_out.step)
+        return clout
+
+    def _learn_window_dp_python(self, layers, trains, buckets, x_t, target, t_stride, T, clout, group, stream, burnin):
+        """The same schedule issued layer by layer from Python over torch.distributed (any backend)."""
+        n = self.num_layers
+        pending, needs_apply = [None] * n, [False] * n
+        step_bwd, apply = _lib.lib.dcll_conv_step_bwd_update, _lib.lib.dcll_conv_apply_update
         x_stride = x_t[0].numel() * x_t.element_size()
         x_base = x_t.data_ptr()
-        burnin = int(self.dcll_slices[0].burnin)
         iters = [int(s.iter) for s in self.dcll_slices]
 
         def finish(i):
@@ -306,6 +367,7 @@ class ConvNetwork(torch.nn.Module):
         for t in range(T):
             for i in range(n):
                 finish(i)
+                trains[i].target = target.data_ptr() + t * t_stride * 4
                 xin = x_base + t * x_stride if i == 0 else layers[i - 1].spikes
                 _lib.check(chain(ctypes.byref(layers[i]), ctypes.byref(layers[i + 1]) if fuse[i] else None,
                                  1 if i > 0 and fuse[i - 1] else 0, xin, clout[t, i].data_ptr(), stream))
@@ -316,17 +378,6 @@ class ConvNetwork(torch.nn.Module):
                     needs_apply[i] = True
         for i in range(n):
             finish(i)
-        for i, s in enumerate(self.dcll_slices):
-            s.dclllayer.i2h._commit_state(*olds[i], flips=T)
-            s.dclllayer._ctx = None
-            first = max(0, int(s.burnin) - int(s.iter) - 1)
-            if first < T:
-                s.clout.extend(clout[first:, i, :])
-            s.iter += T
-            _store_steps(states[i][0], trains[i].adam_i2h.step)
-            if s.dclllayer.output_layer:
-                _store_steps(states[i][1], trains[i].adam_out.step)
-        return clout
 
     def learn_window(self, x, labels):
         """``for t in range(T): self.learn(x[t], labels[t])`` (train.py:249-251) in one call."""
