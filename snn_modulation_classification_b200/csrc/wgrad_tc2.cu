@@ -24,11 +24,12 @@
 //   * g_u: the packed backward read-out (readout_bwd2_kernel<.., IMG>) leaves it as bf16 {hi,lo} NCHW planes
 //     [b][part][co][Hc][Wc] in the g_u buffer (same bytes as fp32).  16-byte pieces (8 columns of one channel) are staged as the
 //     K-MAJOR B operand: core matrix = [co % 8][8 columns], N-group order (part, row parity, co/8), two K chunks per group.
-// Tiles are moved by TMA: one thread issues three cp.async.bulk.tensor boxes per tile (tensor maps whose DIMENSION ORDER is chosen
-// so that the box lands in shared memory already in operand order; zero fill outside the picture) into one half of a double
-// buffer while two issuer warps work on the other; mbarriers both ways.  (The first version staged the same tiles with 5 216
-// 16-byte cp.async per tile: ncu showed 2.4 GB of L2 sector reads per launch for 1.37 GB of tile bytes -- nearly one 32-byte
-// sector per 16-byte piece -- and the kernel bound by that load path: 0.34 ms with the MMAs removed, 0.28 ms with the loads removed.)  Each CTA leaves its accumulators as one compact partial block
+// Tiles are moved by TMA: one thread issues three cp.async.bulk.tensor boxes per unit of 8 rows x 16 columns (tensor maps whose
+// DIMENSION ORDER is chosen so that the box lands in shared memory already in operand order; zero fill outside the picture)
+// through a FOUR-stage ring while two issuer warps consume; mbarriers both ways.  (History, B200 measurements: the first version
+// staged 16-row tiles with 5 216 16-byte cp.async per tile into a double buffer -- 0.39 ms per launch, 0.34 ms with the MMAs
+// removed and 0.27 ms with the loads removed: bound by the load path.  One TMA box instead of the cp.async changed nothing
+// (0.35 ms loads-only): it is the LATENCY of a tile load with a single tile in flight per SM, 12 B/cycle/SM, hence the deeper ring.)  Each CTA leaves its accumulators as one compact partial block
 // [co][ci][kernel column a][slot = kh - (4g-1)] (+ 32 bias sums); reduce_adam_rp_kernel (wgrad.cu) adds the blocks that hold a
 // given element in a fixed order -- deterministic, no float atomics.
 #include <cuda_bf16.h>
@@ -41,41 +42,41 @@
 namespace dcll {
 
 struct Wg2P {
-    const uint4 *gimg;   // g_u as bf16 {hi,lo} NCHW planes, in 16-byte pieces
-    const uint4 *ximg;   // eps1 operand image
-    float *partial;      // [n_cta][WG2_BLK]
+    float *partial;      // [n_cta][Wg2Geo::BLK]
     int B, H, W, padH, padW, Hc, Wc;
     int tiles_h, tiles_w, n_units;
     int nA, nB;          // CTA pairs of role A (kernel columns 0..3) and role B (4..6 + bias)
-    int use_tma;         // tiles by cp.async.bulk.tensor (3 loads per tile) instead of 5216 16-byte cp.async
     int dbg;             // DCLL_WG2_DEBUG (timing experiments only, results are garbage): bit 0 skip eps1 loads, bit 1 skip g_u loads,
                          // bit 2 skip the MMAs
 };
 
 struct Wg2Geo {
     static constexpr int KH = 7, KW = 7, CIN = 32, COUT = 32;
-    static constexpr int TH = 16, TW = 16, PAIRS = TH / 2;
+    static constexpr int TH = 8, TW = 16, PAIRS = TH / 2;   // a unit = 8 output rows x 16 columns = 4 row pairs
     static constexpr int CGR = 4, DY = 4;
-    static constexpr int XROWS = TH + DY - 2;               // halo rows 2*pair + dy of one kernel-row group: 18
+    static constexpr int XROWS = TH + DY - 2;               // halo rows 2*pair + dy of one kernel-row group: 10
     static constexpr int XCOLS = TW + KW - 1;               // 22
     static constexpr int X_CP = XCOLS * 16, X_RP = CGR * X_CP, X_PART = XROWS * X_RP, X_BYTES = 2 * X_PART;
-    // g_u tile: [k chunk 2][pair 8][part 2][row parity 2][co 32][8 columns] bf16 -- exactly what ONE tensor-map box per k chunk
+    // g_u tile: [k chunk 2][pair 4][part 2][row parity 2][co 32][8 columns] bf16 -- exactly what ONE tensor-map box per k chunk
     // delivers; an N-group (8 channels) is 128 bytes, 16 groups (part, parity, co/8) per pair, the k chunks G_KC apart
     static constexpr int G_GRP = 128;
     static constexpr int G_PAIR = 16 * G_GRP;
-    static constexpr int G_KC = PAIRS * G_PAIR;              // 16 KB
+    static constexpr int G_KC = PAIRS * G_PAIR;              // 8 KB
     static constexpr int G_BYTES = 2 * G_KC;
-    static constexpr int BUF = X_BYTES + G_BYTES;
-    static constexpr int OFF_ONES = 2 * BUF, OFF_BAR = OFF_ONES + 4096, SMEM = OFF_BAR + 128;
-    static constexpr int NT = 512, LOADER_WARPS = 12;
+    static constexpr int BUF = X_BYTES + G_BYTES;            // 44 544 B per pipeline stage
+    // FOUR stages: a tile load takes ~2.7 us from request to landing (measured: loads alone 0.34 ms per launch with one tile in
+    // flight per SM -- 12 B/cycle/SM, a third of what L2 can deliver), the MMAs of a unit ~1 us, so three loads must be in flight
+    static constexpr int NSTAGE = 4;
+    static constexpr int OFF_ONES = NSTAGE * BUF, OFF_BAR = OFF_ONES + 4096, SMEM = OFF_BAR + 128;
+    static constexpr int NT = 512;
     static constexpr int ACC_COLS = 128, TMEM_COLS = 512;
     static constexpr int SLOTS = 5, NACC = 4, PER_CC = NACC * SLOTS;   // floats per (co, ci) in a partial block
     static constexpr int PITCH = PER_CC + 1;                 // staging pitch (odd: conflict-free across ci)
     static constexpr int NW_BLK = COUT * CIN * PER_CC;       // 20 480
     static constexpr int BLK = NW_BLK + COUT;                // + bias sums
     static_assert(SMEM <= 227 * 1024, "shared memory");
-    static_assert(COUT * CIN * PITCH * 4 <= 2 * BUF, "staging fits the tile buffers");
-    static_assert(X_PART % 16 == 0 && BUF % 128 == 0, "alignment");
+    static_assert(COUT * CIN * PITCH * 4 <= NSTAGE * BUF, "staging fits the tile buffers");
+    static_assert(X_PART % 16 == 0 && BUF % 128 == 0 && X_BYTES % 128 == 0 && G_KC % 128 == 0, "alignment");
 };
 
 size_t wgrad_tc2_partial_floats() { return (size_t)148 * Wg2Geo::BLK; }
@@ -86,13 +87,13 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
     using namespace tc;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + G::OFF_BAR);
-    uint64_t *full = bars, *empty = bars + 2, *done = bars + 4;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
+    uint64_t *full = bars, *empty = bars + G::NSTAGE, *done = bars + 2 * G::NSTAGE;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * G::NSTAGE + 1);
     uint32_t *ones_used = tmem_slot + 1;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) mbar_init(full + i, p.use_tma ? 1 : G::LOADER_WARPS), mbar_init(empty + i, 2);
+        for (int i = 0; i < G::NSTAGE; ++i) mbar_init(full + i, 1), mbar_init(empty + i, 2);
         mbar_init(done, 2);
         *ones_used = 0u;
         mbar_fence_init();
@@ -115,75 +116,29 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
     const int tiles = p.tiles_h * p.tiles_w;
     const int row_off = G::DY * grp;
 
-    if (warp >= 4 && p.use_tma) {
-        // ================= tile producer, TMA: one thread, three tensor-map boxes per tile (UTMALDG), zero fill outside the picture:
-        //   eps1 image  dims (8 ci, W, ci/8, H, (b, part))          box (8, 22, 4, 18, 2)  -> [part][row][ci/8][col][8 ci]
-        //   g_u planes  dims (w, co, row parity, (b, part), row/2)  box (8, 32, 2, 2, 8)   -> [pair][part][parity][co][8 w], per k chunk
-        if (warp == 4 && lane == 0) {
+    if (warp == 4) {
+        // ================= tile producer: one thread, three tensor-map boxes per unit (UTMALDG), zero fill outside the picture:
+        //   eps1 image  dims (8 ci, W, ci/8, H, (b, part))          box (8, 22, 4, 10, 2)  -> [part][row][ci/8][col][8 ci]
+        //   g_u planes  dims (w, co, row parity, (b, part), row/2)  box (8, 32, 2, 2, 4)   -> [pair][part][parity][co][8 w], per k chunk
+        // It runs up to NSTAGE units ahead of the issuers.
+        if (lane == 0) {
             tma_prefetch_desc(&tmx);
             tma_prefetch_desc(&tmg);
             int i = 0;
             for (int u = u_first; u < p.n_units; u += u_step, ++i) {
-                const int buf = i & 1;
-                const uint32_t sX = smem_u32(smem + buf * G::BUF), sG = sX + G::X_BYTES, bar = smem_u32(full + buf);
+                const int sg = i % G::NSTAGE;
+                const uint32_t sX = smem_u32(smem + sg * G::BUF), sG = sX + G::X_BYTES, bar = smem_u32(full + sg);
                 const int b = u / tiles, tile = u - b * tiles;
                 const int th_i = tile / p.tiles_w, tw_i = tile - th_i * p.tiles_w;
                 const int h0 = th_i * G::TH, w0 = tw_i * G::TW;
-                if (i >= 2) mbar_wait(empty + buf, ((i >> 1) - 1) & 1);
-                mbar_expect_tx(full + buf, ((p.dbg & 1) ? 0 : G::X_BYTES) + ((p.dbg & 2) ? 0 : G::G_BYTES));
+                if (i >= G::NSTAGE) mbar_wait(empty + sg, ((i / G::NSTAGE) - 1) & 1);   // MMAs of unit i-NSTAGE have read this stage
+                mbar_expect_tx(full + sg, ((p.dbg & 1) ? 0 : G::X_BYTES) + ((p.dbg & 2) ? 0 : G::G_BYTES));
                 if (!(p.dbg & 1)) tma_load_5d(sX, &tmx, bar, 0, w0 - p.padW, 0, h0 - p.padH + row_off, 2 * b);
                 if (!(p.dbg & 2)) {
                     tma_load_5d(sG, &tmg, bar, w0, 0, 0, 2 * b, h0 >> 1);
                     tma_load_5d(sG + G::G_KC, &tmg, bar, w0 + 8, 0, 0, 2 * b, h0 >> 1);
                 }
             }
-        }
-    } else if (warp >= 4) {
-        // ================= loaders (fallback when the driver refuses the tensor maps): 384 threads, everything by cp.async =================
-        const int l = (warp - 4) * 32 + lane;
-        const size_t hw = (size_t)p.H * p.W;
-        const size_t gplane = (size_t)p.Hc * p.Wc / 8;            // 16-byte pieces per (b, part, co) plane (Wc % 8 == 0)
-        const int wc8 = p.Wc >> 3;
-        int i = 0;
-        for (int u = u_first; u < p.n_units; u += u_step, ++i) {
-            const int buf = i & 1;
-            const uint32_t sX = smem_u32(smem + buf * G::BUF), sG = sX + G::X_BYTES;
-            const int b = u / tiles, tile = u - b * tiles;
-            const int th_i = tile / p.tiles_w, tw_i = tile - th_i * p.tiles_w;
-            const int h0 = th_i * G::TH, w0 = tw_i * G::TW;
-            if (i >= 2) mbar_wait(empty + buf, ((i >> 1) - 1) & 1);   // MMAs of unit i-2 have finished reading this half
-            if (!(p.dbg & 1)) {   // ---- eps1 halo tile: [row][cg][col][8 ci], bf16 hi | lo
-                const uint4 *src0 = p.ximg + (size_t)b * 2 * G::CGR * hw;
-                for (int idx = l; idx < 2 * G::XROWS * G::CGR * G::XCOLS; idx += G::LOADER_WARPS * 32) {
-                    const int c = idx % G::XCOLS;
-                    int t = idx / G::XCOLS;
-                    const int cg = t % G::CGR;
-                    t /= G::CGR;
-                    const int r = t % G::XROWS, part = t / G::XROWS;
-                    const int gh = h0 - p.padH + row_off + r, gw = w0 - p.padW + c;
-                    const bool in = gh >= 0 && gh < p.H && gw >= 0 && gw < p.W;
-                    const uint4 *src = in ? src0 + (size_t)(part * G::CGR + cg) * hw + (size_t)gh * p.W + gw : src0;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sX + part * G::X_PART + r * G::X_RP + cg * G::X_CP + c * 16),
-                                 "l"(src), "r"(in ? 16u : 0u)
-                                 : "memory");
-                }
-            }
-            if (!(p.dbg & 2)) {   // ---- g_u tile: piece = 8 columns of one channel; N-group (part, row parity, co/8), k chunk, co % 8
-                const uint4 *src0 = p.gimg + (size_t)b * 2 * G::COUT * gplane;
-                for (int idx = l; idx < 2 * G::COUT * G::TH * 2; idx += G::LOADER_WARPS * 32) {
-                    const int kc = idx & 1, row = (idx >> 1) & 15, co = (idx >> 5) & 31, part = idx >> 10;
-                    const int oh = h0 + row, ow = w0 + 8 * kc;
-                    const bool in = oh < p.Hc && ow < p.Wc;
-                    const uint4 *src = in ? src0 + (size_t)(part * G::COUT + co) * gplane + (size_t)oh * wc8 + (ow >> 3) : src0;
-                    const uint32_t dst = sG + kc * G::G_KC + (row >> 1) * G::G_PAIR + (part * 8 + (row & 1) * 4 + (co >> 3)) * G::G_GRP + (co & 7) * 16;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(in ? 16u : 0u) : "memory");
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full + buf);
         }
     } else if (warp < 2) {
         // ================= MMA issuers: warp 0 = first two kernel columns of the role, warp 1 = the rest (+ bias) =================
@@ -199,13 +154,13 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
         uint32_t ones_acc = 0;
         int i = 0;
         for (int u = u_first; u < p.n_units; u += u_step, ++i) {
-            const int buf = i & 1;
+            const int sg = i % G::NSTAGE;
             const int tile = u % tiles;
             const int h0 = (tile / p.tiles_w) * G::TH;
             const int npair = (min(G::TH, p.Hc - h0) + 1) >> 1;
-            const uint32_t a_base = desc_lo(smem_u32(smem + buf * G::BUF), 128);                 // LBO: next 8 positions (K)
-            const uint32_t b_base = desc_lo(smem_u32(smem + buf * G::BUF + G::X_BYTES), G::G_KC);   // LBO: next 8 columns (K)
-            mbar_wait(full + buf, (i >> 1) & 1);
+            const uint32_t a_base = desc_lo(smem_u32(smem + sg * G::BUF), 128);                      // LBO: next 8 positions (K)
+            const uint32_t b_base = desc_lo(smem_u32(smem + sg * G::BUF + G::X_BYTES), G::G_KC);     // LBO: next 8 columns (K)
+            mbar_wait(full + sg, (i / G::NSTAGE) & 1);
             fence_after();
             if (elected) {
                 for (int pr = 0; pr < ((p.dbg & 4) ? (i == 0 ? 1 : 0) : npair); ++pr) {
@@ -223,7 +178,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
                         ones_acc = 1;
                     }
                 }
-                commit(empty + buf);
+                commit(empty + sg);
             }
             __syncwarp();
         }
@@ -299,8 +254,24 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
     if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)G::TMEM_COLS);
 }
 
-// The row-pair kernel takes the layer when its operands exist in image form: the tensor-core forward wrote eps1_mma, and the
-// packed backward read-out can write g_u as bf16 planes (even F, 16-byte aligned rows of 8 columns).
+// Tensor maps of the two operand images (cached per buffer and geometry, tmap.cu).  Dimension ORDER = order of the box in
+// shared memory; the row-parity / row-pair split of the g_u rows needs an even Hc, global strides multiples of 16 bytes.
+static bool wg2_tmaps(const dcll_conv_layer *L, TmapDesc *tmx, TmapDesc *tmg) {
+    using G = Wg2Geo;
+    Geo g = geo_of(L);
+    const uint64_t hw16 = (uint64_t)L->H * L->W * 16, plane = (uint64_t)g.Hc * g.Wc * 2;
+    const uint64_t xd[5] = {8, (uint64_t)L->W, 4, (uint64_t)L->H, (uint64_t)2 * L->B};
+    const uint64_t xs[4] = {16, hw16, (uint64_t)L->W * 16, 4 * hw16};
+    const uint32_t xb[5] = {8, (uint32_t)G::XCOLS, 4, (uint32_t)G::XROWS, 2};
+    const uint64_t gd[5] = {(uint64_t)g.Wc, 32, 2, (uint64_t)2 * L->B, (uint64_t)g.Hc / 2};
+    const uint64_t gs[4] = {plane, (uint64_t)g.Wc * 2, 32 * plane, (uint64_t)g.Wc * 4};
+    const uint32_t gb[5] = {8, 32, 2, 2, (uint32_t)G::PAIRS};
+    return tmap_bf16(tmx, L->eps1_mma, 5, xd, xs, xb) && tmap_bf16(tmg, L->g_u, 5, gd, gs, gb);
+}
+
+// The row-pair kernel takes the layer when its operands exist in image form -- the tensor-core forward wrote eps1_mma, and the
+// packed backward read-out can write g_u as bf16 planes (even F, rows of 8 columns 16-byte aligned, even Hc) -- and the driver
+// accepts the tensor maps.  The writer of g_u (launch_readout_bwd) and its reader (launch_wgrad) both ask this function.
 bool wgrad_tc2_supported(const dcll_conv_layer *L) {
     static int on = -1;                                     // DCLL_WGRAD_TC2=0: keep wgrad_tc_kernel (A/B measurements)
     if (on < 0) {
@@ -309,14 +280,17 @@ bool wgrad_tc2_supported(const dcll_conv_layer *L) {
     }
     if (!on) return false;
     Geo g = geo_of(L);
-    return wgrad_tc_supported(L) && tc_supported(L) && L->Cin == 32 && L->eps1_mma && (g.Wc % 8) == 0 && L->K <= 32 &&
-           (((uintptr_t)L->pv | (uintptr_t)L->wo | (uintptr_t)L->g_u) % 16) == 0;
+    if (!(wgrad_tc_supported(L) && tc_supported(L) && L->Cin == 32 && L->eps1_mma && L->g_u && (g.Wc % 8) == 0 && (g.Hc % 2) == 0 &&
+          L->K <= 32 && (((uintptr_t)L->pv | (uintptr_t)L->wo | (uintptr_t)L->g_u | (uintptr_t)L->eps1_mma) % 16) == 0))
+        return false;
+    TmapDesc tmx, tmg;
+    return wg2_tmaps(L, &tmx, &tmg);
 }
 
 void wgrad_tc2_roles(const dcll_conv_layer *L, int *nA, int *nB) {
     Geo g = geo_of(L);
-    const int n_units = L->B * ceil_div(g.Hc, 16) * ceil_div(g.Wc, 16);
-    // 74 CTA pairs: role A does 4 kernel columns per tile (8 x 4 x 113 cycles), role B 3 + half of the bias MMAs (8 x 3 x 113 + 4 x 64)
+    const int n_units = L->B * ceil_div(g.Hc, Wg2Geo::TH) * ceil_div(g.Wc, Wg2Geo::TW);
+    // 74 CTA pairs: role A does 4 kernel columns per unit (4 x 4 x 113 cycles), role B 3 + half of the bias MMAs (4 x 3 x 113 + 2 x 64)
     if (n_units >= 40) *nA = 40, *nB = 34;
     else *nA = *nB = n_units < 37 ? n_units : 37;
 }
@@ -325,35 +299,20 @@ int launch_wgrad_tc2(const dcll_conv_layer *L, float *partial, int *nA_out, int 
     using G = Wg2Geo;
     Geo g = geo_of(L);
     Wg2P p;
-    p.gimg = reinterpret_cast<const uint4 *>(L->g_u), p.ximg = reinterpret_cast<const uint4 *>(L->eps1_mma), p.partial = partial;
+    p.partial = partial;
     p.B = L->B, p.H = L->H, p.W = L->W, p.padH = L->padH, p.padW = L->padW, p.Hc = g.Hc, p.Wc = g.Wc;
     p.tiles_h = ceil_div(g.Hc, G::TH), p.tiles_w = ceil_div(g.Wc, G::TW);
     p.n_units = L->B * p.tiles_h * p.tiles_w;
     wgrad_tc2_roles(L, &p.nA, &p.nB);
     *nA_out = p.nA, *nB_out = p.nB;
-    static int dbg = -1, tma = -1;
+    static int dbg = -1;
     if (dbg < 0) {
         const char *e = getenv("DCLL_WG2_DEBUG");
         dbg = e ? atoi(e) : 0;
-        e = getenv("DCLL_WG2_TMA");                         // 0: cp.async loaders (A/B measurements)
-        tma = (e && e[0] == '0') ? 0 : 1;
     }
     p.dbg = dbg;
-    // tensor maps (cached per buffer and geometry).  The row-parity / row-pair split of the g_u rows needs an even Hc; global
-    // strides must be multiples of 16 bytes (Wc % 8 == 0 is part of wgrad_tc2_supported).
     TmapDesc tmx, tmg;
-    memset(&tmx, 0, sizeof(tmx)), memset(&tmg, 0, sizeof(tmg));
-    p.use_tma = 0;
-    if (tma && (g.Hc % 2) == 0) {
-        const uint64_t hw16 = (uint64_t)L->H * L->W * 16, plane = (uint64_t)g.Hc * g.Wc * 2;
-        const uint64_t xd[5] = {8, (uint64_t)L->W, 4, (uint64_t)L->H, (uint64_t)2 * L->B};
-        const uint64_t xs[4] = {16, hw16, (uint64_t)L->W * 16, 4 * hw16};
-        const uint32_t xb[5] = {8, (uint32_t)G::XCOLS, 4, (uint32_t)G::XROWS, 2};
-        const uint64_t gd[5] = {(uint64_t)g.Wc, 32, 2, (uint64_t)2 * L->B, (uint64_t)g.Hc / 2};
-        const uint64_t gs[4] = {plane, (uint64_t)g.Wc * 2, 32 * plane, (uint64_t)g.Wc * 4};
-        const uint32_t gb[5] = {8, 32, 2, 2, (uint32_t)G::PAIRS};
-        if (tmap_bf16(&tmx, L->eps1_mma, 5, xd, xs, xb) && tmap_bf16(&tmg, L->g_u, 5, gd, gs, gb)) p.use_tma = 1;
-    }
+    DCLL_REQUIRE(wg2_tmaps(L, &tmx, &tmg), DCLL_ECUDA, "wgrad_tc2: cuTensorMapEncodeTiled failed");
     DCLL_SMEM_ATTR(wgrad_tc2_kernel, G::SMEM);
     launch_k(wgrad_tc2_kernel, 2 * (p.nA + p.nB), G::NT, G::SMEM, st, p, tmx, tmg);
     DCLL_LAUNCH_OK("wgrad_tc2_kernel");
