@@ -310,9 +310,13 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
     return *reinterpret_cast<float2 *>(&rd);
 }
 
-// IMG: g_u leaves the kernel as bf16 {hi,lo} NCHW planes in the same buffer -- sample b occupies the same F*4 bytes,
-// [part 2][F] bf16 -- which is the operand form wgrad_tc2_kernel stages with plain 16-byte copies (no conversion there).
-// q32 = 32-bit address of the bf16 pair (f, f+1) in the hi plane of the sample; the lo plane starts F/2 words later.
+// IMG: g_u leaves the kernel as a bf16 {hi,lo} operand image in the same buffer -- sample b occupies the same F*4 bytes,
+//     [part 2][co/8][position/8][co % 8][8 positions] bf16,
+// i.e. 128-byte core matrices (8 channels x 8 consecutive positions) of the K-major B operand of wgrad_tc2_kernel, which moves
+// them with one tensor-map box per unit (full 128-byte lines; the first, plain-NCHW form of the image made every 16-byte piece
+// its own half-used L2 sector).  The thread -> feature map follows the image: a warp = 8 channels x 8 positions, so its 32
+// stores of 4 bytes fill one 128-byte line and its loads of pv / Wo touch 8 full 32-byte sectors, as many as the linear map.
+// q32 = 32-bit address of the bf16 pair in the hi part of the sample; the lo part starts F/2 words later.
 __device__ __forceinline__ void store_gu_img(uint32_t *q32, int half_f, float2 v) {
     const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
     const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
@@ -323,7 +327,7 @@ __device__ __forceinline__ void store_gu_img(uint32_t *q32, int half_f, float2 v
 template <int KMAX, int UB, int MINB, bool IMG>
 __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
                                                               const float *__restrict__ g_o, int B, int F, int K, int b_per_blk,
-                                                              float *__restrict__ g_u) {
+                                                              float *__restrict__ g_u, int hw) {
     pdl_entry();
     // g rows are read back as broadcast LDS.128 (4 k per load) and enter the FFMA2 as a scalar-broadcast operand: ptxas folds
     // the {g,g} pair into `FFMA2 Rd, Rg.F32, Rw.F32x2, Rs.F32x2`.  (Storing the rows duplicated {g,g} doubled the LDS traffic
@@ -331,8 +335,17 @@ __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__
     __shared__ __align__(16) float gd[64][KMAX];
     static_assert(KMAX % 4 == 0, "float4 rows");
     const int tid = threadIdx.x;
-    const int f = 2 * (blockIdx.x * 256 + tid);
-    const bool fok = f < F;
+    int f = 2 * (blockIdx.x * 256 + tid);
+    bool fok = f < F;
+    int img_word = 0;                                      // IMG: 32-bit word of this thread's bf16 pair inside one part of the sample
+    if (IMG) {
+        const int chunks = hw >> 3, blk_per_cog = (chunks + 7) >> 3;          // 8-position chunks per plane, 64-position blocks
+        const int cog = blockIdx.x / blk_per_cog, pb = blockIdx.x - cog * blk_per_cog;
+        const int c8 = pb * 8 + (tid >> 5), co8 = (tid & 31) >> 2, pr = tid & 3;
+        f = (cog * 8 + co8) * hw + c8 * 8 + 2 * pr;
+        fok = c8 < chunks && f < F;
+        img_word = ((cog * chunks + c8) * 8 + co8) * 4 + pr;
+    }
     float2 w[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) w[k] = (k < K && fok) ? __ldg(reinterpret_cast<const float2 *>(wo + (size_t)k * F + f)) : make_float2(0.f, 0.f);
@@ -386,7 +399,7 @@ __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__
 #pragma unroll
                     for (int u = 0; u < UB; ++u, q += rowF) {
                         const float2 v = sample(bb + u, cur[u]);
-                        if (IMG) store_gu_img(reinterpret_cast<uint32_t *>(q - f) + (f >> 1), F >> 1, v);
+                        if (IMG) store_gu_img(reinterpret_cast<uint32_t *>(q - f) + img_word, F >> 1, v);
                         else *reinterpret_cast<float2 *>(q) = v;
                     }
                     gup = q;
@@ -398,7 +411,7 @@ __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__
             }
             for (; bb < nb; ++bb, pvp += rowF, gup += rowF) {
                 const float2 v = sample(bb, __ldg(reinterpret_cast<const float2 *>(pvp)));
-                if (IMG) store_gu_img(reinterpret_cast<uint32_t *>(gup - f) + (f >> 1), F >> 1, v);
+                if (IMG) store_gu_img(reinterpret_cast<uint32_t *>(gup - f) + img_word, F >> 1, v);
                 else *reinterpret_cast<float2 *>(gup) = v;
             }
         }
@@ -702,7 +715,9 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
     // odd F / unaligned rows: the scalar fused sweep -- never when the weight-gradient kernel expects g_u in image form (then the
     // packed g_u sweep below runs and the output_ gradient takes the generic kernel)
     const bool fused_out = big_out && !packed_out && !wgrad_tc2_supported(L);
-    const int fblk = ceil_div(g.F, (packed && !fused_out) ? 512 : 256);
+    int fblk = ceil_div(g.F, (packed && !fused_out) ? 512 : 256);
+    const int hw = g.Hp * g.Wp;
+    if (wgrad_tc2_supported(L)) fblk = (L->Cout / 8) * ceil_div(hw / 8, 8);   // image-ordered blocks: 8 channels x 64 positions
     if (packed_out) {
         // large F: packed g_u sweep below + packed output_ gradient/Adam kernel (pv read twice, both at >= 4 waves)
         sc = adam_scalars(a->adam_out, a->adam_out.step + 1);
@@ -750,8 +765,8 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
             // image form of g_u (bf16 {hi,lo} planes in the same buffer) when the row-pair weight-gradient kernel consumes it
 #define RB2(KM)                                                                                                                    \
     do {                                                                                                                           \
-        if (wgrad_tc2_supported(L)) launch_k(readout_bwd2_kernel<KM, 8, 2, true>, grid, 256, 0, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u); \
-        else launch_k(readout_bwd2_kernel<KM, 8, 2, false>, grid, 256, 0, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u);  \
+        if (wgrad_tc2_supported(L)) launch_k(readout_bwd2_kernel<KM, 8, 2, true>, grid, 256, 0, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u, hw); \
+        else launch_k(readout_bwd2_kernel<KM, 8, 2, false>, grid, 256, 0, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u, hw);  \
     } while (0)
             if (L->K <= 16) { RB2(16); }
             else if (L->K <= 24) { RB2(24); }

@@ -50,23 +50,24 @@ struct Wg2P {
                          // bit 2 skip the MMAs
 };
 
-struct Wg2Geo {
+template <int TH_, int NSTAGE_>
+struct Wg2GeoT {
     static constexpr int KH = 7, KW = 7, CIN = 32, COUT = 32;
-    static constexpr int TH = 8, TW = 16, PAIRS = TH / 2;   // a unit = 8 output rows x 16 columns = 4 row pairs
+    static constexpr int TH = TH_, TW = 16, PAIRS = TH / 2;  // a unit = TH output rows x 16 columns = TH/2 row pairs
     static constexpr int CGR = 4, DY = 4;
     static constexpr int XROWS = TH + DY - 2;               // halo rows 2*pair + dy of one kernel-row group: 10
     static constexpr int XCOLS = TW + KW - 1;               // 22
     static constexpr int X_CP = XCOLS * 16, X_RP = CGR * X_CP, X_PART = XROWS * X_RP, X_BYTES = 2 * X_PART;
-    // g_u tile: [k chunk 2][pair 4][part 2][row parity 2][co 32][8 columns] bf16 -- exactly what ONE tensor-map box per k chunk
-    // delivers; an N-group (8 channels) is 128 bytes, 16 groups (part, parity, co/8) per pair, the k chunks G_KC apart
-    static constexpr int G_GRP = 128;
-    static constexpr int G_PAIR = 16 * G_GRP;
-    static constexpr int G_KC = PAIRS * G_PAIR;              // 8 KB
-    static constexpr int G_BYTES = 2 * G_KC;
+    // g_u tile: [pair 4][plane 8 = (part, co/8)][row parity 2][k chunk 2][co % 8][8 columns] bf16 -- ONE tensor-map box per unit out
+    // of the image the backward read-out wrote (128-byte core matrices).  N-group (8 channels) = plane*2 + parity, 256 bytes
+    // apart; the two K chunks of a group 128 bytes apart.
+    static constexpr int G_GRP = 256;
+    static constexpr int G_PAIR = 16 * G_GRP;                // 4 KB
+    static constexpr int G_BYTES = PAIRS * G_PAIR;           // 16 KB
     static constexpr int BUF = X_BYTES + G_BYTES;            // 44 544 B per pipeline stage
     // FOUR stages: a tile load takes ~2.7 us from request to landing (measured: loads alone 0.34 ms per launch with one tile in
     // flight per SM -- 12 B/cycle/SM, a third of what L2 can deliver), the MMAs of a unit ~1 us, so three loads must be in flight
-    static constexpr int NSTAGE = 4;
+    static constexpr int NSTAGE = NSTAGE_;
     static constexpr int OFF_ONES = NSTAGE * BUF, OFF_BAR = OFF_ONES + 4096, SMEM = OFF_BAR + 128;
     static constexpr int NT = 512;
     static constexpr int ACC_COLS = 128, TMEM_COLS = 512;
@@ -76,14 +77,16 @@ struct Wg2Geo {
     static constexpr int BLK = NW_BLK + COUT;                // + bias sums
     static_assert(SMEM <= 227 * 1024, "shared memory");
     static_assert(COUT * CIN * PITCH * 4 <= NSTAGE * BUF, "staging fits the tile buffers");
-    static_assert(X_PART % 16 == 0 && BUF % 128 == 0 && X_BYTES % 128 == 0 && G_KC % 128 == 0, "alignment");
+    static_assert(X_PART % 16 == 0 && BUF % 128 == 0 && X_BYTES % 128 == 0, "alignment");
 };
+using Wg2Geo = Wg2GeoT<8, 4>;          // default: 8-row units, four stages (DCLL_WG2_TILE=16: 16-row units, two stages)
 
 size_t wgrad_tc2_partial_floats() { return (size_t)148 * Wg2Geo::BLK; }
 
+template <int TH_, int NSTAGE_>
 __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const __grid_constant__ TmapDesc tmx,
                                                            const __grid_constant__ TmapDesc tmg) {
-    using G = Wg2Geo;
+    using G = Wg2GeoT<TH_, NSTAGE_>;
     using namespace tc;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + G::OFF_BAR);
@@ -119,7 +122,8 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
     if (warp == 4) {
         // ================= tile producer: one thread, three tensor-map boxes per unit (UTMALDG), zero fill outside the picture:
         //   eps1 image  dims (8 ci, W, ci/8, H, (b, part))          box (8, 22, 4, 10, 2)  -> [part][row][ci/8][col][8 ci]
-        //   g_u planes  dims (w, co, row parity, (b, part), row/2)  box (8, 32, 2, 2, 4)   -> [pair][part][parity][co][8 w], per k chunk
+        //   g_u image   dims (64 = co%8 x 8 w, w/8, row parity, (b, part, co/8), row/2)  box (64, 2, 2, 8, 4)
+        //                                                           -> [pair][part, co/8][parity][k chunk][co % 8][8 w]
         // It runs up to NSTAGE units ahead of the issuers.
         if (lane == 0) {
             tma_prefetch_desc(&tmx);
@@ -134,10 +138,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
                 if (i >= G::NSTAGE) mbar_wait(empty + sg, ((i / G::NSTAGE) - 1) & 1);   // MMAs of unit i-NSTAGE have read this stage
                 mbar_expect_tx(full + sg, ((p.dbg & 1) ? 0 : G::X_BYTES) + ((p.dbg & 2) ? 0 : G::G_BYTES));
                 if (!(p.dbg & 1)) tma_load_5d(sX, &tmx, bar, 0, w0 - p.padW, 0, h0 - p.padH + row_off, 2 * b);
-                if (!(p.dbg & 2)) {
-                    tma_load_5d(sG, &tmg, bar, w0, 0, 0, 2 * b, h0 >> 1);
-                    tma_load_5d(sG + G::G_KC, &tmg, bar, w0 + 8, 0, 0, 2 * b, h0 >> 1);
-                }
+                if (!(p.dbg & 2)) tma_load_5d(sG, &tmg, bar, 0, w0 >> 3, 0, 8 * b, h0 >> 1);
             }
         }
     } else if (warp < 2) {
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
         constexpr uint32_t IDESC_N128 = idesc_bf16(128, 128, true, false);   // A MN-major (M = (dy, ci) contiguous), B K-major
         constexpr uint32_t IDESC_N64 = idesc_bf16(128, 64, true, false);
         constexpr uint32_t A_HI = desc_hi(G::X_CP);          // SBO: next 8 rows of M = next (dy, cg) group
-        constexpr uint32_t B_HI = desc_hi(G::G_GRP);         // SBO: next 8 rows of N = next (part, parity, co/8) group
+        constexpr uint32_t B_HI = desc_hi(G::G_GRP);         // SBO: next 8 rows of N = next (part, co/8, parity) group
         constexpr uint32_t ONES_HI = desc_hi(128);
         const uint32_t elected = elect_one();
         const int kw0 = kw_base + (warp == 0 ? 0 : 2), kw1 = roleB ? (warp == 0 ? 6 : 7) : (warp == 0 ? 2 : 4);
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
             const int h0 = (tile / p.tiles_w) * G::TH;
             const int npair = (min(G::TH, p.Hc - h0) + 1) >> 1;
             const uint32_t a_base = desc_lo(smem_u32(smem + sg * G::BUF), 128);                      // LBO: next 8 positions (K)
-            const uint32_t b_base = desc_lo(smem_u32(smem + sg * G::BUF + G::X_BYTES), G::G_KC);     // LBO: next 8 columns (K)
+            const uint32_t b_base = desc_lo(smem_u32(smem + sg * G::BUF + G::X_BYTES), 128);         // LBO: next 8 columns (K)
             mbar_wait(full + sg, (i / G::NSTAGE) & 1);
             fence_after();
             if (elected) {
@@ -188,11 +189,12 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
         }
         __syncwarp();
     }
-    // ---- drain.  Lane m = (dy, ci) of accumulator a holds, per output channel co:
-    //        j = 0 (even rows): D[co] + D[64 + co]        -> kernel row 4g + dy      -> slot dy + 1
-    //        j = 1 (odd rows) : D[32 + co] + D[96 + co]   -> kernel row 4g + dy - 1  -> slot dy
-    //      (slot s <-> kh = 4g - 1 + s).  Two phases through the idle tile buffers: j = 0 stores slots 1..4, then j = 1 stores
-    //      slot 0 and adds to slots 1..3; each (co, ci, a, slot) is touched by one thread per phase.
+    // ---- drain.  Lane m = (dy, ci) of accumulator a; its 128 columns are N-groups (part, co/8, row parity) x 8 channels:
+    //        column = part*64 + (co/8)*16 + parity*8 + co%8;   part 0 = X_hi G_hi + X_lo G_hi, part 1 = X_hi G_lo
+    //        parity 0 (even rows): kernel row 4g + dy      -> slot dy + 1
+    //        parity 1 (odd rows) : kernel row 4g + dy - 1  -> slot dy
+    //      (slot s <-> kh = 4g - 1 + s).  Two passes through the idle tile buffers: parity 0 stores slots 1..4, then parity 1 stores
+    //      slot 0 and adds to slots 1..3; each (co, ci, a, slot) is touched by one thread per pass.
     float *out = p.partial + (size_t)blockIdx.x * G::BLK;
     mbar_wait(done, 0);
     fence_after();
@@ -202,44 +204,44 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
         const int ci = lane;
         float *stg = reinterpret_cast<float *>(smem);
         const int nacc = roleB ? 3 : 4;
-        for (int a = (warp >> 2); a < nacc; a += 4) {
-            uint32_t v[32], v2[32];
-            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS;
-            ld32(ta, v);
-            ld32(ta + 64, v2);
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int a = (warp >> 2); a < nacc; a += 4) {
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS;
 #pragma unroll
-            for (int co = 0; co < 32; ++co)
-                stg[(co * G::CIN + ci) * G::PITCH + a * G::SLOTS + q + 1] = __uint_as_float(v[co]) + __uint_as_float(v2[co]);
-        }
-        __syncthreads();
-        for (int a = (warp >> 2); a < nacc; a += 4) {
-            uint32_t v[32], v2[32];
-            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS;
-            ld32(ta + 32, v);
-            ld32(ta + 96, v2);
+                for (int hc = 0; hc < 2; ++hc) {                         // columns [32 hc, 32 hc + 32) of both parts: co/8 = 2 hc, 2 hc + 1
+                    uint32_t v[32], v2[32];
+                    ld32(ta + 32 * hc, v);
+                    ld32(ta + 64 + 32 * hc, v2);
 #pragma unroll
-            for (int co = 0; co < 32; ++co) {
-                float *s = stg + (co * G::CIN + ci) * G::PITCH + a * G::SLOTS + q;
-                const float val = __uint_as_float(v[co]) + __uint_as_float(v2[co]);
-                *s = q == 0 ? val : *s + val;
+                    for (int c = 0; c < 32; ++c) {
+                        if (((c >> 3) & 1) != pass) continue;
+                        const int co = (2 * hc + (c >> 4)) * 8 + (c & 7);
+                        const float val = __uint_as_float(v[c]) + __uint_as_float(v2[c]);
+                        float *sp = stg + (co * G::CIN + ci) * G::PITCH + a * G::SLOTS + q + 1 - pass;
+                        *sp = (pass == 0 || q == 0) ? val : *sp + val;
+                    }
+                }
             }
+            __syncthreads();
         }
-        // bias gradient (role B): every lane of the spare accumulator holds [sum G_hi(even) | sum G_hi(odd) | sum G_lo(even) | sum G_lo(odd)]
+        // bias gradient (role B): every lane of the spare accumulator holds the column sums of B_main over this CTA's pairs
         if (warp == 0) {
             float bsum = 0.f;
             if (roleB && *ones_used) {
-                uint32_t c0[32], c1[32];
                 const uint32_t ta = tmem_base + 3 * G::ACC_COLS;
-                ld32(ta, c0);
-                ld32(ta + 32, c1);
-                float s01[32];
+                const int idx = ((lane >> 3) & 1) * 16 + (lane & 7);     // column of (co/8 parity-0 block) inside a 32-column chunk
 #pragma unroll
-                for (int co = 0; co < 32; ++co) s01[co] = __uint_as_float(c0[co]) + __uint_as_float(c1[co]);
-                ld32(ta + 64, c0);
-                ld32(ta + 96, c1);
+                for (int hc = 0; hc < 2; ++hc) {
+                    uint32_t c0[32], c1[32];
+                    ld32(ta + 32 * hc, c0);
+                    ld32(ta + 64 + 32 * hc, c1);
+                    if ((lane >> 4) == hc) {
 #pragma unroll
-                for (int co = 0; co < 32; ++co)
-                    if (co == lane) bsum = s01[co] + (__uint_as_float(c0[co]) + __uint_as_float(c1[co]));
+                        for (int c = 0; c < 24; ++c)
+                            if (c == idx) bsum = (__uint_as_float(c0[c]) + __uint_as_float(c1[c])) + (__uint_as_float(c0[c + 8]) + __uint_as_float(c1[c + 8]));
+                    }
+                }
             }
             out[G::NW_BLK + lane] = bsum;
         }
@@ -256,17 +258,30 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
 
 // Tensor maps of the two operand images (cached per buffer and geometry, tmap.cu).  Dimension ORDER = order of the box in
 // shared memory; the row-parity / row-pair split of the g_u rows needs an even Hc, global strides multiples of 16 bytes.
-static bool wg2_tmaps(const dcll_conv_layer *L, TmapDesc *tmx, TmapDesc *tmg) {
-    using G = Wg2Geo;
+static int wg2_tile() {
+    static int th = -1;
+    if (th < 0) {
+        const char *e = getenv("DCLL_WG2_TILE");
+        th = (e && atoi(e) == 16) ? 16 : 8;
+    }
+    return th;
+}
+
+template <class G>
+static bool wg2_tmaps_g(const dcll_conv_layer *L, TmapDesc *tmx, TmapDesc *tmg) {
     Geo g = geo_of(L);
     const uint64_t hw16 = (uint64_t)L->H * L->W * 16, plane = (uint64_t)g.Hc * g.Wc * 2;
     const uint64_t xd[5] = {8, (uint64_t)L->W, 4, (uint64_t)L->H, (uint64_t)2 * L->B};
     const uint64_t xs[4] = {16, hw16, (uint64_t)L->W * 16, 4 * hw16};
     const uint32_t xb[5] = {8, (uint32_t)G::XCOLS, 4, (uint32_t)G::XROWS, 2};
-    const uint64_t gd[5] = {(uint64_t)g.Wc, 32, 2, (uint64_t)2 * L->B, (uint64_t)g.Hc / 2};
-    const uint64_t gs[4] = {plane, (uint64_t)g.Wc * 2, 32 * plane, (uint64_t)g.Wc * 4};
-    const uint32_t gb[5] = {8, 32, 2, 2, (uint32_t)G::PAIRS};
+    // g_u image [b][part][co/8][position/8][co % 8][8 positions]: 128 bytes per (channel group, 8 positions)
+    const uint64_t gd[5] = {64, (uint64_t)g.Wc / 8, 2, (uint64_t)8 * L->B, (uint64_t)g.Hc / 2};
+    const uint64_t gs[4] = {128, (uint64_t)g.Wc * 16, plane * 8, (uint64_t)g.Wc * 32};
+    const uint32_t gb[5] = {64, 2, 2, 8, (uint32_t)G::PAIRS};
     return tmap_bf16(tmx, L->eps1_mma, 5, xd, xs, xb) && tmap_bf16(tmg, L->g_u, 5, gd, gs, gb);
+}
+static bool wg2_tmaps(const dcll_conv_layer *L, TmapDesc *tmx, TmapDesc *tmg) {
+    return wg2_tile() == 16 ? wg2_tmaps_g<Wg2GeoT<16, 2>>(L, tmx, tmg) : wg2_tmaps_g<Wg2GeoT<8, 4>>(L, tmx, tmg);
 }
 
 // The row-pair kernel takes the layer when its operands exist in image form -- the tensor-core forward wrote eps1_mma, and the
@@ -289,14 +304,14 @@ bool wgrad_tc2_supported(const dcll_conv_layer *L) {
 
 void wgrad_tc2_roles(const dcll_conv_layer *L, int *nA, int *nB) {
     Geo g = geo_of(L);
-    const int n_units = L->B * ceil_div(g.Hc, Wg2Geo::TH) * ceil_div(g.Wc, Wg2Geo::TW);
+    const int n_units = L->B * ceil_div(g.Hc, wg2_tile()) * ceil_div(g.Wc, Wg2Geo::TW);
     // 74 CTA pairs: role A does 4 kernel columns per unit (4 x 4 x 113 cycles), role B 3 + half of the bias MMAs (4 x 3 x 113 + 2 x 64)
     if (n_units >= 40) *nA = 40, *nB = 34;
     else *nA = *nB = n_units < 37 ? n_units : 37;
 }
 
-int launch_wgrad_tc2(const dcll_conv_layer *L, float *partial, int *nA_out, int *nB_out, cudaStream_t st) {
-    using G = Wg2Geo;
+template <class G>
+static int launch_wgrad_tc2_g(const dcll_conv_layer *L, float *partial, int *nA_out, int *nB_out, cudaStream_t st) {
     Geo g = geo_of(L);
     Wg2P p;
     p.partial = partial;
@@ -313,10 +328,15 @@ int launch_wgrad_tc2(const dcll_conv_layer *L, float *partial, int *nA_out, int 
     p.dbg = dbg;
     TmapDesc tmx, tmg;
     DCLL_REQUIRE(wg2_tmaps(L, &tmx, &tmg), DCLL_ECUDA, "wgrad_tc2: cuTensorMapEncodeTiled failed");
-    DCLL_SMEM_ATTR(wgrad_tc2_kernel, G::SMEM);
-    launch_k(wgrad_tc2_kernel, 2 * (p.nA + p.nB), G::NT, G::SMEM, st, p, tmx, tmg);
+    DCLL_SMEM_ATTR((wgrad_tc2_kernel<G::TH, G::NSTAGE>), G::SMEM);
+    launch_k(wgrad_tc2_kernel<G::TH, G::NSTAGE>, 2 * (p.nA + p.nB), G::NT, G::SMEM, st, p, tmx, tmg);
     DCLL_LAUNCH_OK("wgrad_tc2_kernel");
     return DCLL_OK;
+}
+
+int launch_wgrad_tc2(const dcll_conv_layer *L, float *partial, int *nA_out, int *nB_out, cudaStream_t st) {
+    return wg2_tile() == 16 ? launch_wgrad_tc2_g<Wg2GeoT<16, 2>>(L, partial, nA_out, nB_out, st)
+                            : launch_wgrad_tc2_g<Wg2GeoT<8, 4>>(L, partial, nA_out, nB_out, st);
 }
 
 }  // namespace dcll
