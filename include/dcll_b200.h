@@ -140,6 +140,13 @@ int dcll_iq_encode(const float *x, int B, int N, double min_I, double max_I, dou
 /* dense one-hot frames [T,B,1,H,W] float32 (what data/utils.py:57,81-82 materialises) */
 int dcll_cells_to_frames(const int32_t *cells, int T, int B, int H, int W, float *frames, void *stream);
 
+/* image2spiketrain (data/utils.py:15-40): frozen Poisson spike train of an image, out float32 [Tmax,B,Nin]:
+ *   spike[t,b,n] = t < t_len[b] && !(u[b,t,n] < p[b,n]),  p = (1000 - gain*x[b,n]) / 1000 in float32.
+ * u: device float64 [B,Tmax,Nin] = the uniforms of the reference's numpy stream (bit-exact parity for the same draws), or NULL:
+ * a seeded counter-based generator on the device (same distribution, not the numpy stream). */
+int dcll_image_encode(const float *x, const double *u, const int32_t *t_len, int B, int Nin, int Tmax, double gain,
+                      uint64_t seed, float *out, void *stream);
+
 /* -- conv layer step ------------------------------------------------------------------------ */
 size_t dcll_conv_workspace_bytes(const dcll_conv_layer *L);
 /* refresh weight_t from weight (after load_state_dict / external assignment) */

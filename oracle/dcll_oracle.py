@@ -29,6 +29,31 @@ GAMMA_EXPONENT_F32 = float(np.float32(1.0 / 1.2))  # torch CPU pow casts the exp
 
 
 # ----------------------------------------------------------------------------------------------
+# image -> frozen Poisson spike train  (data/utils.py:15-40)
+# ----------------------------------------------------------------------------------------------
+def image2spiketrain(x, y, input_shape, gain=50, min_duration=None, max_duration=500):
+    """data/utils.py:15-40.  x: float32 images [B, ...] (torch tensor or ndarray), y: [B, K].  numpy RNG consumption as the
+    reference: one randint for the durations (:26), then per sample one uniform(size=(T_i, Nin)) (:32).  p is float32
+    (gain * float32 tensor -> float32; (1000.0 - p32) / 1000 stays float32), the comparison promotes it to float64."""
+    if min_duration is None:
+        min_duration = max_duration - 1                                       # :18-19
+    xa = np.asarray(x, dtype=np.float32)
+    batch_size = xa.shape[0]                                                  # :21
+    nin = int(np.prod(input_shape))                                           # :22
+    rates = (np.float32(gain) * xa.reshape(batch_size, -1)).astype(np.float32)    # :23
+    p = ((np.float32(1000.0) - rates) / np.float32(1000)).astype(np.float32)  # :24
+    T = np.random.randint(min_duration, max_duration, batch_size)            # :25
+    all_inputs = np.zeros((max_duration, batch_size, nin))                    # :28
+    for i in range(batch_size):                                               # :29-32
+        spikes = np.ones((T[i], nin))
+        spikes[(np.random.uniform(size=(T[i], nin)) < p[i]).astype('bool')] = 0
+        all_inputs[:T[i], i, :] = spikes
+    all_inputs = all_inputs.reshape(max_duration, batch_size, *input_shape)   # :35
+    all_target = np.repeat(np.asarray(y)[np.newaxis, :, :], max_duration, axis=0)   # :38
+    return all_inputs, all_target
+
+
+# ----------------------------------------------------------------------------------------------
 # IQ -> spike encoding  (data/utils.py:43-87)
 # ----------------------------------------------------------------------------------------------
 def encode_cells(x, out_w=28, out_h=28, min_I=-1, max_I=1, min_Q=-1, max_Q=1, t_start=0,

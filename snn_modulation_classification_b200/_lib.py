@@ -78,6 +78,7 @@ def _load():
         "dcll_iq_encode": [_fp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                            C.c_int, C.c_int, C.c_int, _fp, _fp],
         "dcll_cells_to_frames": [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp],
+        "dcll_image_encode": [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, _fp, _fp],
         "dcll_conv_sync_weights": [P(ConvLayer), _fp],
         "dcll_conv_step_fwd": [P(ConvLayer), _fp, _fp, _fp],
         "dcll_conv_step_fwd_chain": [P(ConvLayer), P(ConvLayer), C.c_int, _fp, _fp, _fp],
@@ -139,7 +140,7 @@ EXPORTS = ["dcll_launch_count", "dcll_profile_enable", "dcll_profile_read", "dcl
            "dcll_conv_core_fwd", "dcll_conv_step_bwd_update", "dcll_conv_apply_update", "dcll_net_window", "dcll_vote",
            "dcll_quantize", "dcll_dequantize", "dcll_sizeof_dense_layer", "dcll_dense_step_fwd",
            "dcll_dense_step_bwd_update", "dcll_net_window_stats", "dcll_infer_stack16", "dcll_conv_readout_rows", "dcll_conv_step_fwd_chain",
-           "dcll_conv_chain_fusable", "dcll_dp_unique_id", "dcll_dp_create", "dcll_dp_destroy", "dcll_net_window_dp"]
+           "dcll_conv_chain_fusable", "dcll_dp_unique_id", "dcll_dp_create", "dcll_dp_destroy", "dcll_net_window_dp", "dcll_image_encode"]
 
 
 def check(rc):

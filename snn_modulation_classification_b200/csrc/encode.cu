@@ -74,9 +74,52 @@ __global__ void __launch_bounds__(256) cells_to_frames_kernel(const int2 *__rest
     }
 }
 
+// image2spiketrain (data/utils.py:15-40): frozen Poisson spike train of an image.
+//     p[b,n] = (1000 - gain * x[b,n]) / 1000   (float32, as numpy evaluates it);  spike[t,b,n] = t < T_b && !(u[t,b,n] < p[b,n])
+// u: the host-drawn uniforms of the reference's numpy stream (float64 [B][Tmax][Nin], compared in double: bit-exact with the
+// reference for the same draws), or -- u == NULL -- a counter-based generator (one 64-bit mix per element, seeded; the same
+// distribution, not the numpy stream).  HBM-bound: 4 B written per element (+ 8 B read in the parity mode).
+__device__ __forceinline__ double mix_uniform(unsigned long long seed, unsigned long long idx) {
+    unsigned long long z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;      // splitmix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);                // 53 random bits -> [0, 1)
+}
+
+__global__ void __launch_bounds__(256) image_encode_kernel(const float *__restrict__ x, const double *__restrict__ u,
+                                                           const int32_t *__restrict__ t_len, int B, int Nin, int Tmax, float gain,
+                                                           unsigned long long seed, float *__restrict__ out) {
+    pdl_entry();
+    const size_t total = (size_t)Tmax * B * Nin;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i % Nin);
+        const size_t tb = i / Nin;
+        const int b = (int)(tb % B), t = (int)(tb / B);
+        float v = 0.f;
+        if (t < __ldg(t_len + b)) {
+            const float rate = __fmul_rn(gain, __ldg(x + (size_t)b * Nin + n));
+            const float p = __fdiv_rn(__fsub_rn(1000.0f, rate), 1000.0f);
+            const double r = u ? __ldg(u + ((size_t)b * Tmax + t) * Nin + n) : mix_uniform(seed, i);
+            v = (r < (double)p) ? 0.f : 1.f;
+        }
+        out[i] = v;
+    }
+}
+
 }  // namespace dcll
 
 using namespace dcll;
+
+extern "C" __attribute__((visibility("default"))) int dcll_image_encode(const float *x, const double *u, const int32_t *t_len, int B, int Nin, int Tmax,
+                                                                         double gain, uint64_t seed, float *out, void *stream) {
+    DCLL_REQUIRE(x && t_len && out && B > 0 && Nin > 0 && Tmax > 0, DCLL_EINVAL, "dcll_image_encode: bad arguments");
+    const size_t total = (size_t)Tmax * B * Nin;
+    const int blocks = (int)((total + 255) / 256 < (size_t)148 * 16 ? (total + 255) / 256 : (size_t)148 * 16);
+    launch_k(image_encode_kernel, blocks, 256, 0, (cudaStream_t)stream, x, u, t_len, B, Nin, Tmax, (float)gain, (unsigned long long)seed, out);
+    DCLL_LAUNCH_OK("image_encode_kernel");
+    return DCLL_OK;
+}
 
 extern "C" __attribute__((visibility("default"))) int dcll_iq_encode(const float *x, int B, int N, double min_I, double max_I, double min_Q, double max_Q,
                               int out_w, int out_h, int t_start, int T, int do_gamma, int32_t *cells, void *stream) {

@@ -69,21 +69,38 @@ def iq2spiketrain(x, y, out_w=28, out_h=28, min_I=-1, max_I=1, min_Q=-1, max_Q=1
     return (wc if as_cells else wc.dense()), all_target
 
 
-def image2spiketrain(x, y, input_shape, gain=50, min_duration=None, max_duration=500):
-    """Frozen Poisson spike train of an image (ref:15-40).  Host-side data generation (numpy RNG, as the
-    reference); used only to shape the MNIST-style input of mnist_conv.yaml, not a hot-path kernel."""
+def image2spiketrain(x, y, input_shape, gain=50, min_duration=None, max_duration=500, device_rng=None):
+    """Frozen Poisson spike train of an image (ref:15-40), on the GPU.
+
+    Same arguments and the same numpy-RNG consumption as the reference: one ``randint`` draw of the per-sample durations
+    (ref:26), then per sample one ``uniform(size=(T_i, Nin))`` draw (ref:32).  Those host-drawn uniforms are compared with
+    ``p = (1000 - gain*x)/1000`` by ``image_encode_kernel`` (csrc/encode.cu), so for a given numpy seed the spikes are the
+    reference's, element for element.  ``device_rng=<seed>`` skips the host draws after the durations and uses the kernel's
+    counter-based generator instead (same distribution, not the numpy stream) -- no 8-byte-per-element upload.
+
+    Returns ``(spike_trains, all_target)``: a float32 CUDA tensor [max_duration, B, *input_shape] (the reference returns the
+    same values as a float64 numpy array that train.py then converts and uploads) and the labels repeated over time."""
     if min_duration is None:
         min_duration = max_duration - 1
-    batch_size = x.shape[0]
+    x_t = x if torch.is_tensor(x) else torch.as_tensor(np.asarray(x))
+    batch_size = int(x_t.shape[0])
     nin = int(np.prod(input_shape))
-    rates = gain * np.asarray(x).reshape(batch_size, -1)
-    p = (1000.0 - rates) / 1000
-    T = np.random.randint(min_duration, max_duration, batch_size)
-    all_inputs = np.zeros((max_duration, batch_size, nin))
-    for i in range(batch_size):
-        spikes = np.ones((T[i], nin))
-        spikes[(np.random.uniform(size=(T[i], nin)) < p[i]).astype('bool')] = 0
-        all_inputs[:T[i], i, :] = spikes
-    all_inputs = all_inputs.reshape(max_duration, batch_size, *input_shape)
-    all_target = np.repeat(np.asarray(y)[np.newaxis, :, :], max_duration, axis=0)
-    return all_inputs, all_target
+    x_d = _as_cuda_f32(x_t.reshape(batch_size, -1))
+    if x_d.shape[1] != nin:
+        raise ValueError('input_shape %r does not match x of shape %s' % (tuple(input_shape), tuple(x_t.shape)))
+    T = np.random.randint(min_duration, max_duration, batch_size)          # ref:26
+    u_d = None
+    if device_rng is None:
+        u = torch.zeros((batch_size, max_duration, nin), dtype=torch.float64,
+                        pin_memory=torch.cuda.is_available())
+        un = u.numpy()
+        for i in range(batch_size):
+            un[i, :T[i]] = np.random.uniform(size=(T[i], nin))             # ref:32, same draw order
+        u_d = u.to(x_d.device, non_blocking=True)
+    t_len = torch.as_tensor(T.astype(np.int32)).to(x_d.device)
+    out = torch.empty((max_duration, batch_size, nin), dtype=torch.float32, device=x_d.device)
+    _lib.check(_lib.lib.dcll_image_encode(_lib.ptr(x_d), _lib.ptr(u_d), _lib.ptr(t_len), batch_size, nin, int(max_duration),
+                                          float(gain), int(device_rng or 0), _lib.ptr(out), _lib.current_stream()))
+    y_t = y if torch.is_tensor(y) else torch.as_tensor(np.asarray(y))
+    all_target = y_t.unsqueeze(0).expand(max_duration, *y_t.shape)
+    return out.reshape(max_duration, batch_size, *input_shape), all_target

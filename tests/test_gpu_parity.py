@@ -449,3 +449,34 @@ def test_window_activity_histogram_matches_numpy():
     net.accuracy(torch.zeros(45, 4, 24))
     net.write_stats(w, epoch=0)
     assert "conv0/low_pv/test" in w.scalars and "conv2/acc/test" in w.scalars
+
+
+# ------------------------------------------------------------------------------------------------
+# image2spiketrain on the device (data/utils.py:15-40)
+# ------------------------------------------------------------------------------------------------
+def test_image2spiketrain_device_matches_numpy_stream():
+    from snn_modulation_classification_b200.data.utils import image2spiketrain
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(9, 1, 28, 28, generator=g)
+    y = O.to_one_hot(torch.randint(0, 10, (9,), generator=g), 10)
+    for kw in (dict(gain=100, max_duration=60), dict(gain=50, min_duration=7, max_duration=41)):
+        np.random.seed(5)
+        want, want_t = O.image2spiketrain(x, y.numpy(), (1, 28, 28), **kw)
+        np.random.seed(5)
+        got, got_t = image2spiketrain(x, y, (1, 28, 28), **kw)
+        assert got.is_cuda and got.dtype == torch.float32 and tuple(got.shape) == want.shape
+        assert np.array_equal(got.cpu().numpy(), want.astype(np.float32))              # bit-exact for the same draws
+        assert np.array_equal(got_t.cpu().numpy(), want_t)
+    # device generator: same distribution (rate = gain * pixel / 1000 per timestep), silent after T_i, reproducible per seed
+    np.random.seed(5)
+    a, _ = image2spiketrain(x, y, (1, 28, 28), gain=100, min_duration=30, max_duration=400, device_rng=7)
+    np.random.seed(5)
+    b, _ = image2spiketrain(x, y, (1, 28, 28), gain=100, min_duration=30, max_duration=400, device_rng=7)
+    np.random.seed(5)
+    T = np.random.randint(30, 400, 9)
+    assert torch.equal(a, b)
+    for i in range(9):
+        assert float(a[T[i]:, i].sum()) == 0
+        rate = a[:T[i], i].mean(0).cpu().reshape(-1)
+        want_rate = (100 * x[i].reshape(-1) / 1000).clamp(0, 1)
+        assert float((rate - want_rate).abs().mean()) < 0.02 and abs(float(rate.mean() - want_rate.mean())) < 3e-3

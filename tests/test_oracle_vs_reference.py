@@ -213,3 +213,18 @@ def test_dense_layer_matches_reference():
             _, _, gW, gb = O.dense_local_grads(p, fo, y)
             torch.testing.assert_close(gW, m.weight.grad, rtol=1e-4, atol=1e-7 * float(gW.abs().max()))
             torch.testing.assert_close(gb, m.bias.grad, rtol=1e-4, atol=1e-7 * float(gb.abs().max()))
+
+
+def test_image2spiketrain_matches_reference():
+    """data/utils.py:15-40 -- same numpy stream, same spikes (incl. a non-default min_duration: ragged T_i)."""
+    _, _, U = refshim.load_reference()
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(6, 1, 7, 5, generator=g)
+    y = O.to_one_hot(torch.randint(0, 10, (6,), generator=g), 10).numpy()
+    for kw in (dict(gain=100, max_duration=40), dict(gain=50, min_duration=10, max_duration=33)):
+        np.random.seed(11)
+        want, want_t = U.image2spiketrain(x, y, (1, 7, 5), **kw)
+        np.random.seed(11)
+        got, got_t = O.image2spiketrain(x, y, (1, 7, 5), **kw)
+        assert got.shape == want.shape and np.array_equal(got, want) and np.array_equal(got_t, want_t)
+        assert 0 < got.mean() < 0.2
