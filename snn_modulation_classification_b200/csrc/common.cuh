@@ -87,6 +87,12 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
         }                                                                                                        \
     } while (0)
 
+// SMs the one-CTA-per-SM persistent kernels may fill: all 148, minus the ones the data-parallel driver (dp.cu) leaves to NCCL
+// while a collective is in flight.  A persistent grid that finds some SMs taken runs its last CTAs as a second wave (static
+// tile striding: up to 2x the kernel time); launching it a few CTAs smaller costs those few CTAs' share instead.
+int sm_budget();
+void set_reserved_sms(int n);
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -69,7 +69,7 @@ struct dcll_dp {
     ncclComm_t comm = nullptr;
     cudaStream_t side = nullptr;
     cudaEvent_t ev_grad[16], ev_red[16];
-    int rank = 0, world = 1;
+    int rank = 0, world = 1, max_ctas = 0;
 };
 
 #define DCLL_NCCL_OK(dp, expr)                                                                         \
@@ -103,7 +103,7 @@ extern "C" __attribute__((visibility("default"))) int dcll_dp_create(const char 
         delete dp;
         return rc;
     }
-    dp->rank = rank, dp->world = world;
+    dp->rank = rank, dp->world = world, dp->max_ctas = max_ctas;
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
@@ -140,6 +140,7 @@ extern "C" __attribute__((visibility("default"))) int dcll_net_window_dp(dcll_dp
                                                                           float *const *bucket, const size_t *bucket_floats, void *stream) {
     DCLL_REQUIRE(dp && dp->comm && layers && train && n_layers > 0 && n_layers <= 16 && x0 && target && T > 0 && iter0 && bucket && bucket_floats,
                  DCLL_EINVAL, "dcll_net_window_dp: bad arguments");
+    set_reserved_sms(0);
     int rc = dp_check(layers, train, n_layers);
     if (rc != DCLL_OK) return rc;
     for (int l = 0; l < n_layers; ++l) {
@@ -155,10 +156,17 @@ extern "C" __attribute__((visibility("default"))) int dcll_net_window_dp(dcll_dp
     const dcll_conv_layer &L0 = layers[0];
     const size_t x_stride = L0.x_mode == DCLL_X_CELLS ? (size_t)L0.B * 2 * sizeof(int32_t) : (size_t)L0.B * L0.Cin * L0.H * L0.W * sizeof(float);
     bool pending[16] = {false};
+    // while a collective may be running, the persistent kernels leave NCCL's CTAs their SMs (common.cuh: sm_budget)
+    auto reserve = [&]() {
+        bool any = false;
+        for (int l = 0; l < n_layers; ++l) any = any || pending[l];
+        set_reserved_sms(any ? (dp->max_ctas > 0 ? dp->max_ctas : 16) : 0);
+    };
     auto finish = [&](int l) -> int {
         if (!pending[l]) return DCLL_OK;
         DCLL_CUDA_OK(cudaStreamWaitEvent(st, dp->ev_red[l], 0));
         pending[l] = false;
+        reserve();
         return launch_bucket_adam(&layers[l], &train[l], bucket[l], st);
     };
     for (int t = 0; t < T; ++t) {
@@ -184,12 +192,14 @@ extern "C" __attribute__((visibility("default"))) int dcll_net_window_dp(dcll_dp
                 DCLL_NCCL_OK(dp, dp->api.AllReduce(bucket[l], bucket[l], bucket_floats[l], ncclFloat32, ncclAvg, dp->comm, dp->side));
                 DCLL_CUDA_OK(cudaEventRecord(dp->ev_red[l], dp->side));
                 pending[l] = true;
+                reserve();
             }
         }
     }
     for (int l = 0; l < n_layers; ++l) {
         rc = finish(l);
-        if (rc != DCLL_OK) return rc;
+        if (rc != DCLL_OK) break;
     }
-    return DCLL_OK;
+    set_reserved_sms(0);
+    return rc;
 }

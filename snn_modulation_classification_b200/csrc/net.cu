@@ -131,6 +131,10 @@ static int check_layer(const dcll_conv_layer *L, const char *who) {
     return DCLL_OK;
 }
 
+static int g_reserved_sms = 0;
+int sm_budget() { return 148 - g_reserved_sms; }
+void set_reserved_sms(int n) { g_reserved_sms = n < 0 ? 0 : (n > 64 ? 64 : n); }
+
 static int g_layer = 0;  // layer index of the step being enqueued (profile key only)
 int prof_layer() { return g_layer; }
 

@@ -232,7 +232,7 @@ bool readout_tc_supported(const dcll_conv_layer *L) {
 // least idle tail in the last wave.
 int readout_tc_blocks(const dcll_conv_layer *L) {
     const int n_chunks = ceil_div(geo_of(L).F, rotc::CH), n_rt = ceil_div(L->B, 128);
-    if (n_rt < 148) return max(1, min(n_chunks, 148 / n_rt));
+    if (n_rt < 148) return max(1, min(n_chunks, sm_budget() / n_rt));
     int best = 1;
     double best_eff = 0.0;
     for (int s = 1; s <= 4 && s <= n_chunks; ++s) {

@@ -360,8 +360,9 @@ bool wgrad_tc_supported(const dcll_conv_layer *L) {
 int wgrad_tc_splits(const dcll_conv_layer *L) {
     Geo g = geo_of(L);
     int n_units = L->B * ceil_div(g.Hc, 16) * ceil_div(g.Wc, 16);
-    if (L->Cin == 32) return n_units < 74 ? n_units : 74;   // partial blocks = CTA pairs (one kernel-row group per CTA)
-    return n_units < 148 ? n_units : 148;
+    const int sms = sm_budget();
+    if (L->Cin == 32) return n_units < sms / 2 ? n_units : sms / 2;   // partial blocks = CTA pairs (one kernel-row group per CTA)
+    return n_units < sms ? n_units : sms;
 }
 
 int launch_wgrad_tc(const dcll_conv_layer *L, float *partial, int S, cudaStream_t st) {

@@ -306,8 +306,9 @@ void wgrad_tc2_roles(const dcll_conv_layer *L, int *nA, int *nB) {
     Geo g = geo_of(L);
     const int n_units = L->B * ceil_div(g.Hc, wg2_tile()) * ceil_div(g.Wc, Wg2Geo::TW);
     // 74 CTA pairs: role A does 4 kernel columns per unit (4 x 4 x 113 cycles), role B 3 + half of the bias MMAs (4 x 3 x 113 + 2 x 64)
-    if (n_units >= 40) *nA = 40, *nB = 34;
-    else *nA = *nB = n_units < 37 ? n_units : 37;
+    const int pairs = sm_budget() / 2;                       // 74 unless the data-parallel driver holds SMs back for NCCL
+    if (n_units >= 40) *nA = (pairs * 40 + 37) / 74, *nB = pairs - *nA;
+    else *nA = *nB = n_units < pairs / 2 ? n_units : pairs / 2;
 }
 
 template <class G>
