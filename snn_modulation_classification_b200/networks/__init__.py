@@ -318,7 +318,9 @@ class ConvNetwork(torch.nn.Module):
         burnin = int(self.dcll_slices[0].burnin)
         if dist.get_backend(group) == 'nccl':
             if max_ctas is None:
-                max_ctas = int(os.environ.get('DCLL_DP_MAX_CTAS', '8'))
+                # measured on 2 B200s (128x128, B = 64 per GPU): 4 and 8 CTAs scale alike (0.969 / 0.967 of the 1-GPU step),
+                # 2 starves the 50 MB output_ bucket (0.941); fewer CTAs = fewer SMs held back from the persistent kernels
+                max_ctas = int(os.environ.get('DCLL_DP_MAX_CTAS', '4'))
             dp = self._dp_handle(group, max_ctas)
             iter0 = (ctypes.c_int32 * n)(*[int(s.iter) for s in self.dcll_slices])
             bptr = (ctypes.c_void_p * n)(*[_lib.ptr(b) for b in buckets])

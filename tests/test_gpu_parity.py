@@ -479,4 +479,6 @@ def test_image2spiketrain_device_matches_numpy_stream():
         assert float(a[T[i]:, i].sum()) == 0
         rate = a[:T[i], i].mean(0).cpu().reshape(-1)
         want_rate = (100 * x[i].reshape(-1) / 1000).clamp(0, 1)
-        assert float((rate - want_rate).abs().mean()) < 0.02 and abs(float(rate.mean() - want_rate.mean())) < 3e-3
+        # per-pixel sampling error of a Bernoulli rate over T_i timesteps ~ sqrt(p(1-p)/T_i); the image mean is 784x tighter
+        assert float((rate - want_rate).abs().mean()) < 1.5 * float(np.sqrt(0.05 / T[i]))
+        assert abs(float(rate.mean() - want_rate.mean())) < 5 * float(np.sqrt(0.05 / (T[i] * 784)))
