@@ -394,6 +394,48 @@ def other_workloads(flush):
     return res_out
 
 
+def config5_line(world, rank, flush, T=128):
+    """radio_ml_conv data-parallel training at global batch 8192 (BASELINE.json configs[4]), 16x16, T timesteps, bf16x3:
+    1 warm-up + 2 timed windows, barrier + device events, max over ranks.  Collective on every rank."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from snn_modulation_classification_b200.data.utils import iq2spiketrain
+    name = "radio_ml_conv_train_dp_global8192_16x16"
+    spec, res, batch, train, arp, burnin, scaling = workload(name, world)
+    net = build_net(name, world).set_precision("bf16x3")
+    if world > 1:
+        for p in net.state_dict().values():
+            dist.broadcast(p, 0)
+    x, y = synth(batch, 100 + rank)
+    x, y = x.cuda(), y.cuda()
+    enc = dict(out_w=res, out_h=res, min_I=-1, max_I=1, min_Q=-1, max_Q=1, max_duration=T, as_cells=True)
+
+    def step():
+        cells, _ = iq2spiketrain(x, y, **enc)
+        net.reset()
+        if world > 1:
+            net.learn_window_dp(cells, y)
+        else:
+            net.learn_window(cells, y)
+    np.random.seed(1)
+    step()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([_event_timed(step, 2, flush)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    del net
+    torch.cuda.empty_cache()
+    return {"workload": name, "global_batch": batch * world, "batch_per_gpu": batch, "n_gpus": world, "timesteps": T,
+            "resolution": "16x16", "scaling": scaling, "windows_per_s": batch * world / (ms / 1e3), "ms_per_window_batch": ms,
+            "sample_timesteps_per_s": batch * world * T / (ms / 1e3),
+            "note": "whole-job windows/s at T=%d (not extrapolated to 1024); %s" % (
+                T, "NCCL all-reduce of the local-layer gradient buckets per timestep inside dcll_net_window_dp" if world > 1
+                else "single GPU: no collective")}
+
+
 def run_b200(a):
     import numpy as np
     import torch
@@ -473,6 +515,14 @@ def run_b200(a):
     _lib.check(_lib.lib.dcll_profile_enable(0))
     ms_e2e = timed(step_e2e, a.steps)
     clocks = sampler.stop() if sampler else None
+    # BASELINE.json configs[4]: data-parallel training at GLOBAL batch 8192 (8192 / N windows per GPU; 16x16 script geometry, which
+    # fits any N), a short window on every rank so that the line is driver-visible at each N of the scaling run
+    cfg5 = None
+    n_layers = len(net.dcll_slices)
+    if not a.no_extras and a.workload == DEFAULT and 8192 % world == 0:
+        net = None
+        torch.cuda.empty_cache()
+        cfg5 = config5_line(world, rank, flush)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -482,7 +532,6 @@ def run_b200(a):
     e2e = world * batch * a.steps / (ms_e2e / 1e3)
     pk = peaks()
     hw = res * res
-    n_layers = len(net.dcll_slices)
     per_class = {}
     for (name, layer), (tms, n) in sorted(prof.items()):
         per_class["%s[l%d]" % (name, layer)] = {"avg_ms": tms / n, "samples": n}
@@ -578,7 +627,11 @@ def run_b200(a):
                    "h2d_bytes_per_step": int(x_pin.numel() * 4 + y_pin.numel() * 4),
                    "d2h_bytes_per_step": int(pred_pin.numel() * 4)},
            "gpu_launches": launches, "roofline": roofline, "kernel_ms": per_class, "clocks": clocks}
+    if cfg5 is not None:
+        out["dp_global_batch_8192"] = cfg5
     if world == 1 and a.precision != "fp32" and not a.no_extras:
+        net = build_net(a.workload, world)
+        net.set_precision(a.precision)
         # BASELINE.json configs[0] says FP32: the same workload in the FP32-exact parity mode (CUDA-core FMA kernels), whole
         # windows at the full T, 1 warm-up + 2 timed
         net.set_precision("fp32")

@@ -160,7 +160,8 @@ extern "C" __attribute__((visibility("default"))) int dcll_net_window_dp(dcll_dp
     auto reserve = [&]() {
         bool any = false;
         for (int l = 0; l < n_layers; ++l) any = any || pending[l];
-        set_reserved_sms(any ? (dp->max_ctas > 0 ? dp->max_ctas : 16) : 0);
+        // (a single-rank communicator moves nothing: no SMs to leave, and the window then equals dcll_net_window bit for bit)
+        set_reserved_sms(any && dp->world > 1 ? (dp->max_ctas > 0 ? dp->max_ctas : 16) : 0);
     };
     auto finish = [&](int l) -> int {
         if (!pending[l]) return DCLL_OK;

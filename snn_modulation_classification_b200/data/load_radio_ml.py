@@ -33,10 +33,10 @@ def _h5_module(h5):
         return h5
     try:
         import h5py
-    except ImportError as e:                   # no silent fallback to synthetic data
-        raise ImportError('reading the RadioML HDF5 files needs h5py (not installed); use '
-                          'snn_modulation_classification_b200.data.synthetic for synthetic records') from e
-    return h5py
+        return h5py
+    except ImportError:                        # install-free reader for the earliest-format files the split writes
+        from . import minih5                   # (contiguous datasets; anything else raises NotImplementedError, never synthetic data)
+        return minih5
 
 
 def pair_file(data_dir, class_idx, snr):

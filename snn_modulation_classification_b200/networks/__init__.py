@@ -52,6 +52,9 @@ def load_network_spec(yaml_path):
     return convs
 
 
+_DP_HANDLES = {}
+
+
 def grad_bucket(lay, dev):
     """One flat float32 bucket per layer holding (gW, gb[, gWout, gbout]) back to back: the unit of the
     data-parallel all-reduce (6.4 KB for conv0, 201 KB for conv1/2, + 24*F+24 floats for
@@ -239,11 +242,8 @@ class ConvNetwork(torch.nn.Module):
         it through torch.distributed, every rank joins)."""
         import torch.distributed as dist
         key = (id(group), dist.get_rank(group), dist.get_world_size(group), int(max_ctas))
-        h = getattr(self, '_dp', None)
-        if h is not None and h['key'] == key:
-            return h['dp']
-        if h is not None:
-            _lib.check(_lib.lib.dcll_dp_destroy(h['dp']))
+        if key in _DP_HANDLES:                     # one communicator per (group, CTA cap) and process, shared by all networks
+            return _DP_HANDLES[key]
         lib_path = _lib.nccl_library_path()
         lib_c = lib_path.encode() if lib_path else None
         dev = self.dcll_slices[0].dclllayer.i2h.weight.device
@@ -258,7 +258,7 @@ class ConvNetwork(torch.nn.Module):
         dp = ctypes.c_void_p()
         _lib.check(_lib.lib.dcll_dp_create(lib_c, ctypes.cast(buf, ctypes.c_void_p), dist.get_rank(group),
                                            dist.get_world_size(group), int(max_ctas), ctypes.byref(dp)))
-        self._dp = dict(key=key, dp=dp)
+        _DP_HANDLES[key] = dp
         return dp
 
     def learn_window_dp(self, x, labels, group=None, max_ctas=None):

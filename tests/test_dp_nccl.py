@@ -9,7 +9,8 @@ import torch
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")]
+pytestmark = [pytest.mark.gpu]
+two_gpus = pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 
 
 def _free_port():
@@ -63,6 +64,7 @@ def _worker(rank, world, port, precision, out_q):
     dist.destroy_process_group()
 
 
+@two_gpus
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 def test_dp_two_gpus_matches_single_process(precision):
     world, port = 2, _free_port()
@@ -77,3 +79,63 @@ def test_dp_two_gpus_matches_single_process(precision):
     assert all(r[1] for r in res), res
     # 5 training steps, error x2 per step from summation-order differences
     assert res[0][2] <= (0.3 if precision == "fp32" else 2.0), res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The C data-parallel driver on ONE GPU: a single-rank NCCL communicator (the all-reduce is the identity), so this runs
+# wherever the other GPU tests run.  dcll_net_window_dp -- side stream, events, bucket layout, Adam from the bucket -- must
+# then reproduce learn_window bit for bit: the gradients are the same numbers, only the route to the Adam step differs.
+# ---------------------------------------------------------------------------------------------------------------------
+def _worker_single(port, precision, out_q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import numpy as np
+    import torch.distributed as dist
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    from oracle import dcll_oracle as O
+    from util_build import build_pair
+    from snn_modulation_classification_b200.data.utils import iq2spiketrain
+    B, K, T, W, burnin = 12, 24, 9, 16, 3
+    g = torch.Generator().manual_seed(4)
+    xs = (torch.randn(B, 2, 1, 1024, generator=g) * 0.4).float()
+    y = O.to_one_hot(torch.randint(0, K, (B,), generator=g), K).cuda()
+    nets = []
+    for _ in range(2):
+        n, _ = build_pair("radio_ml_conv", (1, W, W), B, K, arp=1.0, burnin=burnin)
+        nets.append(n.set_precision(precision))
+    np.random.seed(1)
+    cells, _ = iq2spiketrain(xs, y, out_w=W, out_h=W, max_duration=T, as_cells=True)
+    for n in nets:
+        n.reset()
+    nets[0].learn_window(cells, y)
+    nets[1].learn_window_dp(cells, y)
+    torch.cuda.synchronize()
+    ok = True
+    for a, b in zip(nets[0].dcll_slices, nets[1].dcll_slices):
+        ok = ok and torch.equal(a.dclllayer.i2h.weight, b.dclllayer.i2h.weight) and torch.equal(a.dclllayer.i2h.bias, b.dclllayer.i2h.bias)
+        ok = ok and torch.equal(a.dclllayer.i2h.state.eps1, b.dclllayer.i2h.state.eps1)
+        ok = ok and np.array_equal(np.array(a.clout), np.array(b.clout)) and a.iter == b.iter
+        if a.dclllayer.output_layer:
+            ok = ok and torch.equal(a.dclllayer.output_.weight, b.dclllayer.output_.weight)
+            ok = ok and torch.equal(a.dclllayer.output_.bias, b.dclllayer.output_.bias)
+        sa, sb = a.optimizer.state[a.dclllayer.i2h.weight], b.optimizer.state[b.dclllayer.i2h.weight]
+        ok = ok and float(sa["step"]) == float(sb["step"]) == T - burnin + 1 and torch.equal(sa["exp_avg_sq"], sb["exp_avg_sq"])
+    out_q.put(ok)
+    dist.destroy_process_group()
+
+
+single_gpu = pytest.mark.skipif(torch.cuda.device_count() < 1, reason="needs a GPU")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_dp_driver_single_rank_equals_learn_window(precision):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_worker_single, args=(port, precision, q))
+    p.start()
+    ok = q.get(timeout=600)
+    p.join(timeout=120)
+    assert ok
