@@ -131,6 +131,10 @@ size_t dcll_sizeof_train_args(void);
 int64_t dcll_launch_count(int reset);
 int dcll_profile_enable(int every_n);
 int dcll_profile_read(double *ms, int64_t *n);
+/* dcll_debug_timeline: in-kernel stopwatch of the persistent tensor-core kernels (DCLL_TIMELINE=1 in the environment before the
+ * first launch, otherwise an error): copies [4 kernel kinds][148 CTAs][16 slots] SM-cycle counters of the last launch of each
+ * kind (csrc/common.cuh TL_*; tools/timeline.py prints them).  Synchronises the device.  Returns the number of values. */
+int dcll_debug_timeline(uint64_t *out, int n_u64);
 
 /* -- encoder: data/utils.py:43-87 (iq2spiketrain) ------------------------------------------ *
  * x: device float32 [B,2,N]; cells: device int32 [T,B,2] = (cell_Q, cell_I) for samples

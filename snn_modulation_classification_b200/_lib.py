@@ -113,6 +113,8 @@ def _load():
     lib.dcll_profile_enable.restype = C.c_int
     lib.dcll_profile_read.argtypes = [P(C.c_double), P(C.c_int64)]
     lib.dcll_profile_read.restype = C.c_int
+    lib.dcll_debug_timeline.argtypes = [P(C.c_uint64), C.c_int]
+    lib.dcll_debug_timeline.restype = C.c_int
     lib.dcll_conv_workspace_bytes.argtypes = [P(ConvLayer)]
     lib.dcll_conv_workspace_bytes.restype = C.c_size_t
     return lib
@@ -140,7 +142,7 @@ EXPORTS = ["dcll_launch_count", "dcll_profile_enable", "dcll_profile_read", "dcl
            "dcll_conv_core_fwd", "dcll_conv_step_bwd_update", "dcll_conv_apply_update", "dcll_net_window", "dcll_vote",
            "dcll_quantize", "dcll_dequantize", "dcll_sizeof_dense_layer", "dcll_dense_step_fwd",
            "dcll_dense_step_bwd_update", "dcll_net_window_stats", "dcll_infer_stack16", "dcll_conv_readout_rows", "dcll_conv_step_fwd_chain",
-           "dcll_conv_chain_fusable", "dcll_dp_unique_id", "dcll_dp_create", "dcll_dp_destroy", "dcll_net_window_dp", "dcll_image_encode"]
+           "dcll_conv_chain_fusable", "dcll_dp_unique_id", "dcll_dp_create", "dcll_dp_destroy", "dcll_net_window_dp", "dcll_image_encode", "dcll_debug_timeline"]
 
 
 def check(rc):

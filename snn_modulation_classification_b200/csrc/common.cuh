@@ -87,6 +87,27 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
         }                                                                                                        \
     } while (0)
 
+// ---- in-kernel stopwatch (DCLL_TIMELINE=1; debugging aid, off by default) -----------------------------------------------
+// The persistent tensor-core kernels accumulate, per CTA, the SM cycles their roles spend waiting on each barrier and in each
+// phase into TL_SLOTS 64-bit slots of a per-kernel-kind block; dcll_debug_timeline copies the blocks out (tools/timeline.py).
+// The last launch of a kind wins.  timeline_buf returns nullptr when the stopwatch is off: the kernels then skip every clock read.
+enum { TL_CONV_MMA32 = 0, TL_CONV_MMA1, TL_CONV_MMA2, TL_WGRAD2, TL_KINDS, TL_SLOTS = 16, TL_CTAS = 148 };
+enum { TL_TOTAL = 0, TL_PROLOGUE, TL_ISS_A_FULL, TL_ISS_ACC_EMPTY, TL_ISS_W_FULL, TL_ISS_LOOP, TL_EPI_ACC_FULL, TL_EPI_LOOP, TL_WPROD_EMPTY,
+       TL_APROD_EMPTY, TL_FIRST_MMA, TL_DRAIN, TL_EPI_LOADS };
+unsigned long long *timeline_buf(int kind);
+#ifdef __CUDACC__
+#define TL_TIMED(on, acc, stmt)                  \
+    do {                                         \
+        if (on) {                                \
+            const long long tl_t0_ = clock64();  \
+            stmt;                                \
+            (acc) += clock64() - tl_t0_;         \
+        } else {                                 \
+            stmt;                                \
+        }                                        \
+    } while (0)
+#endif
+
 // SMs the one-CTA-per-SM persistent kernels may fill: all 148, minus the ones the data-parallel driver (dp.cu) leaves to NCCL
 // while a collective is in flight.  A persistent grid that finds some SMs taken runs its last CTAs as a second wave (static
 // tile striding: up to 2x the kernel time); launching it a few CTAs smaller costs those few CTAs' share instead.

@@ -135,7 +135,25 @@ static int g_reserved_sms = 0;
 int sm_budget() { return 148 - g_reserved_sms; }
 void set_reserved_sms(int n) { g_reserved_sms = n < 0 ? 0 : (n > 64 ? 64 : n); }
 
+// in-kernel stopwatch blocks (common.cuh): allocated on first use when DCLL_TIMELINE=1
+static unsigned long long *g_timeline = nullptr;
 static int g_layer = 0;  // layer index of the step being enqueued (profile key only)
+unsigned long long *timeline_buf(int kind) {
+    static int on = -1, only_layer = -1;                    // DCLL_TIMELINE_LAYER=l: only launches of layer l write their block
+    if (on < 0) {
+        const char *e = getenv("DCLL_TIMELINE");
+        const char *el = getenv("DCLL_TIMELINE_LAYER");
+        only_layer = el ? atoi(el) : -1;
+        on = (e && e[0] == '1') ? 1 : 0;
+        if (on) {
+            const size_t bytes = sizeof(unsigned long long) * TL_KINDS * TL_CTAS * TL_SLOTS;
+            if (cudaMalloc(&g_timeline, bytes) != cudaSuccess || cudaMemset(g_timeline, 0, bytes) != cudaSuccess) g_timeline = nullptr, on = 0;
+        }
+    }
+    if (only_layer >= 0 && g_layer != only_layer) return nullptr;
+    return (on && kind >= 0 && kind < TL_KINDS) ? g_timeline + (size_t)kind * TL_CTAS * TL_SLOTS : nullptr;
+}
+
 int prof_layer() { return g_layer; }
 
 static int step_fwd(dcll_conv_layer *L, const void *x, const float *target, int loss_kind, int32_t *clout, float *loss_out,
@@ -311,6 +329,15 @@ extern "C" __attribute__((visibility("default"))) int dcll_profile_read(double *
     }
     g_prof_n = 0;
     return DCLL_OK;
+}
+extern "C" __attribute__((visibility("default"))) int dcll_debug_timeline(uint64_t *out, int n_u64) {
+    const int n = TL_KINDS * TL_CTAS * TL_SLOTS;
+    DCLL_REQUIRE(out && n_u64 >= n, DCLL_EINVAL, "dcll_debug_timeline: need room for %d values", n);
+    timeline_buf(0);
+    DCLL_REQUIRE(g_timeline, DCLL_EINVAL, "dcll_debug_timeline: the stopwatch is off (DCLL_TIMELINE=1 before the first launch)");
+    DCLL_CUDA_OK(cudaDeviceSynchronize());
+    DCLL_CUDA_OK(cudaMemcpy(out, g_timeline, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
+    return n;
 }
 extern "C" __attribute__((visibility("default"))) const char *dcll_last_error(void) { return g_err; }
 extern "C" __attribute__((visibility("default"))) size_t dcll_sizeof_conv_layer(void) { return sizeof(dcll_conv_layer); }

@@ -48,6 +48,7 @@ struct Wg2P {
     int nA, nB;          // CTA pairs of role A (kernel columns 0..3) and role B (4..6 + bias)
     int dbg;             // DCLL_WG2_DEBUG (timing experiments only, results are garbage): bit 0 skip eps1 loads, bit 1 skip g_u loads,
                          // bit 2 skip the MMAs
+    unsigned long long *tl;   // in-kernel stopwatch block (common.cuh TL_*), null when off
 };
 
 template <int TH_, int NSTAGE_>
@@ -95,6 +96,9 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
     uint32_t *ones_used = tmem_slot + 1;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool tl_on = p.tl != nullptr;
+    unsigned long long *tl = tl_on ? p.tl + (size_t)blockIdx.x * TL_SLOTS : nullptr;
+    const long long tl_entry = tl_on ? clock64() : 0;
     if (tid == 0) {
         for (int i = 0; i < G::NSTAGE; ++i) mbar_init(full + i, 1), mbar_init(empty + i, 2);
         mbar_init(done, 2);
@@ -110,6 +114,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_entry();   // nothing global is touched before here
+    if (tl_on && tid == 0) tl[TL_PROLOGUE] = clock64() - tl_entry;
 
     // role / group / unit walk of this CTA: CTAs (2k, 2k+1) form a pair (g = 0, 1) that walks the same units
     const int pair_id = blockIdx.x >> 1, grp = blockIdx.x & 1;
@@ -129,17 +134,19 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
             tma_prefetch_desc(&tmx);
             tma_prefetch_desc(&tmg);
             int i = 0;
+            long long tl_wait = 0;
             for (int u = u_first; u < p.n_units; u += u_step, ++i) {
                 const int sg = i % G::NSTAGE;
                 const uint32_t sX = smem_u32(smem + sg * G::BUF), sG = sX + G::X_BYTES, bar = smem_u32(full + sg);
                 const int b = u / tiles, tile = u - b * tiles;
                 const int th_i = tile / p.tiles_w, tw_i = tile - th_i * p.tiles_w;
                 const int h0 = th_i * G::TH, w0 = tw_i * G::TW;
-                if (i >= G::NSTAGE) mbar_wait(empty + sg, ((i / G::NSTAGE) - 1) & 1);   // MMAs of unit i-NSTAGE have read this stage
+                if (i >= G::NSTAGE) TL_TIMED(tl_on, tl_wait, mbar_wait(empty + sg, ((i / G::NSTAGE) - 1) & 1));   // MMAs of unit i-NSTAGE have read this stage
                 mbar_expect_tx(full + sg, ((p.dbg & 1) ? 0 : G::X_BYTES) + ((p.dbg & 2) ? 0 : G::G_BYTES));
                 if (!(p.dbg & 1)) tma_load_5d(sX, &tmx, bar, 0, w0 - p.padW, 0, h0 - p.padH + row_off, 2 * b);
                 if (!(p.dbg & 2)) tma_load_5d(sG, &tmg, bar, 0, w0 >> 3, 0, 8 * b, h0 >> 1);
             }
+            if (tl_on) tl[TL_APROD_EMPTY] = tl_wait;
         }
     } else if (warp < 2) {
         // ================= MMA issuers: warp 0 = first two kernel columns of the role, warp 1 = the rest (+ bias) =================
@@ -154,6 +161,8 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
         const uint64_t ones_desc = desc(ONES_HI, desc_lo(smem_u32(smem + G::OFF_ONES), 2048));
         uint32_t ones_acc = 0;
         int i = 0;
+        long long tl_wait = 0;
+        const long long tl_loop0 = tl_on ? clock64() : 0;
         for (int u = u_first; u < p.n_units; u += u_step, ++i) {
             const int sg = i % G::NSTAGE;
             const int tile = u % tiles;
@@ -161,8 +170,9 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
             const int npair = (min(G::TH, p.Hc - h0) + 1) >> 1;
             const uint32_t a_base = desc_lo(smem_u32(smem + sg * G::BUF), 128);                      // LBO: next 8 positions (K)
             const uint32_t b_base = desc_lo(smem_u32(smem + sg * G::BUF + G::X_BYTES), 128);         // LBO: next 8 columns (K)
-            mbar_wait(full + sg, (i / G::NSTAGE) & 1);
+            TL_TIMED(tl_on, tl_wait, mbar_wait(full + sg, (i / G::NSTAGE) & 1));
             fence_after();
+            if (tl_on && i == 0 && warp == 0 && elected) tl[TL_FIRST_MMA] = clock64() - tl_entry;
             if (elected) {
                 for (int pr = 0; pr < ((p.dbg & 4) ? (i == 0 ? 1 : 0) : npair); ++pr) {
                     const uint64_t b = desc(B_HI, b_base + pr * (G::G_PAIR >> 4));
@@ -186,6 +196,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
         if (elected) {
             if (do_ones) *ones_used = ones_acc;
             commit(done);
+            if (tl_on) tl[warp == 0 ? TL_ISS_A_FULL : TL_ISS_W_FULL] = tl_wait, tl[warp == 0 ? TL_ISS_LOOP : TL_EPI_LOOP] = clock64() - tl_loop0;
         }
         __syncwarp();
     }
@@ -199,6 +210,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
     mbar_wait(done, 0);
     fence_after();
     __syncthreads();
+    const long long tl_drain0 = tl_on ? clock64() : 0;
     {
         const int q = warp & 3;                                          // TMEM lane quarter of this warp = dy
         const int ci = lane;
@@ -254,6 +266,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
     }
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)G::TMEM_COLS);
+    if (tl_on && tid == 0) tl[TL_DRAIN] = clock64() - tl_drain0, tl[TL_TOTAL] = clock64() - tl_entry;
 }
 
 // Tensor maps of the two operand images (cached per buffer and geometry, tmap.cu).  Dimension ORDER = order of the box in
@@ -327,6 +340,7 @@ static int launch_wgrad_tc2_g(const dcll_conv_layer *L, float *partial, int *nA_
         dbg = e ? atoi(e) : 0;
     }
     p.dbg = dbg;
+    p.tl = timeline_buf(TL_WGRAD2);
     TmapDesc tmx, tmg;
     DCLL_REQUIRE(wg2_tmaps(L, &tmx, &tmg), DCLL_ECUDA, "wgrad_tc2: cuTensorMapEncodeTiled failed");
     DCLL_SMEM_ATTR((wgrad_tc2_kernel<G::TH, G::NSTAGE>), G::SMEM);
