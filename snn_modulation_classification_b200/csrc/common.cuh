@@ -93,9 +93,14 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
 // The last launch of a kind wins.  timeline_buf returns nullptr when the stopwatch is off: the kernels then skip every clock read.
 enum { TL_CONV_MMA32 = 0, TL_CONV_MMA1, TL_CONV_MMA2, TL_WGRAD2, TL_KINDS, TL_SLOTS = 16, TL_CTAS = 148 };
 enum { TL_TOTAL = 0, TL_PROLOGUE, TL_ISS_A_FULL, TL_ISS_ACC_EMPTY, TL_ISS_W_FULL, TL_ISS_LOOP, TL_EPI_ACC_FULL, TL_EPI_LOOP, TL_WPROD_EMPTY,
-       TL_APROD_EMPTY, TL_FIRST_MMA, TL_DRAIN, TL_EPI_LOADS };
+       TL_APROD_EMPTY, TL_FIRST_MMA, TL_DRAIN, TL_EPI_LOADS, TL_T_ENTRY, TL_T_EXIT };   // the last two: %globaltimer (ns)
 unsigned long long *timeline_buf(int kind);
 #ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 #define TL_TIMED(on, acc, stmt)                  \
     do {                                         \
         if (on) {                                \

@@ -323,10 +323,22 @@ __device__ __forceinline__ void store_gu_img(uint32_t *q32, int half_f, float2 v
     q32[half_f] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
 }
 
+// pv rows reach the thread through a ring of thread-PRIVATE shared-memory slots filled by 8-byte cp.async (LDGSTS): NG groups of
+// UB rows, requested NG - 1 groups ahead -- no registers held while the loads fly and no barrier (a thread only ever reads what it
+// copied itself).  With the register double buffer of the first packed version a CTA had 16 KB in flight (32 KB per SM): latency-
+// bound at ~3.3 TB/s of reads; at B = 64 the whole 32-row slice of a CTA is now requested before the first multiply (64 KB per
+// CTA).  The CTAs that share a block of Wo columns (the batch slices) are adjacent in the 1-D grid, so the second read of those
+// columns hits L2 instead of DRAM.
+constexpr int RB2_NG = 4;
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
 template <int KMAX, int UB, int MINB, bool IMG>
 __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
                                                               const float *__restrict__ g_o, int B, int F, int K, int b_per_blk,
-                                                              float *__restrict__ g_u, int hw) {
+                                                              float *__restrict__ g_u, int hw, int slices) {
+    extern __shared__ __align__(16) float2 rb2_ring[];                 // [RB2_NG][UB][256]
+    const int fblk = blockIdx.x / slices, slice = blockIdx.x - fblk * slices;
     pdl_entry();
     // g rows are read back as broadcast LDS.128 (4 k per load) and enter the FFMA2 as a scalar-broadcast operand: ptxas folds
     // the {g,g} pair into `FFMA2 Rd, Rg.F32, Rw.F32x2, Rs.F32x2`.  (Storing the rows duplicated {g,g} doubled the LDS traffic
@@ -334,12 +346,12 @@ __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__
     __shared__ __align__(16) float gd[64][KMAX];
     static_assert(KMAX % 4 == 0, "float4 rows");
     const int tid = threadIdx.x;
-    int f = 2 * (blockIdx.x * 256 + tid);
+    int f = 2 * (fblk * 256 + tid);
     bool fok = f < F;
     int img_word = 0;                                      // IMG: 32-bit word of this thread's bf16 pair inside one part of the sample
     if (IMG) {
         const int chunks = hw >> 3, blk_per_cog = (chunks + 7) >> 3;          // 8-position chunks per plane, 64-position blocks
-        const int cog = blockIdx.x / blk_per_cog, pb = blockIdx.x - cog * blk_per_cog;
+        const int cog = fblk / blk_per_cog, pb = fblk - cog * blk_per_cog;
         // warp = one channel of the group, lanes = 64 consecutive positions: the pv / Wo loads stay 256-byte contiguous per warp
         // (with lanes = 8 channels x 8 positions they were 8 scattered sectors: +0.02 ms per launch, measured); the 4-byte image
         // stores of a warp land as 16-byte runs in 8 lines, whose other runs come from the 7 sibling warps of this CTA
@@ -348,10 +360,27 @@ __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__
         fok = c8 < chunks && f < F;
         img_word = ((cog * chunks + c8) * 8 + co8) * 4 + pr;
     }
+    const int b_begin = slice * b_per_blk, b_end = min(B, b_begin + b_per_blk);
+    const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(rb2_ring) + tid * 8;
+    // group g of the rows b0.. : UB rows of this thread's feature pair -> ring stage g % NG
+    auto request = [&](int b0, int g) {
+        const float *src = pv + (size_t)(b0 + g * UB) * F + f;
+        const uint32_t dst = ring0 + (g % RB2_NG) * (UB * 256 * 8);
+#pragma unroll
+        for (int u = 0; u < UB; ++u, src += F) cp_async8(dst + u * (256 * 8), src);
+    };
+    // the first groups are requested before anything else, so they fly together with the Wo columns and the g_o rows
+    if (fok && b_begin < b_end) {
+        const int ng0 = min(64, b_end - b_begin) / UB;
+#pragma unroll
+        for (int g = 0; g < RB2_NG - 1; ++g) {
+            if (g < ng0) request(b_begin, g);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    }
     float2 w[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) w[k] = (k < K && fok) ? __ldg(reinterpret_cast<const float2 *>(wo + (size_t)k * F + f)) : make_float2(0.f, 0.f);
-    const int b_begin = blockIdx.y * b_per_blk, b_end = min(B, b_begin + b_per_blk);
     for (int b0 = b_begin; b0 < b_end; b0 += 64) {
         const int nb = min(64, b_end - b0);
         __syncthreads();
@@ -380,23 +409,24 @@ __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__
                 return fmul2(fmul2(s, ffma2(p, neg2, one2)), p);
             };
             int bb = 0;
-            // full groups: no per-load predicates, row pointers advance by F (the predicated form spent ~12 instructions
-            // per load on 64-bit address arithmetic).  The loads of group i+1 are issued before group i is multiplied, so
-            // every thread keeps UB rows in flight all the time instead of only between its compute phases.
-            if (nb >= UB) {
-                float2 cur[UB], nxt[UB];
-                const float *p = pvp;
+            // full groups of UB rows through the cp.async ring (requested RB2_NG - 1 groups ahead; the first ones at kernel entry)
+            {
+                const int ng = nb / UB;
+                if (b0 != b_begin) {
 #pragma unroll
-                for (int u = 0; u < UB; ++u, p += rowF) cur[u] = __ldg(reinterpret_cast<const float2 *>(p));
-                pvp = p;
-                for (; bb + UB <= nb; bb += UB) {
-                    const bool more = bb + 2 * UB <= nb;
-                    if (more) {
-                        p = pvp;
-#pragma unroll
-                        for (int u = 0; u < UB; ++u, p += rowF) nxt[u] = __ldg(reinterpret_cast<const float2 *>(p));
-                        pvp = p;
+                    for (int g = 0; g < RB2_NG - 1; ++g) {
+                        if (g < ng) request(b0, g);
+                        asm volatile("cp.async.commit_group;" ::: "memory");
                     }
+                }
+                for (int g = 0; g < ng; ++g, bb += UB) {
+                    if (g + RB2_NG - 1 < ng) request(b0, g + RB2_NG - 1);   // its stage was read by this thread one iteration ago
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    asm volatile("cp.async.wait_group %0;" ::"n"(RB2_NG - 1) : "memory");
+                    const float2 *stage = rb2_ring + (g % RB2_NG) * (UB * 256) + tid;
+                    float2 cur[UB];
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) cur[u] = stage[u * 256];
                     float *q = gup;
 #pragma unroll
                     for (int u = 0; u < UB; ++u, q += rowF) {
@@ -405,11 +435,9 @@ __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__
                         else *reinterpret_cast<float2 *>(q) = v;
                     }
                     gup = q;
-                    if (more) {
-#pragma unroll
-                        for (int u = 0; u < UB; ++u) cur[u] = nxt[u];
-                    }
                 }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                pvp += (size_t)ng * UB * rowF;
             }
             for (; bb < nb; ++bb, pvp += rowF, gup += rowF) {
                 const float2 v = sample(bb, __ldg(reinterpret_cast<const float2 *>(pvp)));
@@ -511,11 +539,27 @@ __global__ void __launch_bounds__(256, 3) wout_grad_adam2_kernel(const float *__
     constexpr int KH = KMAX / 2, UB = 8;
     static_assert(KH % 4 == 0, "float4 rows per half");
     __shared__ __align__(16) float gd[64][KMAX];                  // broadcast LDS.128 rows, see readout_bwd2_kernel
+    extern __shared__ __align__(16) float2 rb2_ring[];            // [RB2_NG][UB][256]: thread-private cp.async slots (readout_bwd2_kernel)
     const int tid = threadIdx.x, pair = tid & 127, half = tid >> 7;
     const int f = 2 * (blockIdx.x * 128 + pair);
     const bool fok = f < F;
     const int kbase = half * KH;
     const size_t rowF = (size_t)F;
+    const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(rb2_ring) + tid * 8;
+    auto request = [&](int b0, int g) {
+        const float *src = pv + (size_t)(b0 + g * UB) * F + f;
+        const uint32_t dst = ring0 + (g % RB2_NG) * (UB * 256 * 8);
+#pragma unroll
+        for (int u = 0; u < UB; ++u, src += F) cp_async8(dst + u * (256 * 8), src);
+    };
+    if (fok) {
+        const int ng0 = min(64, B) / UB;
+#pragma unroll
+        for (int g = 0; g < RB2_NG - 1; ++g) {
+            if (g < ng0) request(0, g);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    }
     float2 acc[KH];
 #pragma unroll
     for (int k = 0; k < KH; ++k) acc[k] = make_float2(0.f, 0.f);
@@ -541,27 +585,28 @@ __global__ void __launch_bounds__(256, 3) wout_grad_adam2_kernel(const float *__
                 }
             };
             int bb = 0;
-            if (nb >= UB) {
-                float2 cur[UB], nxt[UB];
-                const float *p = pvp;
+            {
+                const int ng = nb / UB;
+                if (b0 != 0) {
 #pragma unroll
-                for (int u = 0; u < UB; ++u, p += rowF) cur[u] = __ldg(reinterpret_cast<const float2 *>(p));
-                pvp = p;
-                for (; bb + UB <= nb; bb += UB) {
-                    const bool more = bb + 2 * UB <= nb;
-                    if (more) {
-                        p = pvp;
-#pragma unroll
-                        for (int u = 0; u < UB; ++u, p += rowF) nxt[u] = __ldg(reinterpret_cast<const float2 *>(p));
-                        pvp = p;
-                    }
-#pragma unroll
-                    for (int u = 0; u < UB; ++u) sample(bb + u, cur[u]);
-                    if (more) {
-#pragma unroll
-                        for (int u = 0; u < UB; ++u) cur[u] = nxt[u];
+                    for (int g = 0; g < RB2_NG - 1; ++g) {
+                        if (g < ng) request(b0, g);
+                        asm volatile("cp.async.commit_group;" ::: "memory");
                     }
                 }
+                for (int g = 0; g < ng; ++g, bb += UB) {
+                    if (g + RB2_NG - 1 < ng) request(b0, g + RB2_NG - 1);
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    asm volatile("cp.async.wait_group %0;" ::"n"(RB2_NG - 1) : "memory");
+                    const float2 *stage = rb2_ring + (g % RB2_NG) * (UB * 256) + tid;
+                    float2 cur[UB];
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) cur[u] = stage[u * 256];
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) sample(bb + u, cur[u]);
+                }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                pvp += (size_t)ng * UB * rowF;
             }
             for (; bb < nb; ++bb, pvp += rowF) sample(bb, __ldg(reinterpret_cast<const float2 *>(pvp)));
         }
@@ -725,12 +770,14 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
         sc = adam_scalars(a->adam_out, a->adam_out.step + 1);
         dcll_adam &o = a->adam_out;
         const int grid = ceil_div(g.F, 256);
+        constexpr int ring_bytes = RB2_NG * 8 * 256 * 8;
 #define WG2(KM)                                                                                                           \
-    launch_k(wout_grad_adam2_kernel<KM>, grid, 256, 0, st, L->pv, g_o2, L->B, g.F, L->K, L->wout, L->bout, o.m_w, o.v_w, o.m_b, \
+    DCLL_SMEM_ATTR(wout_grad_adam2_kernel<KM>, ring_bytes);                                                               \
+    launch_k(wout_grad_adam2_kernel<KM>, grid, 256, ring_bytes, st, L->pv, g_o2, L->B, g.F, L->K, L->wout, L->bout, o.m_w, o.v_w, o.m_b, \
                                                      o.v_b, a->grad_wout, a->grad_bout, a->apply_update, sc)
-        if (L->K <= 16) WG2(16);
-        else if (L->K <= 24) WG2(24);
-        else WG2(32);
+        if (L->K <= 16) { WG2(16); }
+        else if (L->K <= 24) { WG2(24); }
+        else { WG2(32); }
 #undef WG2
         DCLL_LAUNCH_OK("wout_grad_adam2_kernel");
     } else if (L->output_layer && !fused_out) {
@@ -763,12 +810,19 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
         dim3 grid(fblk, slices);
         float *nf = nullptr;
         if (packed) {
+            const unsigned grid1 = (unsigned)fblk * slices;                   // 1-D: the slices of a feature block are adjacent
+            constexpr int ring_bytes = RB2_NG * 8 * 256 * 8;
             // 8 rows in flight per thread, next group prefetched: 128 registers, 2 CTAs per SM (4 rows at 3 CTAs per SM was slower)
             // image form of g_u (bf16 {hi,lo} planes in the same buffer) when the row-pair weight-gradient kernel consumes it
 #define RB2(KM)                                                                                                                    \
     do {                                                                                                                           \
-        if (wgrad_tc2_supported(L)) launch_k(readout_bwd2_kernel<KM, 8, 2, true>, grid, 256, 0, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u, hw); \
-        else launch_k(readout_bwd2_kernel<KM, 8, 2, false>, grid, 256, 0, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u, hw);  \
+        if (wgrad_tc2_supported(L)) {                                                                                              \
+            DCLL_SMEM_ATTR((readout_bwd2_kernel<KM, 8, 2, true>), ring_bytes);                                                     \
+            launch_k(readout_bwd2_kernel<KM, 8, 2, true>, grid1, 256, ring_bytes, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u, hw, slices); \
+        } else {                                                                                                                   \
+            DCLL_SMEM_ATTR((readout_bwd2_kernel<KM, 8, 2, false>), ring_bytes);                                                    \
+            launch_k(readout_bwd2_kernel<KM, 8, 2, false>, grid1, 256, ring_bytes, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u, hw, slices); \
+        }                                                                                                                          \
     } while (0)
             if (L->K <= 16) { RB2(16); }
             else if (L->K <= 24) { RB2(24); }

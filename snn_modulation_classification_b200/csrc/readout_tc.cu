@@ -36,22 +36,32 @@ struct RoTcP {
 namespace rotc {
 constexpr int NT = 512, CH = 32;                                 // features per pipeline chunk
 constexpr int CS = 3;                                            // converted (bf16 operand) ring depth
-constexpr int A_F8 = 128 * 16 + 32;                              // pitch of one 8-feature group of pv rows (padded)
-constexpr int A_PART = (CH / 8) * A_F8;                          // one of {hi,lo}
 constexpr int MMA_WARP = 4, NGROUP = 3, GROUP_WARPS = 5, GT = GROUP_WARPS * 32;   // 3 loader/converter groups of 5 warps
 constexpr int ROWS_PER_PASS = GT / 8;                            // a group covers 20 rows x 8 float4 per pass
-template <int NPAD>
+// MROWS = rows a CTA stages per chunk: 128, or 64 when the whole batch is <= 64 rows (training at B = 64: one half-empty row
+// tile).  The MMA stays M = 128 -- rows >= nrow are garbage lanes nobody reads -- but the raw ring shrinks with the rows, which
+// pays for FOUR raw stages per group instead of two: with one chunk ahead per group only ~33 KB per SM were in flight and the
+// kernel sat at 3.5 TB/s (latency x bandwidth of HBM wants ~70 KB per SM); three chunks ahead keep ~100 KB in flight.
+template <int NPAD, int MROWS>
 struct Lay {
+    static constexpr int A_F8 = MROWS * 16 + 32;                 // pitch of one 8-feature group of pv rows (padded)
+    static constexpr int A_PART = (CH / 8) * A_F8;               // one of {hi,lo}
     static constexpr int W_F8 = 2 * NPAD * 16 + 32;              // pitch of one feature group: [{hi,lo}][k][8] (padded)
     static constexpr int OFF_W = 2 * A_PART;
     static constexpr int CONV = OFF_W + (CH / 8) * W_F8;         // converted stage (one per group)
-    static constexpr int U = (128 + NPAD + ROWS_PER_PASS - 1) / ROWS_PER_PASS;   // float4 items per thread and chunk
-    static constexpr int RS = 2;                                 // raw (fp32, cp.async) stages per group
+    static constexpr int U = (MROWS + NPAD + ROWS_PER_PASS - 1) / ROWS_PER_PASS;   // float4 items per thread and chunk
     static constexpr int RAW = U * GT * 16;                      // raw stage: [u][thread] float4, thread-private slots
+    // raw (fp32, cp.async) stages per group: as many as fit beside the converted ring, 2..4
+    static constexpr int RS_FIT = (227 * 1024 - 128 - CS * CONV) / (NGROUP * RAW);
+    static constexpr int RS = RS_FIT >= 4 ? 4 : (RS_FIT >= 3 ? 3 : 2);
     static constexpr int OFF_CONV = NGROUP * RS * RAW;
     static constexpr int OFF_BAR = OFF_CONV + CS * CONV;
     static constexpr int SMEM = OFF_BAR + 128;
     static constexpr int TMEM_COLS = 2 * NPAD <= 32 ? 32 : (2 * NPAD <= 64 ? 64 : 128);
+    // an M = 128 MMA reads 2 KB from the base of every feature group: with MROWS = 64 the tail lies in the following groups /
+    // the W block of the same stage (garbage rows), which must still be inside the CTA's allocation
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+    static_assert(A_PART + (CH / 8 - 1) * A_F8 + 128 * 16 <= CONV, "garbage rows of the last lo group stay inside the stage");
 };
 static_assert(CS == NGROUP, "one operand-ring stage per converter group");
 
@@ -78,12 +88,12 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 }  // namespace rotc
 
-template <int NPAD>
+template <int NPAD, int MROWS>
 __global__ void __launch_bounds__(rotc::NT, 1) readout_tc_kernel(const RoTcP p) {
     using namespace rotc;
     using namespace tc;
-    using G = Lay<NPAD>;
-    constexpr int RS = G::RS;
+    using G = Lay<NPAD, MROWS>;
+    constexpr int RS = G::RS, A_F8 = G::A_F8, A_PART = G::A_PART;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + G::OFF_BAR);
     uint64_t *conv_full = bars, *conv_empty = bars + CS, *acc_full = bars + 2 * CS;
@@ -91,7 +101,7 @@ __global__ void __launch_bounds__(rotc::NT, 1) readout_tc_kernel(const RoTcP p) 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = blockIdx.y * 128;
-    const int nrow = min(128, p.rows - row0);
+    const int nrow = min(MROWS, p.rows - row0);
     // feature range of this CTA, in 32-feature chunks (balanced split)
     const int c0 = (int)(((long long)blockIdx.x * p.n_chunks) / p.n_fs), c1 = (int)(((long long)(blockIdx.x + 1) * p.n_chunks) / p.n_fs);
     if (tid == 0) {
@@ -163,20 +173,19 @@ __global__ void __launch_bounds__(rotc::NT, 1) readout_tc_kernel(const RoTcP p) 
                 if (src[u]) cp_async16(d + u * (GT * 16), in ? src[u] + (size_t)c * CH : src[u], in ? 16u : 0u);
         };
         unsigned char *cv = smem + G::OFF_CONV + g * G::CONV;
-        if (RS > 1 && c0 + g < c1) issue(c0 + g, 0);
-        cp_async_commit();
+        // RS - 1 own chunks ahead, one commit group per chunk (empty groups keep the count uniform at the tail)
+#pragma unroll
+        for (int a = 0; a < RS - 1; ++a) {
+            if (c0 + g + a * NGROUP < c1) issue(c0 + g + a * NGROUP, a);
+            cp_async_commit();
+        }
         int k = 0;
         for (int c = c0 + g; c < c1; c += NGROUP, ++k) {
-            if (RS > 1) {
-                if (c + NGROUP < c1) issue(c + NGROUP, (k + 1) & 1);
-                cp_async_commit();
-                cp_async_wait<1>();
-            } else {
-                issue(c, 0);
-                cp_async_commit();
-                cp_async_wait<0>();
-            }
-            const unsigned char *raw = smem + raw_off + (RS > 1 ? (k & 1) : 0) * G::RAW;
+            // slot (k-1) % RS was converted by this very thread in the previous iteration: refill it with chunk k + RS - 1
+            if (c + (RS - 1) * NGROUP < c1) issue(c + (RS - 1) * NGROUP, (k + RS - 1) % RS);
+            cp_async_commit();
+            cp_async_wait<RS - 1>();
+            const unsigned char *raw = smem + raw_off + (k % RS) * G::RAW;
             if (k >= 1) mbar_wait(conv_empty + g, (k - 1) & 1);
 #pragma unroll
             for (int u = 0; u < G::U; ++u) {
@@ -243,12 +252,16 @@ int readout_tc_blocks(const dcll_conv_layer *L) {
     return best;
 }
 
-template <int NPAD>
-static int launch_rotc(const RoTcP &p, dim3 grid, cudaStream_t st) {
-    DCLL_SMEM_ATTR(readout_tc_kernel<NPAD>, rotc::Lay<NPAD>::SMEM);
-    launch_k(readout_tc_kernel<NPAD>, grid, rotc::NT, rotc::Lay<NPAD>::SMEM, st, p);
+template <int NPAD, int MROWS>
+static int launch_rotc_m(const RoTcP &p, dim3 grid, cudaStream_t st) {
+    DCLL_SMEM_ATTR((readout_tc_kernel<NPAD, MROWS>), (rotc::Lay<NPAD, MROWS>::SMEM));
+    launch_k(readout_tc_kernel<NPAD, MROWS>, grid, rotc::NT, rotc::Lay<NPAD, MROWS>::SMEM, st, p);
     DCLL_LAUNCH_OK("readout_tc_kernel");
     return DCLL_OK;
+}
+template <int NPAD>
+static int launch_rotc(const RoTcP &p, dim3 grid, cudaStream_t st) {
+    return p.rows <= 64 ? launch_rotc_m<NPAD, 64>(p, grid, st) : launch_rotc_m<NPAD, 128>(p, grid, st);
 }
 
 int launch_readout_tc(const dcll_conv_layer *L, float *partial, cudaStream_t st) {

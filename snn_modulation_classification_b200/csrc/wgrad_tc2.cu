@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
     const bool tl_on = p.tl != nullptr;
     unsigned long long *tl = tl_on ? p.tl + (size_t)blockIdx.x * TL_SLOTS : nullptr;
     const long long tl_entry = tl_on ? clock64() : 0;
+    if (tl_on && threadIdx.x == 0) tl[TL_T_ENTRY] = gtimer_ns();
     if (tid == 0) {
         for (int i = 0; i < G::NSTAGE; ++i) mbar_init(full + i, 1), mbar_init(empty + i, 2);
         mbar_init(done, 2);
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
     }
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)G::TMEM_COLS);
-    if (tl_on && tid == 0) tl[TL_DRAIN] = clock64() - tl_drain0, tl[TL_TOTAL] = clock64() - tl_entry;
+    if (tl_on && tid == 0) tl[TL_DRAIN] = clock64() - tl_drain0, tl[TL_TOTAL] = clock64() - tl_entry, tl[TL_T_EXIT] = gtimer_ns();
 }
 
 // Tensor maps of the two operand images (cached per buffer and geometry, tmap.cu).  Dimension ORDER = order of the box in

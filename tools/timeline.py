@@ -61,6 +61,20 @@ def main():
             continue
         print("== %s: %d CTAs, total mean %.1f us  max %.1f us (at %.3f GHz)" % (name, act.sum(), tot[act].mean() / a.ghz / 1e3,
                                                                                tot[act].max() / a.ghz / 1e3, a.ghz))
+        t0, t1 = v[k, act, 13], v[k, act, 14]
+        ghz = (tot[act] / np.maximum(t1 - t0, 1.0)).mean()
+        print("   globaltimer: kernel span (first entry -> last exit) %.1f us; CTA entry skew %.1f us; exit skew %.1f us; SM clock %.3f GHz"
+              % ((t1.max() - t0.min()) / 1e3, (t0.max() - t0.min()) / 1e3, (t1.max() - t1.min()) / 1e3, ghz))
+        idx = np.nonzero(act)[0]
+        dur = (t1 - t0) / 1e3
+        print("   CTA lifetime (us): min %.1f  p10 %.1f  median %.1f  p90 %.1f  max %.1f" % tuple(np.percentile(dur, [0, 10, 50, 90, 100])))
+        if name == "wgrad_tc2":
+            a = dur[idx < 80]
+            bq = dur[idx >= 80]
+            if len(a) and len(bq):
+                print("   role A (CTAs 0..79, default split) mean %.1f max %.1f | role B mean %.1f max %.1f" % (a.mean(), a.max(), bq.mean(), bq.max()))
+        order = np.argsort(dur)
+        print("   slowest CTAs:", ", ".join("%d:%.0f" % (idx[i], dur[i]) for i in order[-6:]), "| fastest:", ", ".join("%d:%.0f" % (idx[i], dur[i]) for i in order[:6]))
         for s in range(1, 13):
             col = v[k, act, s]
             if col.max() == 0:
