@@ -74,6 +74,20 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
     (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);   // the error is picked up by DCLL_LAUNCH_OK
 }
 
+// same, as clusters of two CTAs (CTA pairs for tcgen05 cta_group::2; the grid must be even)
+template <typename... KArgs, typename... Args>
+inline void launch_k_pair(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: set it once per (call site, device), keyed by the
 // current device, so that a process which moves on to a second GPU does not get launch failures there.
 #define DCLL_SMEM_ATTR(kern, bytes)                                                                              \

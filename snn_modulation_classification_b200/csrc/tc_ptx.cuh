@@ -94,6 +94,44 @@ __device__ __forceinline__ uint32_t elect_one() {
     return pred;
 }
 
+// ---- CTA pairs (cta_group::2): two CTAs of one cluster / TPC issue ONE M = 256 MMA.  Each CTA holds its own 128 rows of A and
+// HALF of the N columns of B in its own shared memory (same offsets in both: the instruction carries one descriptor pair), and
+// receives its 128 rows x N columns of D in its own TMEM.  Only the leader (cluster rank 0) issues; barriers are reached in both
+// CTAs with multicast commits, and the peer's TMA loads count their bytes on the LEADER's barrier (address bit 24 cleared).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t *slot, uint32_t cols) {   // one warp of EACH CTA of the pair, same warp index
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t base, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_2cta(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in BOTH CTAs once the pair's previously issued MMAs have completed
+__device__ __forceinline__ void commit_2cta(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's even (leader) CTA
+
 // Shared-memory matrix descriptor, SWIZZLE_NONE: start[0,14) | LBO[16,30) | SBO[32,46) | version[46,48) = 1, all >> 4.
 //   K-major : 8 rows of a core matrix are 16 B apart; SBO = next 8 rows (M/N), LBO = next 16-byte K chunk.
 //   MN-major: 8 K-rows of a core matrix are 16 B apart; SBO = next 8 M/N elements, LBO = next 8 K rows.

@@ -19,6 +19,13 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst_smem, const TmapDesc *m
         "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
+// CTA-pair form: the bytes are counted on the barrier at `bar_smem` in the pair's LEADER CTA (tc::PEER_BIT_MASK), whichever CTA issues
+__device__ __forceinline__ void tma_load_5d_2cta(uint32_t dst_smem, const TmapDesc *map, uint32_t bar_smem, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst_smem),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_smem & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const TmapDesc *map, uint32_t bar_smem, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst_smem),

@@ -76,18 +76,19 @@ struct Wg2GeoT {
     static constexpr int PITCH = PER_CC + 1;                 // staging pitch (odd: conflict-free across ci)
     static constexpr int NW_BLK = COUT * CIN * PER_CC;       // 20 480
     static constexpr int BLK = NW_BLK + COUT;                // + bias sums
-    static_assert(SMEM <= 227 * 1024, "shared memory");
     static_assert(COUT * CIN * PITCH * 4 <= NSTAGE * BUF, "staging fits the tile buffers");
     static_assert(X_PART % 16 == 0 && BUF % 128 == 0 && X_BYTES % 128 == 0, "alignment");
 };
 using Wg2Geo = Wg2GeoT<8, 4>;          // default: 8-row units, four stages (DCLL_WG2_TILE=16: 16-row units, two stages)
 
 size_t wgrad_tc2_partial_floats() { return (size_t)148 * Wg2Geo::BLK; }
+static bool wg2_pair();
 
 template <int TH_, int NSTAGE_>
 __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const __grid_constant__ TmapDesc tmx,
                                                            const __grid_constant__ TmapDesc tmg) {
     using G = Wg2GeoT<TH_, NSTAGE_>;
+    static_assert(G::SMEM <= 227 * 1024, "shared memory");
     using namespace tc;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + G::OFF_BAR);
@@ -270,6 +271,200 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
     if (tl_on && tid == 0) tl[TL_DRAIN] = clock64() - tl_drain0, tl[TL_TOTAL] = clock64() - tl_entry, tl[TL_T_EXIT] = gtimer_ns();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-PAIR form (cta_group::2): the two CTAs of a pair (kernel-row groups g = 0, 1 of the same units) become one cluster and the
+// leader issues ONE M = 256 MMA for both.  Why: the single-CTA kernel is bound by the 128 B/cycle shared-memory path (in-kernel
+// stopwatch: the issuers never wait for tiles; per unit 224 KB of operand reads + 44.5 KB of tile writes = 2 100 cycles, which
+// is the measured rate).  In a pair every CTA keeps only HALF of the N columns of B:
+//     CTA 0 (g = 0): [ G_hi(r)   | G_lo(r)   ]      CTA 1 (g = 1): [ G_hi(r+1) | G_lo(r+1) ]       64 columns each
+// so the g_u tile a CTA stages halves (16 -> 8 KB per unit) and so does the B read of every MMA (4 -> 2 KB, 2 -> 1 KB):
+//     main : X_hi x B,  N = 128 -> D[  0..127] = [ hi.hi(r) | hi.lo(r) | hi.hi(r+1) | hi.lo(r+1) ]
+//     lo   : X_lo x (first half of each CTA's B = G_hi(r) | G_hi(r+1)),  N = 64 -> D[ 32.. 95]
+// The lo product lands on the hi.lo(r) and hi.hi(r+1) columns -- any column of the right (row parity, channel) will do, the
+// drain adds the two 32-column blocks of a parity anyway.  A (the eps1 halo rows of the CTA's own kernel-row group) stays
+// per CTA.  Both producers count their bytes on the LEADER's full barrier; the leader's two issuer warps release the stage in
+// both CTAs with multicast commits.  The bias-gradient MMA (ones x B) now serves both CTAs at once and runs on every row pair.
+template <int TH_, int NSTAGE_>
+struct Wg2PairGeoT : Wg2GeoT<TH_, NSTAGE_> {
+    using Base = Wg2GeoT<TH_, NSTAGE_>;
+    // g_u half tile: [pair][plane 8 = (part, co/8)][k chunk 2][co % 8][8 columns] bf16 of ONE row parity
+    static constexpr int G_GRP = 256, G_PAIR = 8 * G_GRP, G_BYTES = Base::PAIRS * G_PAIR;
+    static constexpr int BUF = Base::X_BYTES + G_BYTES;
+    static constexpr int OFF_ONES = NSTAGE_ * BUF, OFF_BAR = OFF_ONES + 4096, SMEM = OFF_BAR + 128;
+    static_assert(Base::COUT * Base::CIN * Base::PITCH * 4 <= NSTAGE_ * BUF, "staging fits the tile buffers");
+    static_assert(BUF % 128 == 0, "alignment");
+};
+
+template <int TH_, int NSTAGE_>
+__global__ void __launch_bounds__(512, 1) wgrad_tc2p_kernel(const Wg2P p, const __grid_constant__ TmapDesc tmx,
+                                                            const __grid_constant__ TmapDesc tmg) {
+    using G = Wg2PairGeoT<TH_, NSTAGE_>;
+    static_assert(G::SMEM <= 227 * 1024, "shared memory");
+    using namespace tc;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + G::OFF_BAR);
+    uint64_t *full = bars, *empty = bars + G::NSTAGE, *done = bars + 2 * G::NSTAGE;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * G::NSTAGE + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();                    // 0: leader, kernel-row group 0; 1: group 1
+    const bool tl_on = p.tl != nullptr;
+    unsigned long long *tl = tl_on ? p.tl + (size_t)blockIdx.x * TL_SLOTS : nullptr;
+    const long long tl_entry = tl_on ? clock64() : 0;
+    if (tl_on && threadIdx.x == 0) tl[TL_T_ENTRY] = gtimer_ns();
+    if (tid == 0) {
+        // full: ONE arrival (the leader's producer, with the byte count of both CTAs); only the leader's copy is ever waited on
+        for (int i = 0; i < G::NSTAGE; ++i) mbar_init(full + i, 1), mbar_init(empty + i, 2);
+        mbar_init(done, 2);
+        mbar_fence_init();
+    }
+    for (int i = tid; i < 4096 / 4; i += G::NT) reinterpret_cast<uint32_t *>(smem + G::OFF_ONES)[i] = 0x3f803f80u;
+    if (warp == 2) tmem_alloc2(tmem_slot, (uint32_t)G::TMEM_COLS);
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    cluster_sync();                                              // both CTAs' barriers exist before anybody signals across the pair
+    fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_entry();   // nothing global is touched before here (except the stopwatch stamp)
+    if (tl_on && tid == 0) tl[TL_PROLOGUE] = clock64() - tl_entry;
+
+    const int pair_id = blockIdx.x >> 1, grp = (int)rank;
+    const bool roleB = pair_id >= p.nA;
+    const int u_first = roleB ? pair_id - p.nA : pair_id, u_step = roleB ? p.nB : p.nA;
+    const int kw_base = roleB ? 4 : 0;
+    const int tiles = p.tiles_h * p.tiles_w;
+    const int row_off = G::DY * grp;
+
+    if (warp == 4) {
+        // ================= tile producer (one thread per CTA): its own eps1 halo rows and its own row parity of g_u =================
+        //   g_u image dims (64 = co%8 x 8 w, w/8, row parity, (b, part, co/8), row/2), box (64, 2, 1, 8, PAIRS) at parity = rank
+        if (lane == 0) {
+            tma_prefetch_desc(&tmx);
+            tma_prefetch_desc(&tmg);
+            int i = 0;
+            long long tl_wait = 0;
+            for (int u = u_first; u < p.n_units; u += u_step, ++i) {
+                const int sg = i % G::NSTAGE;
+                const uint32_t sX = smem_u32(smem + sg * G::BUF), sG = sX + G::X_BYTES, bar = smem_u32(full + sg);
+                const int b = u / tiles, tile = u - b * tiles;
+                const int th_i = tile / p.tiles_w, tw_i = tile - th_i * p.tiles_w;
+                const int h0 = th_i * G::TH, w0 = tw_i * G::TW;
+                if (i >= G::NSTAGE) TL_TIMED(tl_on, tl_wait, mbar_wait(empty + sg, ((i / G::NSTAGE) - 1) & 1));   // the pair's MMAs have read this stage
+                if (rank == 0) mbar_expect_tx(full + sg, 2 * (G::X_BYTES + G::G_BYTES));
+                tma_load_5d_2cta(sX, &tmx, bar, 0, w0 - p.padW, 0, h0 - p.padH + row_off, 2 * b);
+                tma_load_5d_2cta(sG, &tmg, bar, 0, w0 >> 3, (int)rank, 8 * b, h0 >> 1);
+            }
+            if (tl_on) tl[TL_APROD_EMPTY] = tl_wait;
+        }
+    } else if (warp < 2 && rank == 0) {
+        // ================= MMA issuers (leader only): warp 0 = first two kernel columns of the role, warp 1 = the rest (+ bias) =========
+        constexpr uint32_t IDESC_N128 = idesc_bf16(256, 128, true, false);   // M = 256 over the pair; A MN-major, B K-major
+        constexpr uint32_t IDESC_N64 = idesc_bf16(256, 64, true, false);
+        constexpr uint32_t A_HI = desc_hi(G::X_CP);          // SBO: next 8 rows of M = next (dy, cg) group
+        constexpr uint32_t B_HI = desc_hi(G::G_GRP);         // SBO: next 8 columns of N = next (part, co/8) plane
+        constexpr uint32_t ONES_HI = desc_hi(128);
+        const uint32_t elected = elect_one();
+        const int kw0 = kw_base + (warp == 0 ? 0 : 2), kw1 = roleB ? (warp == 0 ? 6 : 7) : (warp == 0 ? 2 : 4);
+        const bool do_ones = roleB && warp == 1;
+        const uint64_t ones_desc = desc(ONES_HI, desc_lo(smem_u32(smem + G::OFF_ONES), 2048));
+        int i = 0;
+        long long tl_wait = 0;
+        const long long tl_loop0 = tl_on ? clock64() : 0;
+        for (int u = u_first; u < p.n_units; u += u_step, ++i) {
+            const int sg = i % G::NSTAGE;
+            const int tile = u % tiles;
+            const int h0 = (tile / p.tiles_w) * G::TH;
+            const int npair = (min(G::TH, p.Hc - h0) + 1) >> 1;
+            const uint32_t a_base = desc_lo(smem_u32(smem + sg * G::BUF), 128);                      // LBO: next 8 positions (K)
+            const uint32_t b_base = desc_lo(smem_u32(smem + sg * G::BUF + G::X_BYTES), 128);         // LBO: next 8 columns (K)
+            TL_TIMED(tl_on, tl_wait, mbar_wait(full + sg, (i / G::NSTAGE) & 1));
+            fence_after();
+            if (tl_on && i == 0 && warp == 0 && elected) tl[TL_FIRST_MMA] = clock64() - tl_entry;
+            if (elected) {
+                for (int pr = 0; pr < npair; ++pr) {
+                    const uint64_t b = desc(B_HI, b_base + pr * (G::G_PAIR >> 4));
+                    const uint32_t acc = (i == 0 && pr == 0) ? 0u : 1u;
+                    const uint32_t a_row = a_base + ((2 * pr * G::X_RP) >> 4);
+#pragma unroll 2
+                    for (int kw = kw0; kw < kw1; ++kw) {
+                        const uint32_t d = tmem_base + (kw - kw_base) * G::ACC_COLS;
+                        mma_bf16_2cta(d, desc(A_HI, a_row + kw), b, IDESC_N128, acc);
+                        mma_bf16_2cta(d + 32, desc(A_HI, a_row + kw + (G::X_PART >> 4)), b, IDESC_N64, 1);
+                    }
+                    if (do_ones) mma_bf16_2cta(tmem_base + 3 * G::ACC_COLS, ones_desc, b, IDESC_N128, acc);
+                }
+                commit_2cta(empty + sg);
+            }
+            __syncwarp();
+        }
+        if (elected) {
+            commit_2cta(done);
+            if (tl_on) tl[warp == 0 ? TL_ISS_A_FULL : TL_ISS_W_FULL] = tl_wait, tl[warp == 0 ? TL_ISS_LOOP : TL_EPI_LOOP] = clock64() - tl_loop0;
+        }
+        __syncwarp();
+    }
+    // ---- drain.  Lane m = (dy, ci) of accumulator a; its 128 columns are [parity 2][part 2][co 32]:
+    //        parity 0 (even rows): kernel row 4g + dy      -> slot dy + 1
+    //        parity 1 (odd rows) : kernel row 4g + dy - 1  -> slot dy
+    //      (slot s <-> kh = 4g - 1 + s).  Two passes through the idle tile buffers: parity 0 stores slots 1..4, then parity 1 stores
+    //      slot 0 and adds to slots 1..3; each (co, ci, a, slot) is touched by one thread per pass.
+    float *out = p.partial + (size_t)blockIdx.x * G::BLK;
+    mbar_wait(done, 0);
+    fence_after();
+    __syncthreads();
+    const long long tl_drain0 = tl_on ? clock64() : 0;
+    {
+        const int q = warp & 3;                                          // TMEM lane quarter of this warp = dy
+        const int ci = lane;
+        float *stg = reinterpret_cast<float *>(smem);
+        const int nacc = roleB ? 3 : 4;
+        const bool any = u_first < p.n_units;                            // a CTA without units holds no accumulators
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int a = (warp >> 2); a < nacc; a += 4) {
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS + 64 * pass;
+                uint32_t v[32], v2[32];
+                ld32(ta, v);
+                ld32(ta + 32, v2);
+#pragma unroll
+                for (int co = 0; co < 32; ++co) {
+                    const float val = any ? __uint_as_float(v[co]) + __uint_as_float(v2[co]) : 0.f;
+                    float *sp = stg + (co * G::CIN + ci) * G::PITCH + a * G::SLOTS + q + 1 - pass;
+                    *sp = (pass == 0 || q == 0) ? val : *sp + val;
+                }
+            }
+            __syncthreads();
+        }
+        // bias gradient (role B, leader): every lane of the spare accumulator holds the column sums of B over all row pairs
+        if (warp == 0) {
+            float bsum = 0.f;
+            if (roleB && rank == 0 && any) {
+                const uint32_t ta = tmem_base + 3 * G::ACC_COLS;
+#pragma unroll
+                for (int blk = 0; blk < 4; ++blk) {
+                    uint32_t c[32];
+                    ld32(ta + 32 * blk, c);
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        if (k == lane) bsum += __uint_as_float(c[k]);
+                }
+            }
+            out[G::NW_BLK + lane] = bsum;
+        }
+        fence_before();
+        __syncthreads();
+        for (int e = tid; e < G::NW_BLK; e += G::NT) {
+            const int cc = e / G::PER_CC, r = e - cc * G::PER_CC;
+            out[e] = (r < nacc * G::SLOTS) ? stg[cc * G::PITCH + r] : 0.f;
+        }
+    }
+    __syncthreads();
+    cluster_sync();                                              // the peer has drained too: nobody reads this TMEM any more
+    if (warp == 2) tmem_dealloc2(tmem_base, (uint32_t)G::TMEM_COLS);
+    if (tl_on && tid == 0) tl[TL_DRAIN] = clock64() - tl_drain0, tl[TL_TOTAL] = clock64() - tl_entry, tl[TL_T_EXIT] = gtimer_ns();
+}
+
 // Tensor maps of the two operand images (cached per buffer and geometry, tmap.cu).  Dimension ORDER = order of the box in
 // shared memory; the row-parity / row-pair split of the g_u rows needs an even Hc, global strides multiples of 16 bytes.
 static int wg2_tile() {
@@ -281,8 +476,18 @@ static int wg2_tile() {
     return th;
 }
 
+// DCLL_WG2_PAIR=0: the single-CTA kernel (A/B measurements); default: CTA pairs (cta_group::2) with 8-row units
+static bool wg2_pair() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("DCLL_WG2_PAIR");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0 && wg2_tile() == 8;
+}
+
 template <class G>
-static bool wg2_tmaps_g(const dcll_conv_layer *L, TmapDesc *tmx, TmapDesc *tmg) {
+static bool wg2_tmaps_g(const dcll_conv_layer *L, TmapDesc *tmx, TmapDesc *tmg, bool pair = false) {
     Geo g = geo_of(L);
     const uint64_t hw16 = (uint64_t)L->H * L->W * 16, plane = (uint64_t)g.Hc * g.Wc * 2;
     const uint64_t xd[5] = {8, (uint64_t)L->W, 4, (uint64_t)L->H, (uint64_t)2 * L->B};
@@ -291,11 +496,11 @@ static bool wg2_tmaps_g(const dcll_conv_layer *L, TmapDesc *tmx, TmapDesc *tmg) 
     // g_u image [b][part][co/8][position/8][co % 8][8 positions]: 128 bytes per (channel group, 8 positions)
     const uint64_t gd[5] = {64, (uint64_t)g.Wc / 8, 2, (uint64_t)8 * L->B, (uint64_t)g.Hc / 2};
     const uint64_t gs[4] = {128, (uint64_t)g.Wc * 16, plane * 8, (uint64_t)g.Wc * 32};
-    const uint32_t gb[5] = {64, 2, 2, 8, (uint32_t)G::PAIRS};
+    const uint32_t gb[5] = {64, 2, pair ? 1u : 2u, 8, (uint32_t)G::PAIRS};   // pair: one row parity per CTA
     return tmap_bf16(tmx, L->eps1_mma, 5, xd, xs, xb) && tmap_bf16(tmg, L->g_u, 5, gd, gs, gb);
 }
 static bool wg2_tmaps(const dcll_conv_layer *L, TmapDesc *tmx, TmapDesc *tmg) {
-    return wg2_tile() == 16 ? wg2_tmaps_g<Wg2GeoT<16, 2>>(L, tmx, tmg) : wg2_tmaps_g<Wg2GeoT<8, 4>>(L, tmx, tmg);
+    return wg2_tile() == 16 ? wg2_tmaps_g<Wg2GeoT<16, 2>>(L, tmx, tmg) : wg2_tmaps_g<Wg2GeoT<8, 4>>(L, tmx, tmg, wg2_pair());
 }
 
 // The row-pair kernel takes the layer when its operands exist in image form -- the tensor-core forward wrote eps1_mma, and the
@@ -321,7 +526,14 @@ void wgrad_tc2_roles(const dcll_conv_layer *L, int *nA, int *nB) {
     const int n_units = L->B * ceil_div(g.Hc, wg2_tile()) * ceil_div(g.Wc, Wg2Geo::TW);
     // 74 CTA pairs: role A does 4 kernel columns per unit (4 x 4 x 113 cycles), role B 3 + half of the bias MMAs (4 x 3 x 113 + 2 x 64)
     const int pairs = sm_budget() / 2;                       // 74 unless the data-parallel driver holds SMs back for NCCL
-    if (n_units >= 40) *nA = (pairs * 40 + 37) / 74, *nB = pairs - *nA;
+    // (CTA pairs: 4 x 4 x 104 against 4 x 3 x 104 + 4 x 64 cycles plus the tile writes -> 39 : 35; DCLL_WG2_NA overrides, for tuning)
+    static int na_env = -1;
+    if (na_env < 0) {
+        const char *e = getenv("DCLL_WG2_NA");
+        na_env = e ? atoi(e) : 0;
+    }
+    const int na74 = na_env > 0 && na_env < 74 ? na_env : (wg2_pair() ? 39 : 40);
+    if (n_units >= 40) *nA = (pairs * na74 + 37) / 74, *nB = pairs - *nA;
     else *nA = *nB = n_units < pairs / 2 ? n_units : pairs / 2;
 }
 
@@ -350,7 +562,28 @@ static int launch_wgrad_tc2_g(const dcll_conv_layer *L, float *partial, int *nA_
     return DCLL_OK;
 }
 
+static int launch_wgrad_tc2_pair(const dcll_conv_layer *L, float *partial, int *nA_out, int *nB_out, cudaStream_t st) {
+    using G = Wg2PairGeoT<8, 6>;             // six stages fit once the g_u half tile is 8 KB (36 KB per stage)
+    Geo g = geo_of(L);
+    Wg2P p;
+    p.partial = partial;
+    p.B = L->B, p.H = L->H, p.W = L->W, p.padH = L->padH, p.padW = L->padW, p.Hc = g.Hc, p.Wc = g.Wc;
+    p.tiles_h = ceil_div(g.Hc, G::TH), p.tiles_w = ceil_div(g.Wc, G::TW);
+    p.n_units = L->B * p.tiles_h * p.tiles_w;
+    wgrad_tc2_roles(L, &p.nA, &p.nB);
+    *nA_out = p.nA, *nB_out = p.nB;
+    p.dbg = 0;
+    p.tl = timeline_buf(TL_WGRAD2);
+    TmapDesc tmx, tmg;
+    DCLL_REQUIRE(wg2_tmaps(L, &tmx, &tmg), DCLL_ECUDA, "wgrad_tc2: cuTensorMapEncodeTiled failed");
+    DCLL_SMEM_ATTR((wgrad_tc2p_kernel<8, 6>), G::SMEM);
+    launch_k_pair(wgrad_tc2p_kernel<8, 6>, 2 * (p.nA + p.nB), G::NT, G::SMEM, st, p, tmx, tmg);
+    DCLL_LAUNCH_OK("wgrad_tc2p_kernel");
+    return DCLL_OK;
+}
+
 int launch_wgrad_tc2(const dcll_conv_layer *L, float *partial, int *nA_out, int *nB_out, cudaStream_t st) {
+    if (wg2_pair()) return launch_wgrad_tc2_pair(L, partial, nA_out, nB_out, st);
     return wg2_tile() == 16 ? launch_wgrad_tc2_g<Wg2GeoT<16, 2>>(L, partial, nA_out, nB_out, st)
                             : launch_wgrad_tc2_g<Wg2GeoT<8, 4>>(L, partial, nA_out, nB_out, st);
 }

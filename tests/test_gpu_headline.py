@@ -14,7 +14,7 @@ import pytest
 import torch
 
 from oracle import dcll_oracle as O
-from util_build import build_pair, force_state, make_args, rel_err
+from util_build import assert_adam_step_close, build_pair, force_state, make_args, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -60,9 +60,7 @@ def test_bench_config_learn_window_teacher_forced():
             agree = float((clout[0, i].cpu().numpy() == np.asarray(onet.clout[i][-1])).mean()) if len(onet.clout[i]) else 1.0
             assert agree >= 0.95, (t, i, "clout", agree)
             if onet.iters[i] >= burnin:
-                dw = (s.dclllayer.i2h.weight.detach().cpu() - onet.params[i].weight).abs()
-                assert float(dw.max()) <= 0.5 * lr and float(dw.mean()) <= 2e-3 * lr, \
-                    (t, i, float(dw.max()) / lr, float(dw.mean()) / lr)
+                assert_adam_step_close(s.dclllayer.i2h.weight.detach().cpu(), onet.params[i].weight, lr, (t, i))
                 if s.dclllayer.output_layer:
                     dwo = (s.dclllayer.output_.weight.detach().cpu() - onet.params[i].wout).abs()
                     # optimizer2: lr 1e-4 (dcll/pytorch_libdcll.py:636-638)

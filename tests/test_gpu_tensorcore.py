@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle import dcll_oracle as O
-from util_build import build_pair, force_state, make_args, rel_err, state_dict_from_params
+from util_build import assert_adam_step_close, build_pair, force_state, make_args, rel_err, state_dict_from_params
 
 pytestmark = pytest.mark.gpu
 
@@ -96,11 +96,10 @@ def test_tc_training_step_teacher_forced():
             inp = x[t].cuda() if i == 0 else onet.last[i - 1].output.cuda()
             s.train_dcll(inp, y.cuda(), regularize=False)
             if onet.iters[i] >= burnin:
-                dw = (s.dclllayer.i2h.weight.detach().cpu() - onet.params[i].weight).abs()
                 # Looser than the FP32-mode bound: on the first Adam step v_hat = g^2, so the step is
                 # lr*g/(|g|+eps) and elements with |g| ~ eps amplify the ~5e-6 relative error of the split-bf16
                 # gradient.  The mean stays two orders of magnitude below one step.
-                assert float(dw.max()) <= 0.5 * lr and float(dw.mean()) <= 2e-3 * lr, (t, i, float(dw.max()) / lr, float(dw.mean()) / lr)
+                assert_adam_step_close(s.dclllayer.i2h.weight.detach().cpu(), onet.params[i].weight, lr, (t, i))
 
 
 def test_tc_inference_free_running_flip_rate_and_votes():
@@ -224,8 +223,7 @@ def test_tc_layer0_other_padding(pad):
                 fo, st = onet.last[i], s.dclllayer.i2h.state
                 assert torch.equal(st.eps0.cpu(), fo.state.eps0) and torch.equal(st.eps1.cpu(), fo.state.eps1), (t, i)
                 assert rel_err(pvmem, fo.pvmem) <= TC_MEM_TOL, (t, i, rel_err(pvmem, fo.pvmem))
-                dw = (s.dclllayer.i2h.weight.detach().cpu() - onet.params[i].weight).abs()
-                assert float(dw.max()) <= 0.5 * lr and float(dw.mean()) <= 2e-3 * lr, (t, i, float(dw.max()) / lr)
+                assert_adam_step_close(s.dclllayer.i2h.weight.detach().cpu(), onet.params[i].weight, lr, (t, i))
     finally:
         O.BUILTIN_SPECS.pop(name, None)
         N.BUILTIN_SPECS.pop(name, None)

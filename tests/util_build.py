@@ -87,3 +87,15 @@ def rel_err(a, b):
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     scale = float(b.abs().max())
     return float((a - b).abs().max()) / (scale if scale > 0 else 1.0)
+
+
+def assert_adam_step_close(w, w_ref, lr, who):
+    """Weights after ONE Adam step (betas (0, .95): the step is lr * g / (|g| + eps), i.e. +-lr whatever |g| is) against the
+    oracle's.  The split-bf16 gradient is exact to ~1e-5 of the gradient's scale (tools/wgrad_err.py), so an element moves the
+    other way only when gW cancels against weight_decay * w to that level -- a handful of the 50 K weights of a layer per
+    step, whichever kernel computes the sum, and then by at most 2 lr.  Bounds: mean <= 2e-3 lr, at most 1e-4 of the
+    elements beyond 0.5 lr, none beyond 2.1 lr."""
+    dw = (w - w_ref).abs()
+    frac = float((dw > 0.5 * lr).float().mean())
+    assert float(dw.mean()) <= 2e-3 * lr and frac <= 1e-4 and float(dw.max()) <= 2.1 * lr, \
+        (who, float(dw.max()) / lr, float(dw.mean()) / lr, frac)

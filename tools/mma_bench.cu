@@ -17,8 +17,11 @@ struct Cfg {
     int issuers;    // issuing warps (each its own accumulators)
     int commit_every;   // tcgen05.commit + wait every k MMAs (0 = only at the end)
     int swz;            // 0: SWIZZLE_NONE canonical layout, 2: SWIZZLE_128B, 4: 64B, 6: 32B (descriptor bits 61..63), K-major
+    int a_mn;           // 1: A is MN-major (the weight-gradient kernels: M = (kernel row, channel) contiguous), SWIZZLE_NONE
+    int ts;             // 1: A comes from tensor memory (TS mode: tcgen05.mma [d], [a_tmem], b_desc), B from shared memory
 };
 
+template <int TS>
 __global__ void __launch_bounds__(256, 1) bench(Cfg c, long long *out) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar[8];
@@ -42,8 +45,9 @@ __global__ void __launch_bounds__(256, 1) bench(Cfg c, long long *out) {
         const uint32_t swz = (uint32_t)c.swz << 29;
         const uint32_t sbo_sw = c.swz == 2 ? 1024 : (c.swz == 4 ? 512 : 256);
         const uint32_t A_HI = c.swz ? (desc_hi(sbo_sw) | swz) : desc_hi(352), B_HI = c.swz ? (desc_hi(sbo_sw) | swz) : desc_hi(128);
-        const uint32_t i64 = idesc_bf16(128, 64, false, false), i32 = idesc_bf16(128, 32, false, false);
-        const uint32_t iN = idesc_bf16(128, c.nsize, false, false);
+        const uint32_t i64 = idesc_bf16(128, 64, c.a_mn != 0, false), i32 = idesc_bf16(128, 32, c.a_mn != 0, false);
+        const uint32_t iN = idesc_bf16(128, c.nsize, c.a_mn != 0, false);
+        const uint32_t a_base_mn = desc_lo(smem_u32(smem), 128);      // MN-major: LBO = next 8 K rows, SBO (352) = next 8 M elements
         __syncwarp();
         t0 = clock64();
         if (elected) {
@@ -61,10 +65,19 @@ __global__ void __launch_bounds__(256, 1) bench(Cfg c, long long *out) {
                     const uint32_t kk = k + u;
                     const uint32_t d = dbase + (((kk >> 1) & acc_mask) * acc_cols);
                     const uint32_t sh = c.swz ? ((kk >> 1) & sh_mask & 3) * 2 : ((kk >> 1) & sh_mask);
-                    const uint64_t a = desc(A_HI, a_base + sh + ((u & 1) ? lo_off : 0));
+                    const uint64_t a = desc(A_HI, (c.a_mn ? a_base_mn : a_base) + sh + ((u & 1) ? lo_off : 0));
                     const uint64_t b = desc(B_HI, b_base + (c.swz ? (sh & 3) * 2 : (sh & 7) * 256));
                     const uint32_t id = c.pair ? ((u & 1) ? i32 : i64) : iN;
-                    mma_bf16(d, a, b, id, 1);
+                    if (TS) {
+                        // A = 128 lanes x 8 columns (16 bf16) of tensor memory, columns 448.. (never written: timing only)
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d),
+                            "r"(tmem + 448 + 8 * (kk & 7)), "l"(b), "r"(id), "r"(1u)
+                            : "memory");
+                    } else {
+                        mma_bf16(d, a, b, id, 1);
+                    }
                 }
                 since += 8;
                 if (since >= ce) {
@@ -114,8 +127,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) bench2(Cfg c
         const uint32_t elected = elect_one();
         const uint32_t a_base = desc_lo(smem_u32(smem), 7744), b_base = desc_lo(smem_u32(smem + 128 * 1024), 1024);
         constexpr uint32_t A_HI = desc_hi(352), B_HI = desc_hi(128);
-        const uint32_t i64 = idesc_bf16(256, 64, false, false), i32 = idesc_bf16(256, 32, false, false);
-        const uint32_t iN = idesc_bf16(256, c.nsize, false, false);
+        const uint32_t i64 = idesc_bf16(256, 64, c.a_mn != 0, false), i32 = idesc_bf16(256, 32, c.a_mn != 0, false);
+        const uint32_t iN = idesc_bf16(256, c.nsize, c.a_mn != 0, false);
+        const uint32_t a_base_mn = desc_lo(smem_u32(smem), 128);
         __syncwarp();
         t0 = clock64();
         if (elected && rank == 0) {
@@ -127,7 +141,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) bench2(Cfg c
                 for (int u = 0; u < 8; ++u) {
                     const uint32_t kk = k + u;
                     const uint32_t sh = (kk >> 1) & sh_mask;
-                    const uint64_t a = desc(A_HI, a_base + sh + ((u & 1) ? lo_off : 0));
+                    const uint64_t a = desc(A_HI, (c.a_mn ? a_base_mn : a_base) + sh + ((u & 1) ? lo_off : 0));
                     const uint64_t b = desc(B_HI, b_base + (sh & 7) * 256);
                     const uint32_t id = c.pair ? ((u & 1) ? i32 : i64) : iN;
                     asm volatile(
@@ -155,7 +169,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) bench2(Cfg c
 int main() {
     long long *out;
     cudaMallocManaged(&out, 64);
-    cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(bench<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(bench<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const Cfg cfgs[] = {
         // n, n_acc, pair, nsize, shift, issuers, commit_every, swz
         {4096, 1, 0, 64, 1, 1, 0, 0}, {4096, 1, 0, 32, 1, 1, 0, 0}, {4096, 1, 0, 128, 1, 1, 0, 0}, {4096, 1, 0, 256, 1, 1, 0, 0},
@@ -168,7 +183,7 @@ int main() {
     printf("%6s %5s %4s %5s %5s %7s %6s %3s | cycles/MMA (issuer 0)\n", "n", "n_acc", "pair", "N", "shift", "issuers", "commit", "swz");
     for (const Cfg &c : cfgs) {
         for (int rep = 0; rep < 2; ++rep) {
-            bench<<<148, 256, 200 * 1024>>>(c, out);
+            bench<0><<<148, 256, 200 * 1024>>>(c, out);
             if (cudaDeviceSynchronize() != cudaSuccess) {
                 printf("CUDA error: %s\n", cudaGetErrorString(cudaGetLastError()));
                 return 1;
@@ -177,9 +192,36 @@ int main() {
         printf("%6d %5d %4d %5d %5d %7d %6d %3d | %.1f\n", c.n, c.n_acc, c.pair, c.nsize, c.shift, c.issuers, c.commit_every, c.swz,
                (double)out[0] / c.n);
     }
+    printf("\nA MN-major (weight gradient: M = (kernel row, channel) contiguous, K = positions), SWIZZLE_NONE\n");
+    const Cfg cmn[] = {{4096, 1, 0, 32, 1, 1, 0, 0, 1, 0}, {4096, 1, 0, 64, 1, 1, 0, 0, 1, 0}, {4096, 1, 0, 128, 1, 1, 0, 0, 1, 0},
+                       {4096, 1, 0, 256, 1, 1, 0, 0, 1, 0}, {4096, 1, 0, 64, 1, 2, 0, 0, 1, 0}, {4096, 1, 0, 128, 1, 2, 0, 0, 1, 0}};
+    for (const Cfg &c : cmn) {
+        for (int rep = 0; rep < 2; ++rep) {
+            bench<0><<<148, 256, 200 * 1024>>>(c, out);
+            if (cudaDeviceSynchronize() != cudaSuccess) {
+                printf("CUDA error: %s\n", cudaGetErrorString(cudaGetLastError()));
+                return 1;
+            }
+        }
+        printf("A MN-major N=%3d issuers=%d | %.1f cycles per MMA (issuer 0)\n", c.nsize, c.issuers, (double)out[0] / c.n);
+    }
+    printf("\nTS mode (A in tensor memory, B = N x 16 bf16 from shared memory)\n");
+    const Cfg cts[] = {{4096, 1, 0, 32, 1, 1, 0, 0, 0, 1}, {4096, 1, 0, 64, 1, 1, 0, 0, 0, 1}, {4096, 1, 0, 128, 1, 1, 0, 0, 0, 1},
+                       {4096, 1, 0, 256, 1, 1, 0, 0, 0, 1}};
+    for (const Cfg &c : cts) {
+        for (int rep = 0; rep < 2; ++rep) {
+            bench<1><<<148, 256, 200 * 1024>>>(c, out);
+            if (cudaDeviceSynchronize() != cudaSuccess) {
+                printf("CUDA error: %s\n", cudaGetErrorString(cudaGetLastError()));
+                return 1;
+            }
+        }
+        printf("TS N=%3d | %.1f cycles per MMA\n", c.nsize, (double)out[0] / c.n);
+    }
     cudaFuncSetAttribute(bench2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     printf("\nCTA pairs (cta_group::2, M = 256 = 128 rows per CTA, half of B per CTA), 148 CTAs = 74 pairs\n");
-    const Cfg c2[] = {{4096, 1, 0, 64, 1, 1, 0, 0}, {4096, 1, 0, 32, 1, 1, 0, 0}, {4096, 1, 0, 128, 1, 1, 0, 0}, {4096, 1, 1, 64, 1, 1, 0, 0}};
+    const Cfg c2[] = {{4096, 1, 0, 64, 1, 1, 0, 0}, {4096, 1, 0, 32, 1, 1, 0, 0}, {4096, 1, 0, 128, 1, 1, 0, 0}, {4096, 1, 1, 64, 1, 1, 0, 0},
+                      {4096, 1, 0, 256, 1, 1, 0, 0}, {4096, 1, 0, 64, 1, 1, 0, 0, 1, 0}, {4096, 1, 0, 128, 1, 1, 0, 0, 1, 0}};
     for (const Cfg &c : c2) {
         for (int rep = 0; rep < 2; ++rep) {
             bench2<<<148, 256, 200 * 1024>>>(c, out);
@@ -188,7 +230,7 @@ int main() {
                 return 1;
             }
         }
-        printf("pair=%d N=%3d | %.1f cycles per M=256 MMA\n", c.pair, c.nsize, (double)out[0] / c.n);
+        printf("pair=%d N=%3d A %s-major | %.1f cycles per M=256 MMA\n", c.pair, c.nsize, c.a_mn ? "MN" : "K", (double)out[0] / c.n);
     }
     return 0;
 }

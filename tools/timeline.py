@@ -69,10 +69,10 @@ def main():
         dur = (t1 - t0) / 1e3
         print("   CTA lifetime (us): min %.1f  p10 %.1f  median %.1f  p90 %.1f  max %.1f" % tuple(np.percentile(dur, [0, 10, 50, 90, 100])))
         if name == "wgrad_tc2":
-            a = dur[idx < 80]
-            bq = dur[idx >= 80]
-            if len(a) and len(bq):
-                print("   role A (CTAs 0..79, default split) mean %.1f max %.1f | role B mean %.1f max %.1f" % (a.mean(), a.max(), bq.mean(), bq.max()))
+            ra = dur[idx < 78]
+            rb = dur[idx >= 78]
+            if len(ra) and len(rb):
+                print("   role A (CTAs 0..77, 39 : 35 split) mean %.1f max %.1f | role B mean %.1f max %.1f" % (ra.mean(), ra.max(), rb.mean(), rb.max()))
         order = np.argsort(dur)
         print("   slowest CTAs:", ", ".join("%d:%.0f" % (idx[i], dur[i]) for i in order[-6:]), "| fastest:", ", ".join("%d:%.0f" % (idx[i], dur[i]) for i in order[:6]))
         for s in range(1, 13):
