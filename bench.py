@@ -697,7 +697,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
     ap.add_argument("--no-extras", action="store_true", dest="no_extras",
                     help="skip the fp32_mode and other_workloads legs (quick profiling runs)")
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3"],
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "f16x2"],
                     help="fp32: FP32-exact parity mode on the FMA pipe; bf16x3: tcgen05 split-bf16 (headline mode)")
     ap.add_argument("--burnin", type=int, default=None, help="override the workload's burn-in (profiling runs)")
     a = ap.parse_args()

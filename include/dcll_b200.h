@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DCLL_ABI_VERSION 10
+#define DCLL_ABI_VERSION 11
 
 enum { DCLL_OK = 0, DCLL_EINVAL = -1, DCLL_ECUDA = -2, DCLL_EUNSUPPORTED = -3 };
 
@@ -37,8 +37,14 @@ enum { DCLL_X_DENSE = 0, DCLL_X_CELLS = 1 };
 /* loss classes train.py:173 can select; gradient of the mean-reduced loss. */
 enum { DCLL_LOSS_SMOOTHL1 = 0, DCLL_LOSS_MSE = 1, DCLL_LOSS_L1 = 2,
        DCLL_LOSS_EXTERNAL = 3 /* any other loss class: the host supplies dL/dpvoutput (and dL/doutput) */ };
-/* conv arithmetic: FP32 CUDA-core FMA (parity mode) or split-bf16 x3 on tcgen05 tensor cores. */
-enum { DCLL_PREC_FP32 = 0, DCLL_PREC_BF16X3 = 1 };
+/* conv arithmetic: FP32 CUDA-core FMA (parity mode); split-bf16 x3 on tcgen05 tensor cores (both operands bf16 hi + lo, three
+ * products); or F16X2: the same kernels with the TRACE operand as one fp16 value (eps1 lies in [0,1]: relative rounding 2^-12)
+ * against split-fp16 weights / local gradients -- two products, no lo pass over the traces.  kind::f16 wants both operands in
+ * one format, and fp16 has 5 exponent bits, so every operand image carries a power-of-two scale (exact): a_exp for the traces
+ * (static bound from the time constants), g_exp for the local gradient (static bound from the frozen read-out and the batch
+ * size), and a per-layer weight exponent the library tracks on the device (w_exp).  Needs w_exp and 32 input channels; layers
+ * with one input channel keep the split-bf16 form (they are not bound by the tensor pipe). */
+enum { DCLL_PREC_FP32 = 0, DCLL_PREC_BF16X3 = 1, DCLL_PREC_F16X2 = 2 };
 
 /* torch.optim.Adam hyper-parameters + state of one parameter group
  * (dcll/pytorch_libdcll.py:634-638; train.py:164-168). */
@@ -101,6 +107,13 @@ typedef struct dcll_conv_layer {
                                         pool argmax                                          */
     void *workspace;                 /* device scratch, dcll_conv_workspace_bytes()          */
     size_t workspace_bytes;
+    /* DCLL_PREC_F16X2 only (ignored otherwise) */
+    int32_t a_exp;                   /* eps1_mma holds fp16(eps1 * 2^a_exp): 2^a_exp * max eps1 <= 2^15, where
+                                        max eps1 = tau_s/(1-alphas) * tau_m/(1-alpha) for spike input     */
+    int32_t g_exp;                   /* g_u image holds fp16 {hi,lo} of g_u * 2^g_exp (saturating)         */
+    int32_t *w_exp;                  /* device int32[4], zero-initialised by the caller, owned by the library afterwards:
+                                        {exponent of the current weight_mma image, exponent of the next one,
+                                         block ticket, running max |w| bits}; weight_mma holds fp16 {hi,lo} of w * 2^w_exp[0] */
 } dcll_conv_layer;
 
 typedef struct dcll_train_args {

@@ -8,13 +8,13 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdcll_b200.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 OK, EINVAL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3
 COEF_SCALAR, COEF_CHANNEL, COEF_ELEMENT = 0, 1, 2
 X_DENSE, X_CELLS = 0, 1
 LOSS_SMOOTHL1, LOSS_MSE, LOSS_L1, LOSS_EXTERNAL = 0, 1, 2, 3
-PREC_FP32, PREC_BF16X3 = 0, 1
+PREC_FP32, PREC_BF16X3, PREC_F16X2 = 0, 1, 2
 
 _fp = C.c_void_p  # device pointers travel as integers
 
@@ -36,7 +36,8 @@ class ConvLayer(C.Structure):
                 ("wout", _fp), ("bout", _fp),
                 ("eps0", _fp * 2), ("eps1", _fp * 2), ("eps1_mma", _fp), ("arp", _fp),
                 ("spikes", _fp), ("pv", _fp), ("pvmem", _fp), ("pool_idx", _fp), ("pvoutput", _fp),
-                ("output", _fp), ("g_u", _fp), ("workspace", _fp), ("workspace_bytes", C.c_size_t)]
+                ("output", _fp), ("g_u", _fp), ("workspace", _fp), ("workspace_bytes", C.c_size_t),
+                ("a_exp", C.c_int32), ("g_exp", C.c_int32), ("w_exp", _fp)]
 
 
 class TrainArgs(C.Structure):

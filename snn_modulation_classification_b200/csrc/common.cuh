@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/dcll_b200.h"
 
@@ -135,6 +136,29 @@ void set_reserved_sms(int n);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// precision modes: does the layer run on the tensor-core kernels at all / with fp16 traces (DCLL_PREC_F16X2, 32-channel input)
+static inline bool prec_tc(const dcll_conv_layer *L) { return L->precision == DCLL_PREC_BF16X3 || L->precision == DCLL_PREC_F16X2; }
+static inline bool prec_f16(const dcll_conv_layer *L) { return L->precision == DCLL_PREC_F16X2 && L->Cin == 32 && L->w_exp; }
+#ifdef __CUDACC__
+__host__ __device__ __forceinline__ float pow2i(int e) {             // 2^e as a float, e in [-126, 127]
+    const unsigned bits = (unsigned)(e + 127) << 23;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(bits);
+#else
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+#endif
+}
+// exponent k of an fp16 weight image: max |w| * 2^k in [2^7, 2^8) -- 2^8 of headroom below the fp16 maximum
+__device__ __forceinline__ int weight_exp_for(float maxabs) {
+    if (!(maxabs > 0.f)) return 0;
+    const int e = (int)((__float_as_uint(maxabs) >> 23) & 0xff) - 127;     // floor(log2(maxabs)) for normal floats
+    const int k = 7 - e;
+    return k < -100 ? -100 : (k > 100 ? 100 : k);
+}
+#endif
 
 // Derived geometry of a layer.
 struct Geo {

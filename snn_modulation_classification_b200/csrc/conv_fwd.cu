@@ -418,7 +418,7 @@ int sync_kernel_weights(const dcll_conv_layer *L, cudaStream_t st) {
 int launch_conv_fwd(const dcll_conv_layer *L, const void *x, cudaStream_t st, const dcll_conv_layer *next, bool trace_done,
                     bool write_spikes) {
     // "bf16x3" = tensor cores wherever a shape is instantiated; the rest stays on the FMA pipe
-    if (L->precision == DCLL_PREC_BF16X3 && tc_supported(L)) return launch_conv_fwd_tc(L, x, st, next, trace_done, write_spikes);
+    if (prec_tc(L) && tc_supported(L)) return launch_conv_fwd_tc(L, x, st, next, trace_done, write_spikes);
     DCLL_REQUIRE(!next && !trace_done, DCLL_EINVAL, "fused next-layer trace needs the tensor-core path");
     Geo g = geo_of(L);
     FwdP p;

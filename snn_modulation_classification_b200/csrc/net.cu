@@ -111,9 +111,9 @@ static int check_layer(const dcll_conv_layer *L, const char *who) {
                  "%s: pooling (%d,%d): each axis must be 1 or 2", who, L->poolH, L->poolW);
     DCLL_REQUIRE(g.Hp > 0 && g.Wp > 0, DCLL_EINVAL, "%s: pooled output is empty (%dx%d conv output, pooling (%d,%d))", who,
                  g.Hc, g.Wc, L->poolH, L->poolW);
-    DCLL_REQUIRE(L->precision == DCLL_PREC_FP32 || L->precision == DCLL_PREC_BF16X3, DCLL_EINVAL, "%s: unknown precision mode %d",
+    DCLL_REQUIRE(L->precision == DCLL_PREC_FP32 || prec_tc(L), DCLL_EINVAL, "%s: unknown precision mode %d",
                  who, L->precision);
-    DCLL_REQUIRE(L->precision != DCLL_PREC_BF16X3 || !tc_supported(L) || (L->weight_mma && L->eps1_mma), DCLL_EINVAL,
+    DCLL_REQUIRE(!prec_tc(L) || !tc_supported(L) || (L->weight_mma && L->eps1_mma), DCLL_EINVAL,
                  "%s: the bf16x3 tensor-core conv needs weight_mma and eps1_mma", who);
     DCLL_REQUIRE(L->alpha && L->alphas && L->tau_m && L->tau_s && L->weight && L->weight_t && L->bias && L->wo && L->bo,
                  DCLL_EINVAL, "%s: null parameter pointer", who);

@@ -14,6 +14,7 @@
 // over all samples.  Partials are reduced in a fixed order (no float atomics): results are
 // deterministic run to run.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -316,6 +317,14 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
 // them with one tensor-map box per unit (full 128-byte lines; the first, plain-NCHW form of the image made every 16-byte piece
 // its own half-used L2 sector).  The block -> feature map follows the image: a CTA = 8 channels x 64 consecutive positions.
 // q32 = 32-bit address of the bf16 pair in the hi part of the sample; the lo part starts F/2 words later.
+// F16X2 (g_scale != 0): fp16 {hi,lo} of g_u * g_scale, saturated to the fp16 range (the scale comes from a bound on |g_u|)
+__device__ __forceinline__ void store_gu_img_f16(uint32_t *q32, int half_f, float2 v, float g_scale) {
+    const float x = fminf(fmaxf(__fmul_rn(v.x, g_scale), -65504.f), 65504.f), y = fminf(fmaxf(__fmul_rn(v.y, g_scale), -65504.f), 65504.f);
+    const __half h0 = __float2half_rn(x), h1 = __float2half_rn(y);
+    const __half l0 = __float2half_rn(x - __half2float(h0)), l1 = __float2half_rn(y - __half2float(h1));
+    q32[0] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    q32[half_f] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+}
 __device__ __forceinline__ void store_gu_img(uint32_t *q32, int half_f, float2 v) {
     const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
     const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
@@ -336,7 +345,7 @@ __device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
 template <int KMAX, int UB, int MINB, bool IMG>
 __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__restrict__ pv, const float *__restrict__ wo,
                                                               const float *__restrict__ g_o, int B, int F, int K, int b_per_blk,
-                                                              float *__restrict__ g_u, int hw, int slices) {
+                                                              float *__restrict__ g_u, int hw, int slices, float g_scale) {
     extern __shared__ __align__(16) float2 rb2_ring[];                 // [RB2_NG][UB][256]
     const int fblk = blockIdx.x / slices, slice = blockIdx.x - fblk * slices;
     pdl_entry();
@@ -431,7 +440,8 @@ __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__
 #pragma unroll
                     for (int u = 0; u < UB; ++u, q += rowF) {
                         const float2 v = sample(bb + u, cur[u]);
-                        if (IMG) store_gu_img(reinterpret_cast<uint32_t *>(q - f) + img_word, F >> 1, v);
+                        if (IMG && g_scale != 0.f) store_gu_img_f16(reinterpret_cast<uint32_t *>(q - f) + img_word, F >> 1, v, g_scale);
+                        else if (IMG) store_gu_img(reinterpret_cast<uint32_t *>(q - f) + img_word, F >> 1, v);
                         else *reinterpret_cast<float2 *>(q) = v;
                     }
                     gup = q;
@@ -441,7 +451,8 @@ __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__
             }
             for (; bb < nb; ++bb, pvp += rowF, gup += rowF) {
                 const float2 v = sample(bb, __ldg(reinterpret_cast<const float2 *>(pvp)));
-                if (IMG) store_gu_img(reinterpret_cast<uint32_t *>(gup - f) + img_word, F >> 1, v);
+                if (IMG && g_scale != 0.f) store_gu_img_f16(reinterpret_cast<uint32_t *>(gup - f) + img_word, F >> 1, v, g_scale);
+                else if (IMG) store_gu_img(reinterpret_cast<uint32_t *>(gup - f) + img_word, F >> 1, v);
                 else *reinterpret_cast<float2 *>(gup) = v;
             }
         }
@@ -812,16 +823,17 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
         if (packed) {
             const unsigned grid1 = (unsigned)fblk * slices;                   // 1-D: the slices of a feature block are adjacent
             constexpr int ring_bytes = RB2_NG * 8 * 256 * 8;
+            const float g_scale = prec_f16(L) ? pow2i(L->g_exp) : 0.f;   // F16X2: the image is fp16 {hi,lo} of g_u * 2^g_exp
             // 8 rows in flight per thread, next group prefetched: 128 registers, 2 CTAs per SM (4 rows at 3 CTAs per SM was slower)
             // image form of g_u (bf16 {hi,lo} planes in the same buffer) when the row-pair weight-gradient kernel consumes it
 #define RB2(KM)                                                                                                                    \
     do {                                                                                                                           \
         if (wgrad_tc2_supported(L)) {                                                                                              \
             DCLL_SMEM_ATTR((readout_bwd2_kernel<KM, 8, 2, true>), ring_bytes);                                                     \
-            launch_k(readout_bwd2_kernel<KM, 8, 2, true>, grid1, 256, ring_bytes, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u, hw, slices); \
+            launch_k(readout_bwd2_kernel<KM, 8, 2, true>, grid1, 256, ring_bytes, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u, hw, slices, g_scale); \
         } else {                                                                                                                   \
             DCLL_SMEM_ATTR((readout_bwd2_kernel<KM, 8, 2, false>), ring_bytes);                                                    \
-            launch_k(readout_bwd2_kernel<KM, 8, 2, false>, grid1, 256, ring_bytes, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u, hw, slices); \
+            launch_k(readout_bwd2_kernel<KM, 8, 2, false>, grid1, 256, ring_bytes, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u, hw, slices, 0.f); \
         }                                                                                                                          \
     } while (0)
             if (L->K <= 16) { RB2(16); }

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(rotc::NT, 1) readout_tc_kernel(const RoTcP p) 
 
 bool readout_tc_supported(const dcll_conv_layer *L) {
     Geo g = geo_of(L);
-    return L->precision == DCLL_PREC_BF16X3 && g.Ktot <= 64 && (g.F % 4) == 0 &&
+    return prec_tc(L) && g.Ktot <= 64 && (g.F % 4) == 0 &&
            (((uintptr_t)L->pv | (uintptr_t)L->wo | (uintptr_t)L->wout) % 16) == 0;
 }
 

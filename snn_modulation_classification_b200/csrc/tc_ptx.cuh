@@ -145,5 +145,12 @@ __device__ __forceinline__ constexpr uint32_t idesc_bf16(int m, int n, bool a_mn
            ((uint32_t)(m >> 4) << 24);
 }
 
+// same for fp16 x fp16 -> f32 (a/b_format 0; kind::f16 wants both operands in ONE format: fp16 A against bf16 B raises an
+// illegal-instruction fault on B200)
+__device__ __forceinline__ constexpr uint32_t idesc_f16a(int m, int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(m >> 4) << 24);
+}
+
 }  // namespace tc
 }  // namespace dcll

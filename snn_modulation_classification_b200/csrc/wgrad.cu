@@ -13,6 +13,7 @@
 // Partials are summed in a fixed order by reduce_adam_kernel, which also applies Adam and refreshes the
 // [Cin,KH*KW,CoutPad] weight copy the forward kernel consumes -- deterministic, no float atomics.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -239,11 +240,16 @@ __global__ void __launch_bounds__(256) reduce_adam_rp_kernel(const float *__rest
                                                              float *__restrict__ m_w, float *__restrict__ v_w,
                                                              float *__restrict__ m_b, float *__restrict__ v_b,
                                                              float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
-                                                             AdamScalars sc, __nv_bfloat16 *__restrict__ w_mma, int Cin, int KHKW, int KW) {
+                                                             AdamScalars sc, __nv_bfloat16 *__restrict__ w_mma, int Cin, int KHKW, int KW,
+                                                             int *__restrict__ w_exp) {
     pdl_entry();
     __shared__ float red[4][64];
     const int e = threadIdx.x & 63, sl = threadIdx.x >> 6;
     const int i = blockIdx.x * 64 + e;
+    // F16X2: the image written below is fp16 {hi,lo} of w * 2^k, k = w_exp[1] -- read by every block before any block can have
+    // finished (the last block to finish is the only writer of the slots, see the end of the kernel)
+    const int kexp = w_exp ? *reinterpret_cast<volatile int *>(w_exp + 1) : 0;
+    float wabs = 0.f;
     float g = 0.f;
     if (i < nW) {
         const int cc = i / KHKW, tap = i - cc * KHKW;            // cc = co * Cin + ci
@@ -261,7 +267,7 @@ __global__ void __launch_bounds__(256) reduce_adam_rp_kernel(const float *__rest
     }
     red[sl][e] = g;
     __syncthreads();
-    if (sl != 0 || i >= n_tot) return;
+    if (sl == 0 && i < n_tot) {
     g = ((red[0][e] + red[1][e]) + red[2][e]) + red[3][e];
     if (i < nW) {
         if (grad_w) grad_w[i] = g;
@@ -269,15 +275,23 @@ __global__ void __launch_bounds__(256) reduce_adam_rp_kernel(const float *__rest
             float wv = w[i], m = m_w[i], v = v_w[i];
             adam_elem(wv, g, m, v, sc);
             w[i] = wv, m_w[i] = m, v_w[i] = v;
+            wabs = fabsf(wv);
             int co = i / CinKK, r = i - co * CinKK;
             wt[(size_t)r * CoutPad + co] = wv;
             if (w_mma) {
                 const int ci = r / KHKW, tap = r - ci * KHKW;
-                __nv_bfloat16 hi = __float2bfloat16_rn(wv);
-                __nv_bfloat16 lo = __float2bfloat16_rn(wv - __bfloat162float(hi));
                 size_t o = (size_t)tap * (2 * Cin * Cout) + ((size_t)(ci >> 3) * 2 * Cout + co) * 8 + (ci & 7);
-                w_mma[o] = hi;
-                w_mma[o + (size_t)Cout * 8] = lo;
+                if (w_exp) {
+                    const float vs = __fmul_rn(wv, pow2i(kexp));
+                    const __half hi = __float2half_rn(vs);
+                    reinterpret_cast<__half *>(w_mma)[o] = hi;
+                    reinterpret_cast<__half *>(w_mma)[o + (size_t)Cout * 8] = __float2half_rn(vs - __half2float(hi));
+                } else {
+                    __nv_bfloat16 hi = __float2bfloat16_rn(wv);
+                    __nv_bfloat16 lo = __float2bfloat16_rn(wv - __bfloat162float(hi));
+                    w_mma[o] = hi;
+                    w_mma[o + (size_t)Cout * 8] = lo;
+                }
             }
         }
     } else {
@@ -287,6 +301,29 @@ __global__ void __launch_bounds__(256) reduce_adam_rp_kernel(const float *__rest
             float wv = bias[co], m = m_b[co], v = v_b[co];
             adam_elem(wv, g, m, v, sc);
             bias[co] = wv, m_b[co] = m, v_b[co] = v;
+        }
+    }
+    }
+    // F16X2: running max |w| of this step (bit pattern of a non-negative float orders like the float) and, in the LAST block to
+    // finish, the hand-over: slot 0 = the exponent this launch wrote the image with (what the next convolution must undo),
+    // slot 1 = the exponent for the next image from this step's maximum.  Deterministic: the maximum does not depend on the order.
+    if (w_exp && apply) {
+        if (sl == 0) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wabs = fmaxf(wabs, __shfl_xor_sync(0xffffffffu, wabs, o));
+            if ((threadIdx.x & 31) == 0 && wabs > 0.f) atomicMax(reinterpret_cast<unsigned *>(w_exp + 3), __float_as_uint(wabs));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const int ticket = atomicAdd(w_exp + 2, 1);
+            if (ticket == (int)gridDim.x - 1) {
+                __threadfence();
+                const unsigned mb = atomicExch(reinterpret_cast<unsigned *>(w_exp + 3), 0u);
+                w_exp[0] = kexp;
+                w_exp[1] = weight_exp_for(__uint_as_float(mb));
+                w_exp[2] = 0;
+            }
         }
     }
 }
@@ -351,10 +388,10 @@ int launch_bucket_adam(const dcll_conv_layer *L, dcll_train_args *a, const float
         ProfScope ps(KC_ADAM, 0, st);
         launch_k(reduce_adam_kernel, ceil_div(n_tot, 64), 256, 0, st, bucket, 1, n_tot, g.nW, L->Cout, g.CoutPad, L->Cin * L->KH * L->KW,
                  L->weight, L->weight_t, L->bias, o.m_w, o.v_w, o.m_b, o.v_b, (float *)nullptr, (float *)nullptr, 1, sc,
-                 L->quantized ? nullptr : reinterpret_cast<__nv_bfloat16 *>(L->weight_mma), L->Cin, L->KH * L->KW, L->KW);
+                 (L->quantized || prec_f16(L)) ? nullptr : reinterpret_cast<__nv_bfloat16 *>(L->weight_mma), L->Cin, L->KH * L->KW, L->KW);
         DCLL_LAUNCH_OK("reduce_adam_kernel");
         a->adam_i2h.step += 1;
-        if (L->quantized) {
+        if (L->quantized || prec_f16(L)) {                   // (F16X2: the fp16 image and its exponent come from the synchronisation path)
             int rc = sync_kernel_weights(L, st);
             if (rc != DCLL_OK) return rc;
         }
@@ -395,11 +432,13 @@ int launch_wgrad(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st) 
         launch_k(reduce_adam_rp_kernel, ceil_div(p.n_tot, 64), 256, 0, st, p.partial, nA, nB, blk, blk - L->Cout, p.n_tot, p.nW, L->Cout,
                  g.CoutPad, L->Cin * L->KH * L->KW, L->weight, L->weight_t, L->bias, o.m_w, o.v_w, o.m_b, o.v_b, a->grad_w, a->grad_b,
                  a->apply_update, sc, L->quantized ? nullptr : reinterpret_cast<__nv_bfloat16 *>(L->weight_mma), L->Cin,
-                 L->KH * L->KW, L->KW);
+                 L->KH * L->KW, L->KW, (prec_f16(L) && !L->quantized) ? L->w_exp : nullptr);
         DCLL_LAUNCH_OK("reduce_adam_rp_kernel");
         if (a->apply_update && L->quantized) return sync_kernel_weights(L, st);
         return DCLL_OK;
     }
+    DCLL_REQUIRE(!prec_f16(L), DCLL_EUNSUPPORTED,
+                 "f16x2: the layer needs the row-pair weight-gradient kernel (even conv height, conv width a multiple of 8, K <= 32)");
     if (wgrad_tc_supported(L)) {
         p.S = wgrad_tc_splits(L);
         rc = launch_wgrad_tc(L, p.partial, p.S, st);

@@ -353,7 +353,8 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
 }
 
 bool wgrad_tc_supported(const dcll_conv_layer *L) {
-    return L->precision == DCLL_PREC_BF16X3 && L->KH == 7 && L->KW == 7 && (L->Cin == 32 || L->Cin == 1) && L->Cout == 32 &&
+    // (F16X2 with 32 input channels: the fp16 trace image is only understood by wgrad_tc2; without it the FP32 kernel runs)
+    return prec_tc(L) && !prec_f16(L) && L->KH == 7 && L->KW == 7 && (L->Cin == 32 || L->Cin == 1) && L->Cout == 32 &&
            L->poolH == 1 && L->poolW == 1;
 }
 

@@ -49,6 +49,8 @@ struct Wg2P {
     int dbg;             // DCLL_WG2_DEBUG (timing experiments only, results are garbage): bit 0 skip eps1 loads, bit 1 skip g_u loads,
                          // bit 2 skip the MMAs
     unsigned long long *tl;   // in-kernel stopwatch block (common.cuh TL_*), null when off
+    int f16;                  // DCLL_PREC_F16X2: the eps1 image holds ONE fp16 part (scaled), g_u fp16 {hi,lo} (scaled); no X_lo product
+    float unscale, unscale_g; // F16X2: 2^-(a_exp + g_exp) for the weight-gradient sums, 2^-g_exp for the bias sums; else 1
 };
 
 template <int TH_, int NSTAGE_>
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
         mbar_fence_init();
     }
     // the all-ones A tile of the bias-gradient MMA (any layout: every element is 1.0)
-    for (int i = tid; i < 4096 / 4; i += G::NT) reinterpret_cast<uint32_t *>(smem + G::OFF_ONES)[i] = 0x3f803f80u;
+    for (int i = tid; i < 4096 / 4; i += G::NT) reinterpret_cast<uint32_t *>(smem + G::OFF_ONES)[i] = p.f16 ? 0x3c003c00u : 0x3f803f80u;   // 1.0
     if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)G::TMEM_COLS);
     fence_async_smem();
     fence_before();
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
                 const int th_i = tile / p.tiles_w, tw_i = tile - th_i * p.tiles_w;
                 const int h0 = th_i * G::TH, w0 = tw_i * G::TW;
                 if (i >= G::NSTAGE) TL_TIMED(tl_on, tl_wait, mbar_wait(empty + sg, ((i / G::NSTAGE) - 1) & 1));   // MMAs of unit i-NSTAGE have read this stage
-                mbar_expect_tx(full + sg, ((p.dbg & 1) ? 0 : G::X_BYTES) + ((p.dbg & 2) ? 0 : G::G_BYTES));
+                mbar_expect_tx(full + sg, ((p.dbg & 1) ? 0 : (p.f16 ? G::X_PART : G::X_BYTES)) + ((p.dbg & 2) ? 0 : G::G_BYTES));
                 if (!(p.dbg & 1)) tma_load_5d(sX, &tmx, bar, 0, w0 - p.padW, 0, h0 - p.padH + row_off, 2 * b);
                 if (!(p.dbg & 2)) tma_load_5d(sG, &tmg, bar, 0, w0 >> 3, 0, 8 * b, h0 >> 1);
             }
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
         }
     } else if (warp < 2) {
         // ================= MMA issuers: warp 0 = first two kernel columns of the role, warp 1 = the rest (+ bias) =================
-        constexpr uint32_t IDESC_N128 = idesc_bf16(128, 128, true, false);   // A MN-major (M = (dy, ci) contiguous), B K-major
+        const uint32_t IDESC_N128 = p.f16 ? idesc_f16a(128, 128, true, false) : idesc_bf16(128, 128, true, false);   // A MN-major, B K-major
         constexpr uint32_t IDESC_N64 = idesc_bf16(128, 64, true, false);
         constexpr uint32_t A_HI = desc_hi(G::X_CP);          // SBO: next 8 rows of M = next (dy, cg) group
         constexpr uint32_t B_HI = desc_hi(G::G_GRP);         // SBO: next 8 rows of N = next (part, co/8, parity) group
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
                     for (int kw = kw0; kw < kw1; ++kw) {
                         const uint32_t d = tmem_base + (kw - kw_base) * G::ACC_COLS;
                         mma_bf16(d, desc(A_HI, a_row + kw), b, IDESC_N128, acc);
-                        mma_bf16(d, desc(A_HI, a_row + kw + (G::X_PART >> 4)), b, IDESC_N64, 1);
+                        if (!p.f16) mma_bf16(d, desc(A_HI, a_row + kw + (G::X_PART >> 4)), b, IDESC_N64, 1);
                     }
                     if (do_ones && (pr & 1) == grp) {
                         mma_bf16(tmem_base + 3 * G::ACC_COLS, ones_desc, b, IDESC_N128, ones_acc);
@@ -231,7 +233,8 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
                     for (int c = 0; c < 32; ++c) {
                         if (((c >> 3) & 1) != pass) continue;
                         const int co = (2 * hc + (c >> 4)) * 8 + (c & 7);
-                        const float val = __uint_as_float(v[c]) + __uint_as_float(v2[c]);
+                        float val = __uint_as_float(v[c]) + __uint_as_float(v2[c]);
+                        if (p.f16) val *= p.unscale;
                         float *sp = stg + (co * G::CIN + ci) * G::PITCH + a * G::SLOTS + q + 1 - pass;
                         *sp = (pass == 0 || q == 0) ? val : *sp + val;
                     }
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
                     }
                 }
             }
-            out[G::NW_BLK + lane] = bsum;
+            out[G::NW_BLK + lane] = p.f16 ? bsum * p.unscale_g : bsum;
         }
         fence_before();
         __syncthreads();
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2p_kernel(const Wg2P p, const 
         mbar_init(done, 2);
         mbar_fence_init();
     }
-    for (int i = tid; i < 4096 / 4; i += G::NT) reinterpret_cast<uint32_t *>(smem + G::OFF_ONES)[i] = 0x3f803f80u;
+    for (int i = tid; i < 4096 / 4; i += G::NT) reinterpret_cast<uint32_t *>(smem + G::OFF_ONES)[i] = p.f16 ? 0x3c003c00u : 0x3f803f80u;   // 1.0
     if (warp == 2) tmem_alloc2(tmem_slot, (uint32_t)G::TMEM_COLS);
     fence_async_smem();
     fence_before();
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2p_kernel(const Wg2P p, const 
                 const int th_i = tile / p.tiles_w, tw_i = tile - th_i * p.tiles_w;
                 const int h0 = th_i * G::TH, w0 = tw_i * G::TW;
                 if (i >= G::NSTAGE) TL_TIMED(tl_on, tl_wait, mbar_wait(empty + sg, ((i / G::NSTAGE) - 1) & 1));   // the pair's MMAs have read this stage
-                if (rank == 0) mbar_expect_tx(full + sg, 2 * (G::X_BYTES + G::G_BYTES));
+                if (rank == 0) mbar_expect_tx(full + sg, 2 * ((p.f16 ? G::X_PART : G::X_BYTES) + G::G_BYTES));
                 tma_load_5d_2cta(sX, &tmx, bar, 0, w0 - p.padW, 0, h0 - p.padH + row_off, 2 * b);
                 tma_load_5d_2cta(sG, &tmg, bar, 0, w0 >> 3, (int)rank, 8 * b, h0 >> 1);
             }
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2p_kernel(const Wg2P p, const 
         }
     } else if (warp < 2 && rank == 0) {
         // ================= MMA issuers (leader only): warp 0 = first two kernel columns of the role, warp 1 = the rest (+ bias) =========
-        constexpr uint32_t IDESC_N128 = idesc_bf16(256, 128, true, false);   // M = 256 over the pair; A MN-major, B K-major
+        const uint32_t IDESC_N128 = p.f16 ? idesc_f16a(256, 128, true, false) : idesc_bf16(256, 128, true, false);   // M = 256 over the pair
         constexpr uint32_t IDESC_N64 = idesc_bf16(256, 64, true, false);
         constexpr uint32_t A_HI = desc_hi(G::X_CP);          // SBO: next 8 rows of M = next (dy, cg) group
         constexpr uint32_t B_HI = desc_hi(G::G_GRP);         // SBO: next 8 columns of N = next (part, co/8) plane
@@ -390,7 +393,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2p_kernel(const Wg2P p, const 
                     for (int kw = kw0; kw < kw1; ++kw) {
                         const uint32_t d = tmem_base + (kw - kw_base) * G::ACC_COLS;
                         mma_bf16_2cta(d, desc(A_HI, a_row + kw), b, IDESC_N128, acc);
-                        mma_bf16_2cta(d + 32, desc(A_HI, a_row + kw + (G::X_PART >> 4)), b, IDESC_N64, 1);
+                        if (!p.f16) mma_bf16_2cta(d + 32, desc(A_HI, a_row + kw + (G::X_PART >> 4)), b, IDESC_N64, 1);
                     }
                     if (do_ones) mma_bf16_2cta(tmem_base + 3 * G::ACC_COLS, ones_desc, b, IDESC_N128, acc);
                 }
@@ -429,7 +432,8 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2p_kernel(const Wg2P p, const 
                 ld32(ta + 32, v2);
 #pragma unroll
                 for (int co = 0; co < 32; ++co) {
-                    const float val = any ? __uint_as_float(v[co]) + __uint_as_float(v2[co]) : 0.f;
+                    float val = any ? __uint_as_float(v[co]) + __uint_as_float(v2[co]) : 0.f;
+                    if (p.f16) val *= p.unscale;
                     float *sp = stg + (co * G::CIN + ci) * G::PITCH + a * G::SLOTS + q + 1 - pass;
                     *sp = (pass == 0 || q == 0) ? val : *sp + val;
                 }
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2p_kernel(const Wg2P p, const 
                         if (k == lane) bsum += __uint_as_float(c[k]);
                 }
             }
-            out[G::NW_BLK + lane] = bsum;
+            out[G::NW_BLK + lane] = p.f16 ? bsum * p.unscale_g : bsum;
         }
         fence_before();
         __syncthreads();
@@ -492,7 +496,7 @@ static bool wg2_tmaps_g(const dcll_conv_layer *L, TmapDesc *tmx, TmapDesc *tmg, 
     const uint64_t hw16 = (uint64_t)L->H * L->W * 16, plane = (uint64_t)g.Hc * g.Wc * 2;
     const uint64_t xd[5] = {8, (uint64_t)L->W, 4, (uint64_t)L->H, (uint64_t)2 * L->B};
     const uint64_t xs[4] = {16, hw16, (uint64_t)L->W * 16, 4 * hw16};
-    const uint32_t xb[5] = {8, (uint32_t)G::XCOLS, 4, (uint32_t)G::XROWS, 2};
+    const uint32_t xb[5] = {8, (uint32_t)G::XCOLS, 4, (uint32_t)G::XROWS, prec_f16(L) ? 1u : 2u};   // F16X2: the fp16 part only
     // g_u image [b][part][co/8][position/8][co % 8][8 positions]: 128 bytes per (channel group, 8 positions)
     const uint64_t gd[5] = {64, (uint64_t)g.Wc / 8, 2, (uint64_t)8 * L->B, (uint64_t)g.Hc / 2};
     const uint64_t gs[4] = {128, (uint64_t)g.Wc * 16, plane * 8, (uint64_t)g.Wc * 32};
@@ -514,7 +518,7 @@ bool wgrad_tc2_supported(const dcll_conv_layer *L) {
     }
     if (!on) return false;
     Geo g = geo_of(L);
-    if (!(wgrad_tc_supported(L) && tc_supported(L) && L->Cin == 32 && L->eps1_mma && L->g_u && (g.Wc % 8) == 0 && (g.Hc % 2) == 0 &&
+    if (!(prec_tc(L) && tc_supported(L) && L->Cin == 32 && L->eps1_mma && L->g_u && (g.Wc % 8) == 0 && (g.Hc % 2) == 0 &&
           L->K <= 32 && (((uintptr_t)L->pv | (uintptr_t)L->wo | (uintptr_t)L->g_u | (uintptr_t)L->eps1_mma) % 16) == 0))
         return false;
     TmapDesc tmx, tmg;
@@ -553,6 +557,9 @@ static int launch_wgrad_tc2_g(const dcll_conv_layer *L, float *partial, int *nA_
         dbg = e ? atoi(e) : 0;
     }
     p.dbg = dbg;
+    p.f16 = prec_f16(L) ? 1 : 0;
+    p.unscale = p.f16 ? pow2i(-(L->a_exp + L->g_exp)) : 1.f, p.unscale_g = p.f16 ? pow2i(-L->g_exp) : 1.f;
+    DCLL_REQUIRE(!p.f16 || (abs(L->a_exp + L->g_exp) <= 120 && abs(L->g_exp) <= 120), DCLL_EINVAL, "f16x2: operand exponents out of range");
     p.tl = timeline_buf(TL_WGRAD2);
     TmapDesc tmx, tmg;
     DCLL_REQUIRE(wg2_tmaps(L, &tmx, &tmg), DCLL_ECUDA, "wgrad_tc2: cuTensorMapEncodeTiled failed");
@@ -573,6 +580,9 @@ static int launch_wgrad_tc2_pair(const dcll_conv_layer *L, float *partial, int *
     wgrad_tc2_roles(L, &p.nA, &p.nB);
     *nA_out = p.nA, *nB_out = p.nB;
     p.dbg = 0;
+    p.f16 = prec_f16(L) ? 1 : 0;
+    p.unscale = p.f16 ? pow2i(-(L->a_exp + L->g_exp)) : 1.f, p.unscale_g = p.f16 ? pow2i(-L->g_exp) : 1.f;
+    DCLL_REQUIRE(!p.f16 || (abs(L->a_exp + L->g_exp) <= 120 && abs(L->g_exp) <= 120), DCLL_EINVAL, "f16x2: operand exponents out of range");
     p.tl = timeline_buf(TL_WGRAD2);
     TmapDesc tmx, tmg;
     DCLL_REQUIRE(wg2_tmaps(L, &tmx, &tmg), DCLL_ECUDA, "wgrad_tc2: cuTensorMapEncodeTiled failed");

@@ -250,8 +250,10 @@ class ContinuousConv2D(nn.Module):
         self._wt_key = None
         self._spare = None         # the other half of the ping-pong state
         self.quantized = False     # see quant.py
-        self.precision = 'fp32'    # 'fp32' (parity mode) or 'bf16x3' (tcgen05 tensor cores, where instantiated)
+        self.precision = 'fp32'    # 'fp32' (parity mode), 'bf16x3' or 'f16x2' (tcgen05 tensor cores, where instantiated)
         self._wmma = None          # bf16 {hi,lo} weights in the tcgen05 B-operand layout
+        self._wexp = None          # 'f16x2': device int32[4], exponent bookkeeping of the fp16 weight image (library-owned)
+        self._aexp = None          # 'f16x2': (key, exponent) of the trace image scale
         self._e1mma = None         # bf16 {hi,lo} image of eps1 in the tcgen05 A-operand layout (written by the forward)
 
     # ref:359-366
@@ -339,11 +341,30 @@ class ContinuousConv2D(nn.Module):
         """True when this core runs on the tcgen05 split-bf16 kernels (precision 'bf16x3' and an instantiated
         shape: 7x7, {1, 32} -> 32 channels; the layer additionally needs pooling 1, checked by the library).
         Other shapes stay on the FP32 FMA kernel."""
-        if not (self.precision == 'bf16x3' and self.kernel_size == (7, 7) and self.out_channels == 32):
+        if not (self.precision in ('bf16x3', 'f16x2') and self.kernel_size == (7, 7) and self.out_channels == 32):
             return False
         # single input channel: the operand pieces hold the column shifts x-padW .. x-padW+7 of the W input columns,
         # which covers every tap only while the output is not wider than the input (tc_supported, conv_fwd_tc.cu)
         return self.in_channels == 32 or (self.in_channels == 1 and 0 <= self.padding[1] <= 3)
+
+    def f16_ok(self, height, width):
+        """'f16x2' needs 32 input channels and the geometry of the row-pair weight-gradient kernel (even conv height, conv
+        width a multiple of 8); other tensor-core layers of the network keep the split-bf16 kernels."""
+        hc, wc = self.get_output_shape((height, width))
+        return self.tensor_core_ok() and self.in_channels == 32 and hc % 2 == 0 and wc % 8 == 0
+
+    def _trace_exp(self):
+        """Exponent of the trace image: eps1 <= tau_s/(1-alphas) * tau_m/(1-alpha) for spike input (ref:415-416), and
+        2^a_exp times that bound stays below 2^15 (fp16 maximum 65504).  One host read per parameter version."""
+        ps = (self.alpha, self.alphas, self.tau_m__dt, self.tau_s__dt)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._aexp is None or self._aexp[0] != key:
+            a, als, tm, ts = (p.detach().double().flatten() for p in ps)
+            bound = float(((ts / (1 - als)).max() * (tm / (1 - a)).max()).item())
+            if not (bound > 0 and math.isfinite(bound)):
+                raise ValueError("f16x2: time constants give no finite bound on eps1 (alpha, alphas must be < 1)")
+            self._aexp = (key, int(math.floor(math.log2(32768.0 / bound))))
+        return self._aexp[1]
 
     def _fill_core(self, desc, batch, height, width, x_mode):
         """Geometry, parameters and state pointers of the i2h core."""
@@ -358,7 +379,16 @@ class ContinuousConv2D(nn.Module):
         desc.x_mode = x_mode
         # 'bf16x3' selects the tensor-core kernels wherever the library has an instantiation for the shape
         # (forward: 7x7, 32->32; weight gradient: 7x7, {1,32}->32); other kernels of the layer stay FP32.
-        desc.precision = _lib.PREC_BF16X3 if self.precision == 'bf16x3' else _lib.PREC_FP32
+        desc.precision = {'bf16x3': _lib.PREC_BF16X3, 'f16x2': _lib.PREC_F16X2}.get(self.precision, _lib.PREC_FP32)
+        if self.precision == 'f16x2':
+            if self.f16_ok(height, width):
+                if self._wexp is None or self._wexp.device != self.weight.device:
+                    self._wexp = torch.zeros(4, dtype=torch.int32, device=self.weight.device)
+                    self._wt_key = None                      # the image and its exponent are (re)built by the next sync
+                desc.w_exp = _lib.ptr(self._wexp)
+                desc.a_exp = self._trace_exp()
+            else:
+                desc.precision = _lib.PREC_BF16X3             # shapes without the fp16 kernels keep the split-bf16 form
         desc.alpharp, desc.wrp = float(self.alpharp), float(self.wrp)
         mode, ts = self._coef.get(self, self.in_channels, height, width)
         desc.coef_mode = mode
@@ -569,11 +599,24 @@ class Conv2dDCLLlayer(nn.Module):
         if self._g_u is None or tuple(self._g_u.shape) != pooled or self._g_u.device != dev:
             self._g_u = torch.empty(pooled, device=dev)
         desc.g_u = _lib.ptr(self._g_u)
+        if desc.precision == _lib.PREC_F16X2:
+            desc.g_exp = self._grad_exp(batch)
         need = _lib.lib.dcll_conv_workspace_bytes(ctypes.byref(desc))
         if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
             self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
         desc.workspace, desc.workspace_bytes = _lib.ptr(self._workspace), self._workspace.numel()
         return old, outs
+
+    def _grad_exp(self, batch):
+        """Exponent of the g_u image ('f16x2'): |g_u| <= sum_k |g_o| |Wo| / 4 <= max|Wo| / (4 B) for the mean-reduced SmoothL1 /
+        L1 losses (|g_o| <= 1/(B K)); 2^4 of slack for MSE residuals above 1 and external losses, the store saturates beyond.
+        One host read per version of the frozen read-out."""
+        w = self.i2o.weight
+        key = (w.data_ptr(), w._version, batch)
+        if getattr(self, '_gexp', None) is None or self._gexp[0] != key:
+            bound = float(w.detach().abs().max().item()) / (4.0 * batch) * 16.0
+            self._gexp = (key, int(math.floor(math.log2(16384.0 / bound))) if bound > 0 else 0)
+        return self._gexp[1]
 
     def _input(self, input):
         if isinstance(input, SpikeCells):

@@ -107,9 +107,11 @@ class ConvNetwork(torch.nn.Module):
     def set_precision(self, mode):
         """'fp32': FP32-exact parity mode (CUDA-core FMA).  'bf16x3': convolutions of the layers with an
         instantiated tensor-core shape run on tcgen05 with split-bf16 operands (3 MMAs, FP32 accumulation in TMEM);
-        pooled layers fall back to FP32 per layer."""
-        if mode not in ('fp32', 'bf16x3'):
-            raise ValueError("precision must be 'fp32' or 'bf16x3'")
+        pooled layers fall back to FP32 per layer.  'f16x2': the same kernels with the trace operand (eps1, in [0,1]) as ONE fp16
+        value against split-bf16 weights / local gradients -- two products instead of three and no lo pass over the traces
+        (membrane error ~1e-4 of its scale instead of ~1e-5; spike-flip rate within the 1e-3 bound of the headline mode)."""
+        if mode not in ('fp32', 'bf16x3', 'f16x2'):
+            raise ValueError("precision must be 'fp32', 'bf16x3' or 'f16x2'")
         for s in self.dcll_slices:
             lay = s.dclllayer
             lay.i2h.precision = mode if max(lay.pooling) == 1 else 'fp32'

@@ -27,10 +27,11 @@ def run(im, B, arp, steps=4, mode='bf16x3'):
                 im, B, arp, t, i, s.dclllayer.i2h.tensor_core_ok(), eq, rel_err(pvmem, fo.pvmem), flips, rel_err(pvo, fo.pvoutput)))
     torch.cuda.synchronize()
 
+MODE = os.environ.get("DCLL_PRECISION", "bf16x3")
 if __name__ == "__main__":
-    run((16, 16), 4, 0.0)
-    run((40, 24), 3, 1.0)
-    run((128, 128), 2, 0.0, steps=2)
+    run((16, 16), 4, 0.0, mode=MODE)
+    run((40, 24), 3, 1.0, mode=MODE)
+    run((128, 128), 2, 0.0, steps=2, mode=MODE)
 
 
 def check_wgrad(im, B, arp=0.0, mode='bf16x3'):
@@ -65,6 +66,6 @@ def check_wgrad(im, B, arp=0.0, mode='bf16x3'):
 
 
 if __name__ == "__main__" and "--wgrad" in sys.argv:
-    check_wgrad((16, 16), 8)
-    check_wgrad((40, 24), 3, 1.0)
-    check_wgrad((128, 128), 2)
+    check_wgrad((16, 16), 8, mode=MODE)
+    check_wgrad((40, 24), 3, 1.0, mode=MODE)
+    check_wgrad((128, 128), 2, mode=MODE)

@@ -28,7 +28,7 @@ def main():
     net = net.to("cuda")
     net.reset(True)
     net.load_state_dict(sd)
-    net.set_precision("bf16x3")
+    net.set_precision(os.environ.get("DCLL_PRECISION", "bf16x3"))
     onet = O.OracleNet(specs, params, B, burnin=0)
     g = torch.Generator().manual_seed(5)
     x = (torch.rand(3, B, 1, *im, generator=g) < 0.1).float()
