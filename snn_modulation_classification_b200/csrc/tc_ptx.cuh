@@ -31,6 +31,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// the same for warps that have nothing else to do for a long time (producers waiting for a free stage, epilogue / drain warps
+// waiting for accumulators): every failed poll is a shared-memory access that competes with the tensor core's operand reads, so
+// these warps sleep between polls
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, uint32_t sleep_ns = 200) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!ok) __nanosleep(sleep_ns);
+    } while (!ok);
+}
 // 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (UBLKCP in SASS)
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),

@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(256) reduce_adam_rp_kernel(const float *__rest
                 const int ci = r / KHKW, tap = r - ci * KHKW;
                 size_t o = (size_t)tap * (2 * Cin * Cout) + ((size_t)(ci >> 3) * 2 * Cout + co) * 8 + (ci & 7);
                 if (w_exp) {
-                    const float vs = __fmul_rn(wv, pow2i(kexp));
+                    // (the exponent is one step old: 2^8 of headroom; a weight that outgrows it within ONE step saturates)
+                    const float vs = fminf(fmaxf(__fmul_rn(wv, pow2i(kexp)), -65504.f), 65504.f);
                     const __half hi = __float2half_rn(vs);
                     reinterpret_cast<__half *>(w_mma)[o] = hi;
                     reinterpret_cast<__half *>(w_mma)[o + (size_t)Cout * 8] = __float2half_rn(vs - __half2float(hi));

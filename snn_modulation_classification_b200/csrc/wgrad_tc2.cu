@@ -51,6 +51,7 @@ struct Wg2P {
     unsigned long long *tl;   // in-kernel stopwatch block (common.cuh TL_*), null when off
     int f16;                  // DCLL_PREC_F16X2: the eps1 image holds ONE fp16 part (scaled), g_u fp16 {hi,lo} (scaled); no X_lo product
     float unscale, unscale_g; // F16X2: 2^-(a_exp + g_exp) for the weight-gradient sums, 2^-g_exp for the bias sums; else 1
+    int g16;                  // the g_u tensor map merges the two 8-column chunks of a unit row into one 256-byte box row
 };
 
 template <int TH_, int NSTAGE_>
@@ -104,8 +105,8 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
     const long long tl_entry = tl_on ? clock64() : 0;
     if (tl_on && threadIdx.x == 0) tl[TL_T_ENTRY] = gtimer_ns();
     if (tid == 0) {
-        for (int i = 0; i < G::NSTAGE; ++i) mbar_init(full + i, 1), mbar_init(empty + i, 2);
-        mbar_init(done, 2);
+        for (int i = 0; i < G::NSTAGE; ++i) mbar_init(full + i, 1), mbar_init(empty + i, 1);
+        mbar_init(done, 1);
         *ones_used = 0u;
         mbar_fence_init();
     }
@@ -145,23 +146,25 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
                 const int b = u / tiles, tile = u - b * tiles;
                 const int th_i = tile / p.tiles_w, tw_i = tile - th_i * p.tiles_w;
                 const int h0 = th_i * G::TH, w0 = tw_i * G::TW;
-                if (i >= G::NSTAGE) TL_TIMED(tl_on, tl_wait, mbar_wait(empty + sg, ((i / G::NSTAGE) - 1) & 1));   // MMAs of unit i-NSTAGE have read this stage
+                if (i >= G::NSTAGE) TL_TIMED(tl_on, tl_wait, mbar_wait_relaxed(empty + sg, ((i / G::NSTAGE) - 1) & 1));   // MMAs of unit i-NSTAGE have read this stage
                 mbar_expect_tx(full + sg, ((p.dbg & 1) ? 0 : (p.f16 ? G::X_PART : G::X_BYTES)) + ((p.dbg & 2) ? 0 : G::G_BYTES));
                 if (!(p.dbg & 1)) tma_load_5d(sX, &tmx, bar, 0, w0 - p.padW, 0, h0 - p.padH + row_off, 2 * b);
-                if (!(p.dbg & 2)) tma_load_5d(sG, &tmg, bar, 0, w0 >> 3, 0, 8 * b, h0 >> 1);
+                if (!(p.dbg & 2)) tma_load_5d(sG, &tmg, bar, 0, p.g16 ? w0 >> 4 : w0 >> 3, 0, 8 * b, h0 >> 1);
             }
             if (tl_on) tl[TL_APROD_EMPTY] = tl_wait;
         }
-    } else if (warp < 2) {
-        // ================= MMA issuers: warp 0 = first two kernel columns of the role, warp 1 = the rest (+ bias) =================
+    } else if (warp == 0) {
+        // ================= MMA issuer: ONE warp.  (Two issuer warps -- kernel columns split between them -- were right for the
+        // N = 64 / 32 MMAs of wgrad_tc_kernel, which a single thread cannot issue fast enough; with N = 128 and the MN-major A
+        // operand two concurrent streams cost 92 cycles per MMA in aggregate against 64 for one, tools/mma_bench.cu.) ==========
         const uint32_t IDESC_N128 = p.f16 ? idesc_f16a(128, 128, true, false) : idesc_bf16(128, 128, true, false);   // A MN-major, B K-major
         constexpr uint32_t IDESC_N64 = idesc_bf16(128, 64, true, false);
         constexpr uint32_t A_HI = desc_hi(G::X_CP);          // SBO: next 8 rows of M = next (dy, cg) group
         constexpr uint32_t B_HI = desc_hi(G::G_GRP);         // SBO: next 8 rows of N = next (part, co/8, parity) group
         constexpr uint32_t ONES_HI = desc_hi(128);
         const uint32_t elected = elect_one();
-        const int kw0 = kw_base + (warp == 0 ? 0 : 2), kw1 = roleB ? (warp == 0 ? 6 : 7) : (warp == 0 ? 2 : 4);
-        const bool do_ones = roleB && warp == 1;
+        const int kw0 = kw_base, kw1 = roleB ? 7 : 4;
+        const bool do_ones = roleB;
         const uint64_t ones_desc = desc(ONES_HI, desc_lo(smem_u32(smem + G::OFF_ONES), 2048));
         uint32_t ones_acc = 0;
         int i = 0;
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2_kernel(const Wg2P p, const _
     //      (slot s <-> kh = 4g - 1 + s).  Two passes through the idle tile buffers: parity 0 stores slots 1..4, then parity 1 stores
     //      slot 0 and adds to slots 1..3; each (co, ci, a, slot) is touched by one thread per pass.
     float *out = p.partial + (size_t)blockIdx.x * G::BLK;
-    mbar_wait(done, 0);
+    mbar_wait_relaxed(done, 0, 1000);   // 13+ idle warps: sleep between polls (see tc_ptx.cuh)
     fence_after();
     __syncthreads();
     const long long tl_drain0 = tl_on ? clock64() : 0;
@@ -298,6 +301,39 @@ struct Wg2PairGeoT : Wg2GeoT<TH_, NSTAGE_> {
     static_assert(BUF % 128 == 0, "alignment");
 };
 
+// The MMAs of one unit, straight-line: with the pair / kernel-column loops rolled the issuing thread spent ~110 cycles of
+// uniform-datapath work per iteration (ncu: tensor pipe 59 % active, the issuer never waiting on a barrier), i.e. the 64-cycle
+// N = 128 MMAs were issue-bound.  Unrolled, an MMA is a descriptor add and the instruction.
+template <class G, bool ROLEB, bool F16>
+__device__ __forceinline__ void wg2p_issue_unit(uint32_t tmem_base, uint32_t a_base, uint32_t b_base, uint64_t ones_desc, uint32_t acc0,
+                                                int npair) {
+    using namespace tc;
+    constexpr int NKW = ROLEB ? 3 : 4, KW0 = ROLEB ? 4 : 0;
+    constexpr uint32_t IDESC_N128 = F16 ? idesc_f16a(256, 128, true, false) : idesc_bf16(256, 128, true, false);   // M = 256 over the pair
+    constexpr uint32_t IDESC_N64 = idesc_bf16(256, 64, true, false);
+    constexpr uint32_t A_HI = desc_hi(G::X_CP);          // SBO: next 8 rows of M = next (dy, cg) group
+    constexpr uint32_t B_HI = desc_hi(G::G_GRP);         // SBO: next 8 columns of N = next (part, co/8) plane
+    auto pair_row = [&](int pr, uint32_t acc) {
+        const uint64_t b = desc(B_HI, b_base + pr * (G::G_PAIR >> 4));
+        const uint32_t a_row = a_base + ((2 * pr * G::X_RP) >> 4) + KW0;
+#pragma unroll
+        for (int k = 0; k < NKW; ++k) {
+            const uint32_t d = tmem_base + k * G::ACC_COLS;
+            mma_bf16_2cta(d, desc(A_HI, a_row + k), b, IDESC_N128, acc);
+            if (!F16) mma_bf16_2cta(d + 32, desc(A_HI, a_row + k + (G::X_PART >> 4)), b, IDESC_N64, 1);
+        }
+        if (ROLEB) mma_bf16_2cta(tmem_base + 3 * G::ACC_COLS, ones_desc, b, IDESC_N128, acc);
+    };
+    if (npair == G::PAIRS) {
+        pair_row(0, acc0);
+#pragma unroll
+        for (int pr = 1; pr < G::PAIRS; ++pr) pair_row(pr, 1u);
+    } else {
+#pragma unroll 1
+        for (int pr = 0; pr < npair; ++pr) pair_row(pr, pr == 0 ? acc0 : 1u);
+    }
+}
+
 template <int TH_, int NSTAGE_>
 __global__ void __launch_bounds__(512, 1) wgrad_tc2p_kernel(const Wg2P p, const __grid_constant__ TmapDesc tmx,
                                                             const __grid_constant__ TmapDesc tmg) {
@@ -317,8 +353,8 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2p_kernel(const Wg2P p, const 
     if (tl_on && threadIdx.x == 0) tl[TL_T_ENTRY] = gtimer_ns();
     if (tid == 0) {
         // full: ONE arrival (the leader's producer, with the byte count of both CTAs); only the leader's copy is ever waited on
-        for (int i = 0; i < G::NSTAGE; ++i) mbar_init(full + i, 1), mbar_init(empty + i, 2);
-        mbar_init(done, 2);
+        for (int i = 0; i < G::NSTAGE; ++i) mbar_init(full + i, 1), mbar_init(empty + i, 1);
+        mbar_init(done, 1);
         mbar_fence_init();
     }
     for (int i = tid; i < 4096 / 4; i += G::NT) reinterpret_cast<uint32_t *>(smem + G::OFF_ONES)[i] = p.f16 ? 0x3c003c00u : 0x3f803f80u;   // 1.0
@@ -353,23 +389,17 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2p_kernel(const Wg2P p, const 
                 const int b = u / tiles, tile = u - b * tiles;
                 const int th_i = tile / p.tiles_w, tw_i = tile - th_i * p.tiles_w;
                 const int h0 = th_i * G::TH, w0 = tw_i * G::TW;
-                if (i >= G::NSTAGE) TL_TIMED(tl_on, tl_wait, mbar_wait(empty + sg, ((i / G::NSTAGE) - 1) & 1));   // the pair's MMAs have read this stage
+                if (i >= G::NSTAGE) TL_TIMED(tl_on, tl_wait, mbar_wait_relaxed(empty + sg, ((i / G::NSTAGE) - 1) & 1));   // the pair's MMAs have read this stage
                 if (rank == 0) mbar_expect_tx(full + sg, 2 * ((p.f16 ? G::X_PART : G::X_BYTES) + G::G_BYTES));
                 tma_load_5d_2cta(sX, &tmx, bar, 0, w0 - p.padW, 0, h0 - p.padH + row_off, 2 * b);
-                tma_load_5d_2cta(sG, &tmg, bar, 0, w0 >> 3, (int)rank, 8 * b, h0 >> 1);
+                tma_load_5d_2cta(sG, &tmg, bar, 0, p.g16 ? w0 >> 4 : w0 >> 3, (int)rank, 8 * b, h0 >> 1);
             }
             if (tl_on) tl[TL_APROD_EMPTY] = tl_wait;
         }
-    } else if (warp < 2 && rank == 0) {
-        // ================= MMA issuers (leader only): warp 0 = first two kernel columns of the role, warp 1 = the rest (+ bias) =========
-        const uint32_t IDESC_N128 = p.f16 ? idesc_f16a(256, 128, true, false) : idesc_bf16(256, 128, true, false);   // M = 256 over the pair
-        constexpr uint32_t IDESC_N64 = idesc_bf16(256, 64, true, false);
-        constexpr uint32_t A_HI = desc_hi(G::X_CP);          // SBO: next 8 rows of M = next (dy, cg) group
-        constexpr uint32_t B_HI = desc_hi(G::G_GRP);         // SBO: next 8 columns of N = next (part, co/8) plane
+    } else if (warp == 0 && rank == 0) {
+        // ================= MMA issuer (leader only, one warp: see wgrad_tc2_kernel) =========
         constexpr uint32_t ONES_HI = desc_hi(128);
         const uint32_t elected = elect_one();
-        const int kw0 = kw_base + (warp == 0 ? 0 : 2), kw1 = roleB ? (warp == 0 ? 6 : 7) : (warp == 0 ? 2 : 4);
-        const bool do_ones = roleB && warp == 1;
         const uint64_t ones_desc = desc(ONES_HI, desc_lo(smem_u32(smem + G::OFF_ONES), 2048));
         int i = 0;
         long long tl_wait = 0;
@@ -385,17 +415,13 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2p_kernel(const Wg2P p, const 
             fence_after();
             if (tl_on && i == 0 && warp == 0 && elected) tl[TL_FIRST_MMA] = clock64() - tl_entry;
             if (elected) {
-                for (int pr = 0; pr < npair; ++pr) {
-                    const uint64_t b = desc(B_HI, b_base + pr * (G::G_PAIR >> 4));
-                    const uint32_t acc = (i == 0 && pr == 0) ? 0u : 1u;
-                    const uint32_t a_row = a_base + ((2 * pr * G::X_RP) >> 4);
-#pragma unroll 2
-                    for (int kw = kw0; kw < kw1; ++kw) {
-                        const uint32_t d = tmem_base + (kw - kw_base) * G::ACC_COLS;
-                        mma_bf16_2cta(d, desc(A_HI, a_row + kw), b, IDESC_N128, acc);
-                        if (!p.f16) mma_bf16_2cta(d + 32, desc(A_HI, a_row + kw + (G::X_PART >> 4)), b, IDESC_N64, 1);
-                    }
-                    if (do_ones) mma_bf16_2cta(tmem_base + 3 * G::ACC_COLS, ones_desc, b, IDESC_N128, acc);
+                const uint32_t acc0 = i == 0 ? 0u : 1u;
+                if (roleB) {
+                    if (p.f16) wg2p_issue_unit<G, true, true>(tmem_base, a_base, b_base, ones_desc, acc0, npair);
+                    else wg2p_issue_unit<G, true, false>(tmem_base, a_base, b_base, ones_desc, acc0, npair);
+                } else {
+                    if (p.f16) wg2p_issue_unit<G, false, true>(tmem_base, a_base, b_base, ones_desc, acc0, npair);
+                    else wg2p_issue_unit<G, false, false>(tmem_base, a_base, b_base, ones_desc, acc0, npair);
                 }
                 commit_2cta(empty + sg);
             }
@@ -413,7 +439,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc2p_kernel(const Wg2P p, const 
     //      (slot s <-> kh = 4g - 1 + s).  Two passes through the idle tile buffers: parity 0 stores slots 1..4, then parity 1 stores
     //      slot 0 and adds to slots 1..3; each (co, ci, a, slot) is touched by one thread per pass.
     float *out = p.partial + (size_t)blockIdx.x * G::BLK;
-    mbar_wait(done, 0);
+    mbar_wait_relaxed(done, 0, 1000);   // 13+ idle warps: sleep between polls (see tc_ptx.cuh)
     fence_after();
     __syncthreads();
     const long long tl_drain0 = tl_on ? clock64() : 0;
@@ -490,6 +516,8 @@ static bool wg2_pair() {
     return on != 0 && wg2_tile() == 8;
 }
 
+static bool wg2_g16(const dcll_conv_layer *L) { return (geo_of(L).Wc % 16) == 0; }
+
 template <class G>
 static bool wg2_tmaps_g(const dcll_conv_layer *L, TmapDesc *tmx, TmapDesc *tmg, bool pair = false) {
     Geo g = geo_of(L);
@@ -497,10 +525,13 @@ static bool wg2_tmaps_g(const dcll_conv_layer *L, TmapDesc *tmx, TmapDesc *tmg, 
     const uint64_t xd[5] = {8, (uint64_t)L->W, 4, (uint64_t)L->H, (uint64_t)2 * L->B};
     const uint64_t xs[4] = {16, hw16, (uint64_t)L->W * 16, 4 * hw16};
     const uint32_t xb[5] = {8, (uint32_t)G::XCOLS, 4, (uint32_t)G::XROWS, prec_f16(L) ? 1u : 2u};   // F16X2: the fp16 part only
-    // g_u image [b][part][co/8][position/8][co % 8][8 positions]: 128 bytes per (channel group, 8 positions)
-    const uint64_t gd[5] = {64, (uint64_t)g.Wc / 8, 2, (uint64_t)8 * L->B, (uint64_t)g.Hc / 2};
-    const uint64_t gs[4] = {128, (uint64_t)g.Wc * 16, plane * 8, (uint64_t)g.Wc * 32};
-    const uint32_t gb[5] = {64, 2, pair ? 1u : 2u, 8, (uint32_t)G::PAIRS};   // pair: one row parity per CTA
+    // g_u image [b][part][co/8][position/8][co % 8][8 positions]: 128 bytes per (channel group, 8 positions).  The two chunks of
+    // a 16-column unit row are adjacent in memory, so with Wc % 16 == 0 they are ONE 256-byte box row (the TMA unit works row by
+    // row: 32 instead of 64 rows per half tile; with fp16 traces the producer, not the MMAs, bounded the kernel).
+    const bool g16 = wg2_g16(L);
+    const uint64_t gd[5] = {g16 ? 128u : 64u, (uint64_t)g.Wc / (g16 ? 16 : 8), 2, (uint64_t)8 * L->B, (uint64_t)g.Hc / 2};
+    const uint64_t gs[4] = {g16 ? 256u : 128u, (uint64_t)g.Wc * 16, plane * 8, (uint64_t)g.Wc * 32};
+    const uint32_t gb[5] = {g16 ? 128u : 64u, g16 ? 1u : 2u, pair ? 1u : 2u, 8, (uint32_t)G::PAIRS};   // pair: one row parity per CTA
     return tmap_bf16(tmx, L->eps1_mma, 5, xd, xs, xb) && tmap_bf16(tmg, L->g_u, 5, gd, gs, gb);
 }
 static bool wg2_tmaps(const dcll_conv_layer *L, TmapDesc *tmx, TmapDesc *tmg) {
@@ -536,7 +567,8 @@ void wgrad_tc2_roles(const dcll_conv_layer *L, int *nA, int *nB) {
         const char *e = getenv("DCLL_WG2_NA");
         na_env = e ? atoi(e) : 0;
     }
-    const int na74 = na_env > 0 && na_env < 74 ? na_env : (wg2_pair() ? 39 : 40);
+    // (F16X2: no lo products -- 16 N = 128 MMAs per unit in both roles, the bias MMAs included: 37 : 37)
+    const int na74 = na_env > 0 && na_env < 74 ? na_env : (prec_f16(L) ? 37 : (wg2_pair() ? 39 : 40));
     if (n_units >= 40) *nA = (pairs * na74 + 37) / 74, *nB = pairs - *nA;
     else *nA = *nB = n_units < pairs / 2 ? n_units : pairs / 2;
 }
@@ -557,7 +589,7 @@ static int launch_wgrad_tc2_g(const dcll_conv_layer *L, float *partial, int *nA_
         dbg = e ? atoi(e) : 0;
     }
     p.dbg = dbg;
-    p.f16 = prec_f16(L) ? 1 : 0;
+    p.f16 = prec_f16(L) ? 1 : 0, p.g16 = wg2_g16(L) ? 1 : 0;
     p.unscale = p.f16 ? pow2i(-(L->a_exp + L->g_exp)) : 1.f, p.unscale_g = p.f16 ? pow2i(-L->g_exp) : 1.f;
     DCLL_REQUIRE(!p.f16 || (abs(L->a_exp + L->g_exp) <= 120 && abs(L->g_exp) <= 120), DCLL_EINVAL, "f16x2: operand exponents out of range");
     p.tl = timeline_buf(TL_WGRAD2);
@@ -580,7 +612,7 @@ static int launch_wgrad_tc2_pair(const dcll_conv_layer *L, float *partial, int *
     wgrad_tc2_roles(L, &p.nA, &p.nB);
     *nA_out = p.nA, *nB_out = p.nB;
     p.dbg = 0;
-    p.f16 = prec_f16(L) ? 1 : 0;
+    p.f16 = prec_f16(L) ? 1 : 0, p.g16 = wg2_g16(L) ? 1 : 0;
     p.unscale = p.f16 ? pow2i(-(L->a_exp + L->g_exp)) : 1.f, p.unscale_g = p.f16 ? pow2i(-L->g_exp) : 1.f;
     DCLL_REQUIRE(!p.f16 || (abs(L->a_exp + L->g_exp) <= 120 && abs(L->g_exp) <= 120), DCLL_EINVAL, "f16x2: operand exponents out of range");
     p.tl = timeline_buf(TL_WGRAD2);

@@ -1,0 +1,206 @@
+"""'f16x2' precision mode vs the FP32 oracle (needs a B200: pytest -m gpu).
+
+The trace operand of the 32-channel tensor-core layers is ONE fp16 value (eps1 times a static power of two), the weights and
+the local gradient are split fp16 {hi,lo} with power-of-two scales (weights: exponent tracked on the device from max |w|;
+gradient: static bound), two products per MAC instead of the three of 'bf16x3'.  The trace rounding, 2^-12 relative, is the
+only new error: the membrane stays within ~2.5e-4 of its scale and the spike-flip rate within the headline mode's stated
+bound of 1e-3 (BASELINE.json north_star); traces themselves stay bit-exact (FP32 recurrences).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dcll_oracle as O
+from util_build import build_pair, force_state, make_args, rel_err, state_dict_from_params
+
+pytestmark = pytest.mark.gpu
+
+F16_MEM_TOL = 6e-4     # membrane, relative to tensor scale: 2^-12 = 2.4e-4 per trace value, worst case over a layer
+F16_RO_TOL = 5e-5      # read-outs (the forward read-out GEMM is split-bf16 x3 in every tensor-core mode)
+FLIP_TOL = 1e-3        # stated flip-rate bound of the headline mode
+F16_GRAD_TOL = 1e-3    # weight gradient, max error relative to the gradient's scale (measured 2-4e-4)
+
+
+def _modes(net):
+    return [s.dclllayer._ctx[0].precision for s in net.dcll_slices]
+
+
+@pytest.mark.parametrize("im,B,arp", [((16, 16), 6, 0.0), ((40, 24), 3, 1.0), ((128, 128), 2, 0.0), ((21, 45), 2, 1.0)])
+def test_f16x2_forward_teacher_forced(im, B, arp):
+    from snn_modulation_classification_b200 import _lib
+    K, steps = 24, 4
+    net, onet = build_pair("radio_ml_conv", (1,) + im, B, K, arp=arp, train=False)
+    net.set_precision("f16x2")
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(steps, B, 1, *im, generator=g) < 0.1).float()
+    net.reset()
+    onet.reset()
+    flips, total = np.zeros(3), np.zeros(3)
+    for t in range(steps):
+        force_state(net, onet)
+        onet.test(x[t])
+        for i, s in enumerate(net.dcll_slices):
+            inp = x[t].cuda() if i == 0 else onet.last[i - 1].output.cuda()
+            out, pvo, pv, pvmem = s.forward(inp, ignore_burnin=True)
+            fo, st = onet.last[i], s.dclllayer.i2h.state
+            assert torch.equal(st.eps0.cpu(), fo.state.eps0) and torch.equal(st.eps1.cpu(), fo.state.eps1)
+            assert rel_err(pvmem, fo.pvmem) <= F16_MEM_TOL, (t, i, rel_err(pvmem, fo.pvmem))
+            assert rel_err(pvo, fo.pvoutput) <= F16_RO_TOL, (t, i, rel_err(pvo, fo.pvoutput))
+            spk = s.dclllayer._ctx[1]["spikes"].cpu()
+            flips[i] += float((spk != fo.spikes).sum())
+            total[i] += spk.numel()
+    assert (flips / total).max() <= FLIP_TOL, flips / total
+    # layer 0 (one input channel) keeps the split-bf16 kernels; the 32-channel layers run the fp16 form when the geometry
+    # of the row-pair weight-gradient kernel holds (even conv height, conv width a multiple of 8), else split-bf16
+    hc, wc = im
+    want = _lib.PREC_F16X2 if (hc % 2 == 0 and wc % 8 == 0) else _lib.PREC_BF16X3
+    assert _modes(net) == [_lib.PREC_BF16X3, want, want]
+
+
+@pytest.mark.parametrize("im,B,arp", [((16, 16), 8, 0.0), ((40, 24), 3, 1.0), ((128, 128), 2, 0.0)])
+def test_f16x2_weight_gradient(im, B, arp):
+    from snn_modulation_classification_b200 import networks as N
+    K = 24
+    specs = O.make_specs(O.BUILTIN_SPECS["radio_ml_conv"], (1,) + im, K, wrp=arp)
+    params = O.random_params(specs, seed=2)
+    sd = state_dict_from_params(params)
+    net = N.ConvNetwork(make_args(arp), (1,) + im, B, N.load_network_spec("radio_ml_conv"), K, act=torch.nn.Sigmoid(),
+                        loss=torch.nn.SmoothL1Loss, opt=torch.optim.SGD, opt_param={}, learning_rates=[0.0], burnin=0)
+    net.load_state_dict(sd)
+    net = net.to("cuda")
+    net.reset(True)
+    net.load_state_dict(sd)
+    net.set_precision("f16x2")
+    onet = O.OracleNet(specs, params, B, burnin=0)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(2, B, 1, *im, generator=g) < 0.1).float()
+    y = O.to_one_hot(torch.randint(0, K, (B,), generator=g), K)
+    for t in range(2):
+        force_state(net, onet)
+        fos, grads, inp = [], [], x[t]
+        for i, sp in enumerate(specs):
+            fo = O.conv_step_fwd(sp, params[i], onet.states[i], inp)
+            grads.append(O.conv_local_grads(sp, params[i], fo, y))
+            fos.append(fo)
+            onet.states[i], inp = fo.state, fo.spikes
+        for i, s in enumerate(net.dcll_slices):
+            s.train_dcll(x[t].cuda() if i == 0 else fos[i - 1].spikes.cuda(), y.cuda(), regularize=False)
+            assert rel_err(s.dclllayer.i2h.weight.grad, grads[i].gW) <= F16_GRAD_TOL, (t, i)
+            assert rel_err(s.dclllayer.i2h.bias.grad, grads[i].gb) <= 5e-5, (t, i)      # the bias sums see no trace rounding
+
+
+@pytest.mark.parametrize("lr", [1e-6, 3e-5])
+def test_f16x2_training_steps_follow_the_weights(lr):
+    """Teacher-forced training steps through the fused Adam: the fp16 weight image and its device-tracked exponent must follow
+    the weights (lr 3e-5 moves them by 30x their initial size per step), so the NEXT step's membrane still meets the bound.
+    Weights after a step: the trace rounding shows as ~2e-4 relative gradient error, which Adam (step +-lr whatever |g|) turns
+    into a sign change only for elements whose gradient cancels against weight_decay * w to that level."""
+    B, K, burnin, steps = 8, 24, 1, 6
+    net, onet = build_pair("radio_ml_conv", (1, 16, 16), B, K, arp=1.0, burnin=burnin, lr=lr)
+    net.set_precision("f16x2")
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(steps, B, 1, 16, 16, generator=g) < 0.1).float()
+    y = O.to_one_hot(torch.randint(0, K, (B,), generator=g), K)
+    net.reset()
+    onet.reset()
+    for t in range(steps):
+        force_state(net, onet)
+        onet.learn(x[t], y)
+        for i, s in enumerate(net.dcll_slices):
+            inp = x[t].cuda() if i == 0 else onet.last[i - 1].output.cuda()
+            out, pvo, pv, pvmem, _ = s.train_dcll(inp, y.cuda(), regularize=False)
+            fo = onet.last[i]
+            assert rel_err(pvmem, fo.pvmem) <= F16_MEM_TOL, (t, i, rel_err(pvmem, fo.pvmem))
+            if onet.iters[i] >= burnin:
+                dw = (s.dclllayer.i2h.weight.detach().cpu() - onet.params[i].weight).abs()
+                frac = float((dw > 0.5 * lr).float().mean())
+                assert float(dw.mean()) <= 2e-2 * lr and frac <= 5e-3 and float(dw.max()) <= 2.1 * lr, \
+                    (t, i, float(dw.max()) / lr, float(dw.mean()) / lr, frac)
+
+
+def test_f16x2_window_equals_per_step_and_is_deterministic():
+    from snn_modulation_classification_b200.data.utils import iq2spiketrain
+    B, K, T, W, burnin = 8, 24, 10, 16, 3
+    nets = []
+    for _ in range(3):
+        n, _ = build_pair("radio_ml_conv", (1, W, W), B, K, arp=1.0, burnin=burnin)
+        nets.append(n.set_precision("f16x2"))
+    g = torch.Generator().manual_seed(4)
+    xs = (torch.randn(B, 2, 1, 1024, generator=g) * 0.4).float()
+    y = O.to_one_hot(torch.randint(0, K, (B,), generator=g), K).cuda()
+    np.random.seed(1)
+    cells, tgt = iq2spiketrain(xs, y, out_w=W, out_h=W, max_duration=T, as_cells=True)
+    for n in nets:
+        n.reset()
+    for t in range(T):
+        nets[0].learn(cells[t], tgt[t])
+    nets[1].learn_window(cells, y)
+    nets[2].learn_window(cells, y)
+    for a, b, c in zip(nets[0].dcll_slices, nets[1].dcll_slices, nets[2].dcll_slices):
+        assert torch.equal(a.dclllayer.i2h.weight, b.dclllayer.i2h.weight)
+        assert torch.equal(b.dclllayer.i2h.weight, c.dclllayer.i2h.weight)       # run-to-run reproducible
+        assert torch.equal(a.dclllayer.i2h.state.eps1, b.dclllayer.i2h.state.eps1)
+        assert np.array_equal(np.array(a.clout), np.array(b.clout))
+
+
+def test_f16x2_bench_config_teacher_forced():
+    """The benchmarked configuration (128x128, B = 64, learn_window: fused next-layer trace, conv_mma2, wgrad_tc2p in CTA pairs)
+    in 'f16x2' mode, teacher-forced against the oracle for three post-burn-in steps."""
+    from snn_modulation_classification_b200.dcll.pytorch_libdcll import SpikeCells
+    B, K, lr, burnin, W, steps = 64, 24, 1e-6, 2, 128, 5
+    net, onet = build_pair("radio_ml_conv", (1, W, W), B, K, arp=0.0, burnin=burnin, lr=lr)
+    net.set_precision("f16x2")
+    g = torch.Generator().manual_seed(11)
+    xs = (torch.randn(B, 2, 1, 1024, generator=g) * 0.4).float()
+    y = O.to_one_hot(torch.randint(0, K, (B,), generator=g), K)
+    cells_np = O.encode_cells(xs.numpy(), W, W, t_start=17, max_duration=steps)
+    frames = torch.from_numpy(O.cells_to_frames(cells_np, W, W))
+    cells = SpikeCells(torch.from_numpy(cells_np).cuda(), W, W)
+    yc = y.cuda()
+    net.reset()
+    onet.reset()
+    for t in range(steps):
+        force_state(net, onet)
+        onet.learn(frames[t], y)
+        clout = net.learn_window(SpikeCells(cells.cells[t:t + 1].contiguous(), W, W), yc)
+        for i, s in enumerate(net.dcll_slices):
+            st, fo = s.dclllayer.i2h.state, onet.last[i]
+            if i == 0:
+                assert torch.equal(st.eps0.cpu(), fo.state.eps0) and torch.equal(st.eps1.cpu(), fo.state.eps1), (t, i)
+            else:
+                # layer i's traces are exact wherever layer i-1's spike agrees with the oracle's
+                assert float((st.eps0.cpu() != fo.state.eps0).float().mean()) <= FLIP_TOL, (t, i, "upstream spike flips")
+                assert float((st.eps1.cpu() != fo.state.eps1).float().mean()) <= FLIP_TOL, (t, i)
+            agree = float((clout[0, i].cpu().numpy() == np.asarray(onet.clout[i][-1])).mean()) if len(onet.clout[i]) else 1.0
+            assert agree >= 0.95, (t, i, "clout", agree)
+            if onet.iters[i] >= burnin:
+                dw = (s.dclllayer.i2h.weight.detach().cpu() - onet.params[i].weight).abs()
+                frac = float((dw > 0.5 * lr).float().mean())
+                assert float(dw.mean()) <= 2e-2 * lr and frac <= 5e-3 and float(dw.max()) <= 2.1 * lr, \
+                    (t, i, float(dw.max()) / lr, float(dw.mean()) / lr, frac)
+
+
+def test_f16x2_inference_free_running_flip_rate_and_votes():
+    """Free-running 3-layer inference over 150 timesteps: flip rate per layer and vote agreement vs the FP32 oracle."""
+    from snn_modulation_classification_b200.data.utils import iq2spiketrain
+    B, K, T, W = 16, 24, 150, 16
+    net, onet = build_pair("radio_ml_conv", (1, W, W), B, K, arp=0.0, train=False)
+    net.set_precision("f16x2")
+    g = torch.Generator().manual_seed(9)
+    xs = (torch.randn(B, 2, 1, 1024, generator=g) * 0.4).float()
+    y = O.to_one_hot(torch.randint(0, K, (B,), generator=g), K)
+    np.random.seed(1)
+    cells, tgt = iq2spiketrain(xs, y, out_w=W, out_h=W, max_duration=T, as_cells=True)
+    frames = cells.dense()
+    net.reset()
+    onet.reset()
+    fl = np.zeros(2)
+    for t in range(T):
+        net.test(frames[t])
+        onet.test(frames[t].cpu())
+        for i in range(2):
+            fl[i] += float((net.dcll_slices[i].dclllayer._ctx[1]["spikes"].cpu() != onet.last[i].spikes).float().mean())
+    assert (fl / T).max() <= FLIP_TOL, fl / T
+    for i, s in enumerate(net.dcll_slices):
+        agree = (np.array(s.clout) == np.array(onet.clout[i])).mean()
+        assert agree >= 0.98, (i, agree)

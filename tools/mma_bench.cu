@@ -19,6 +19,8 @@ struct Cfg {
     int swz;            // 0: SWIZZLE_NONE canonical layout, 2: SWIZZLE_128B, 4: 64B, 6: 32B (descriptor bits 61..63), K-major
     int a_mn;           // 1: A is MN-major (the weight-gradient kernels: M = (kernel row, channel) contiguous), SWIZZLE_NONE
     int ts;             // 1: A comes from tensor memory (TS mode: tcgen05.mma [d], [a_tmem], b_desc), B from shared memory
+    int f16;            // 1: fp16 x fp16 operands instead of bf16 x bf16
+    int b256;           // 1: B as the weight-gradient kernels stage it (N groups 256 B apart, the two K chunks 128 B apart)
 };
 
 template <int TS>
@@ -46,8 +48,10 @@ __global__ void __launch_bounds__(256, 1) bench(Cfg c, long long *out) {
         const uint32_t sbo_sw = c.swz == 2 ? 1024 : (c.swz == 4 ? 512 : 256);
         const uint32_t A_HI = c.swz ? (desc_hi(sbo_sw) | swz) : desc_hi(352), B_HI = c.swz ? (desc_hi(sbo_sw) | swz) : desc_hi(128);
         const uint32_t i64 = idesc_bf16(128, 64, c.a_mn != 0, false), i32 = idesc_bf16(128, 32, c.a_mn != 0, false);
-        const uint32_t iN = idesc_bf16(128, c.nsize, c.a_mn != 0, false);
+        const uint32_t iN = c.f16 ? idesc_f16a(128, c.nsize, c.a_mn != 0, false) : idesc_bf16(128, c.nsize, c.a_mn != 0, false);
         const uint32_t a_base_mn = desc_lo(smem_u32(smem), 128);      // MN-major: LBO = next 8 K rows, SBO (352) = next 8 M elements
+        const uint32_t b_base256 = desc_lo(smem_u32(smem + 128 * 1024), 128);
+        const uint32_t B_HI256 = desc_hi(256);
         __syncwarp();
         t0 = clock64();
         if (elected) {
@@ -66,7 +70,7 @@ __global__ void __launch_bounds__(256, 1) bench(Cfg c, long long *out) {
                     const uint32_t d = dbase + (((kk >> 1) & acc_mask) * acc_cols);
                     const uint32_t sh = c.swz ? ((kk >> 1) & sh_mask & 3) * 2 : ((kk >> 1) & sh_mask);
                     const uint64_t a = desc(A_HI, (c.a_mn ? a_base_mn : a_base) + sh + ((u & 1) ? lo_off : 0));
-                    const uint64_t b = desc(B_HI, b_base + (c.swz ? (sh & 3) * 2 : (sh & 7) * 256));
+                    const uint64_t b = c.b256 ? desc(B_HI256, b_base256 + (sh & 3) * 256) : desc(B_HI, b_base + (c.swz ? (sh & 3) * 2 : (sh & 7) * 256));
                     const uint32_t id = c.pair ? ((u & 1) ? i32 : i64) : iN;
                     if (TS) {
                         // A = 128 lanes x 8 columns (16 bf16) of tensor memory, columns 448.. (never written: timing only)
@@ -204,6 +208,33 @@ int main() {
             }
         }
         printf("A MN-major N=%3d issuers=%d | %.1f cycles per MMA (issuer 0)\n", c.nsize, c.issuers, (double)out[0] / c.n);
+    }
+    printf("\nAccumulator rotation: consecutive MMA pairs go to n_acc different accumulators (N = 128: 128 columns each)\n");
+    const Cfg cacc[] = {{4096, 1, 0, 128, 1, 1, 0, 0, 0, 0}, {4096, 2, 0, 128, 1, 1, 0, 0, 0, 0}, {4096, 4, 0, 128, 1, 1, 0, 0, 0, 0},
+                        {4096, 4, 0, 128, 1, 1, 0, 0, 1, 0}, {4096, 2, 0, 64, 1, 1, 0, 0, 0, 0}, {4096, 4, 0, 64, 1, 1, 0, 0, 0, 0},
+                        {4096, 8, 0, 64, 1, 1, 0, 0, 0, 0}};
+    for (const Cfg &c : cacc) {
+        for (int rep = 0; rep < 2; ++rep) {
+            bench<0><<<148, 256, 200 * 1024>>>(c, out);
+            if (cudaDeviceSynchronize() != cudaSuccess) {
+                printf("CUDA error: %s\n", cudaGetErrorString(cudaGetLastError()));
+                return 1;
+            }
+        }
+        printf("n_acc=%d N=%3d A %s-major | %.1f cycles per MMA\n", c.n_acc, c.nsize, c.a_mn ? "MN" : "K", (double)out[0] / c.n);
+    }
+    printf("\nfp16 operands / weight-gradient B layout (N = 128, A MN-major)\n");
+    const Cfg cf[] = {{4096, 4, 0, 128, 1, 1, 0, 0, 1, 0, 0, 0}, {4096, 4, 0, 128, 1, 1, 0, 0, 1, 0, 1, 0}, {4096, 4, 0, 128, 1, 1, 0, 0, 1, 0, 0, 1},
+                      {4096, 4, 0, 128, 1, 1, 0, 0, 1, 0, 1, 1}, {4096, 2, 0, 128, 1, 2, 0, 0, 1, 0, 1, 1}, {4096, 4, 0, 128, 1, 1, 0, 0, 0, 0, 1, 0}};
+    for (const Cfg &c : cf) {
+        for (int rep = 0; rep < 2; ++rep) {
+            bench<0><<<148, 256, 200 * 1024>>>(c, out);
+            if (cudaDeviceSynchronize() != cudaSuccess) {
+                printf("CUDA error: %s\n", cudaGetErrorString(cudaGetLastError()));
+                return 1;
+            }
+        }
+        printf("f16=%d b256=%d A %s-major issuers=%d | %.1f cycles per MMA\n", c.f16, c.b256, c.a_mn ? "MN" : "K", c.issuers, (double)out[0] / c.n);
     }
     printf("\nTS mode (A in tensor memory, B = N x 16 bf16 from shared memory)\n");
     const Cfg cts[] = {{4096, 1, 0, 32, 1, 1, 0, 0, 0, 1}, {4096, 1, 0, 64, 1, 1, 0, 0, 0, 1}, {4096, 1, 0, 128, 1, 1, 0, 0, 0, 1},
