@@ -179,6 +179,83 @@ __global__ void __launch_bounds__(8 * wg_ci_t(KH) * KH) wgrad_kernel(const WgP p
     }
 }
 
+// Tail shared by the two reducers: thread (sl == 0, element i) holds the combined gradient in red[.][e]; Adam on the element,
+// kernel-side weight copies, and -- F16X2 (w_exp != null) -- the fp16 image with the device-tracked exponent:
+//   * the image written here is fp16 {hi,lo} of w * 2^k, k = w_exp[1], read by every block at its start;
+//   * every block folds max |w_new| into w_exp[3] (bit pattern of a non-negative float orders like the float; the maximum does
+//     not depend on the order, so this stays deterministic);
+//   * the LAST block to finish (ticket in w_exp[2]) publishes slot 0 = the exponent this launch wrote the image with -- what the
+//     next convolution must undo -- and slot 1 = the exponent for the next image from this step's maximum, and resets 2 and 3.
+//     It is the only writer of the slots, and by then every other block has read slot 1.
+__device__ __forceinline__ void reduce_adam_tail(float (&red)[4][64], int n_tot, int nW, int Cout, int CoutPad, int CinKK,
+                                                 float *__restrict__ w, float *__restrict__ wt, float *__restrict__ bias,
+                                                 float *__restrict__ m_w, float *__restrict__ v_w, float *__restrict__ m_b,
+                                                 float *__restrict__ v_b, float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
+                                                 const AdamScalars &sc, __nv_bfloat16 *__restrict__ w_mma, int Cin, int KHKW, int KW,
+                                                 int *__restrict__ w_exp, int kexp) {
+    const int e = threadIdx.x & 63, sl = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + e;
+    float wabs = 0.f;
+    if (sl == 0 && i < n_tot) {
+        const float g = ((red[0][e] + red[1][e]) + red[2][e]) + red[3][e];
+        if (i < nW) {
+            if (grad_w) grad_w[i] = g;
+            if (apply) {
+                float wv = w[i], m = m_w[i], v = v_w[i];
+                adam_elem(wv, g, m, v, sc);
+                w[i] = wv, m_w[i] = m, v_w[i] = v;
+                wabs = fabsf(wv);
+                int co = i / CinKK, r = i - co * CinKK;
+                wt[(size_t)r * CoutPad + co] = wv;
+                if (w_mma) {   // {hi,lo} copy in the tcgen05 B-operand layout [tap][ci/8][{hi,lo}][co][8] (conv_fwd_tc.cu)
+                    const int ci = r / KHKW, tap = r - ci * KHKW;
+                    size_t o = (size_t)tap * (2 * Cin * Cout) + ((size_t)(ci >> 3) * 2 * Cout + co) * 8 + (ci & 7);
+                    if (Cin == 1) o = ((size_t)(tap / KW) * 2 * Cout + co) * 8 + tap % KW;   // [kh][part][co][8 column shifts]
+                    if (w_exp) {
+                        // (the exponent is one step old: 2^8 of headroom; a weight that outgrows it within ONE step saturates)
+                        const float vs = fminf(fmaxf(__fmul_rn(wv, pow2i(kexp)), -65504.f), 65504.f);
+                        const __half hi = __float2half_rn(vs);
+                        reinterpret_cast<__half *>(w_mma)[o] = hi;
+                        reinterpret_cast<__half *>(w_mma)[o + (size_t)Cout * 8] = __float2half_rn(vs - __half2float(hi));
+                    } else {
+                        __nv_bfloat16 hi = __float2bfloat16_rn(wv);
+                        __nv_bfloat16 lo = __float2bfloat16_rn(wv - __bfloat162float(hi));
+                        w_mma[o] = hi;
+                        w_mma[o + (size_t)Cout * 8] = lo;
+                    }
+                }
+            }
+        } else {
+            int co = i - nW;
+            if (grad_b) grad_b[co] = g;
+            if (apply) {
+                float wv = bias[co], m = m_b[co], v = v_b[co];
+                adam_elem(wv, g, m, v, sc);
+                bias[co] = wv, m_b[co] = m, v_b[co] = v;
+            }
+        }
+    }
+    if (w_exp && apply) {
+        if (sl == 0) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wabs = fmaxf(wabs, __shfl_xor_sync(0xffffffffu, wabs, o));
+            if ((threadIdx.x & 31) == 0 && wabs > 0.f) atomicMax(reinterpret_cast<unsigned *>(w_exp + 3), __float_as_uint(wabs));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const int ticket = atomicAdd(w_exp + 2, 1);
+            if (ticket == (int)gridDim.x - 1) {
+                __threadfence();
+                const unsigned mb = atomicExch(reinterpret_cast<unsigned *>(w_exp + 3), 0u);
+                w_exp[0] = kexp;
+                w_exp[1] = weight_exp_for(__uint_as_float(mb));
+                w_exp[2] = 0;
+            }
+        }
+    }
+}
+
 // grad = sum_s partial[s] (fixed order) ; Adam ; W, W^T, moments
 __global__ void __launch_bounds__(256) reduce_adam_kernel(const float *__restrict__ partial, int S, int n_tot, int nW,
                                                           int Cout, int CoutPad, int CinKK, float *__restrict__ w,
@@ -186,47 +263,22 @@ __global__ void __launch_bounds__(256) reduce_adam_kernel(const float *__restric
                                                           float *__restrict__ m_w, float *__restrict__ v_w,
                                                           float *__restrict__ m_b, float *__restrict__ v_b,
                                                           float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
-                                                          AdamScalars sc, __nv_bfloat16 *__restrict__ w_mma, int Cin, int KHKW, int KW) {
+                                                          AdamScalars sc, __nv_bfloat16 *__restrict__ w_mma, int Cin, int KHKW, int KW,
+                                                          int *__restrict__ w_exp) {
     pdl_entry();
     // CTA = 64 elements x 4 slices of the partial blocks (a single serial walk over ~150 blocks was pure load latency);
     // the slices are combined in a fixed order, so the result stays bit-reproducible
     __shared__ float red[4][64];
     const int e = threadIdx.x & 63, sl = threadIdx.x >> 6;
     const int i = blockIdx.x * 64 + e;
+    const int kexp = w_exp ? *reinterpret_cast<volatile int *>(w_exp + 1) : 0;
     float g = 0.f;
     if (i < n_tot)
         for (int s = sl; s < S; s += 4) g += __ldg(partial + (size_t)s * n_tot + i);
     red[sl][e] = g;
     __syncthreads();
-    if (sl != 0 || i >= n_tot) return;
-    g = ((red[0][e] + red[1][e]) + red[2][e]) + red[3][e];
-    if (i < nW) {
-        if (grad_w) grad_w[i] = g;
-        if (apply) {
-            float wv = w[i], m = m_w[i], v = v_w[i];
-            adam_elem(wv, g, m, v, sc);
-            w[i] = wv, m_w[i] = m, v_w[i] = v;
-            int co = i / CinKK, r = i - co * CinKK;
-            wt[(size_t)r * CoutPad + co] = wv;
-            if (w_mma) {   // bf16 {hi,lo} copy in the tcgen05 B-operand layout [tap][ci/8][{hi,lo}][co][8] (conv_fwd_tc.cu)
-                const int ci = r / KHKW, tap = r - ci * KHKW;
-                __nv_bfloat16 hi = __float2bfloat16_rn(wv);
-                __nv_bfloat16 lo = __float2bfloat16_rn(wv - __bfloat162float(hi));
-                size_t o = (size_t)tap * (2 * Cin * Cout) + ((size_t)(ci >> 3) * 2 * Cout + co) * 8 + (ci & 7);
-                if (Cin == 1) o = ((size_t)(tap / KW) * 2 * Cout + co) * 8 + tap % KW;   // [kh][part][co][8 column shifts]
-                w_mma[o] = hi;
-                w_mma[o + (size_t)Cout * 8] = lo;
-            }
-        }
-    } else {
-        int co = i - nW;
-        if (grad_b) grad_b[co] = g;
-        if (apply) {
-            float wv = bias[co], m = m_b[co], v = v_b[co];
-            adam_elem(wv, g, m, v, sc);
-            bias[co] = wv, m_b[co] = m, v_b[co] = v;
-        }
-    }
+    reduce_adam_tail(red, n_tot, nW, Cout, CoutPad, CinKK, w, wt, bias, m_w, v_w, m_b, v_b, grad_w, grad_b, apply, sc, w_mma, Cin, KHKW,
+                     KW, w_exp, kexp);
 }
 
 // Same reduction + Adam tail for the partial blocks of wgrad_tc2_kernel (wgrad_tc2.cu): one compact block per CTA,
@@ -249,7 +301,6 @@ __global__ void __launch_bounds__(256) reduce_adam_rp_kernel(const float *__rest
     // F16X2: the image written below is fp16 {hi,lo} of w * 2^k, k = w_exp[1] -- read by every block before any block can have
     // finished (the last block to finish is the only writer of the slots, see the end of the kernel)
     const int kexp = w_exp ? *reinterpret_cast<volatile int *>(w_exp + 1) : 0;
-    float wabs = 0.f;
     float g = 0.f;
     if (i < nW) {
         const int cc = i / KHKW, tap = i - cc * KHKW;            // cc = co * Cin + ci
@@ -267,66 +318,8 @@ __global__ void __launch_bounds__(256) reduce_adam_rp_kernel(const float *__rest
     }
     red[sl][e] = g;
     __syncthreads();
-    if (sl == 0 && i < n_tot) {
-    g = ((red[0][e] + red[1][e]) + red[2][e]) + red[3][e];
-    if (i < nW) {
-        if (grad_w) grad_w[i] = g;
-        if (apply) {
-            float wv = w[i], m = m_w[i], v = v_w[i];
-            adam_elem(wv, g, m, v, sc);
-            w[i] = wv, m_w[i] = m, v_w[i] = v;
-            wabs = fabsf(wv);
-            int co = i / CinKK, r = i - co * CinKK;
-            wt[(size_t)r * CoutPad + co] = wv;
-            if (w_mma) {
-                const int ci = r / KHKW, tap = r - ci * KHKW;
-                size_t o = (size_t)tap * (2 * Cin * Cout) + ((size_t)(ci >> 3) * 2 * Cout + co) * 8 + (ci & 7);
-                if (w_exp) {
-                    // (the exponent is one step old: 2^8 of headroom; a weight that outgrows it within ONE step saturates)
-                    const float vs = fminf(fmaxf(__fmul_rn(wv, pow2i(kexp)), -65504.f), 65504.f);
-                    const __half hi = __float2half_rn(vs);
-                    reinterpret_cast<__half *>(w_mma)[o] = hi;
-                    reinterpret_cast<__half *>(w_mma)[o + (size_t)Cout * 8] = __float2half_rn(vs - __half2float(hi));
-                } else {
-                    __nv_bfloat16 hi = __float2bfloat16_rn(wv);
-                    __nv_bfloat16 lo = __float2bfloat16_rn(wv - __bfloat162float(hi));
-                    w_mma[o] = hi;
-                    w_mma[o + (size_t)Cout * 8] = lo;
-                }
-            }
-        }
-    } else {
-        int co = i - nW;
-        if (grad_b) grad_b[co] = g;
-        if (apply) {
-            float wv = bias[co], m = m_b[co], v = v_b[co];
-            adam_elem(wv, g, m, v, sc);
-            bias[co] = wv, m_b[co] = m, v_b[co] = v;
-        }
-    }
-    }
-    // F16X2: running max |w| of this step (bit pattern of a non-negative float orders like the float) and, in the LAST block to
-    // finish, the hand-over: slot 0 = the exponent this launch wrote the image with (what the next convolution must undo),
-    // slot 1 = the exponent for the next image from this step's maximum.  Deterministic: the maximum does not depend on the order.
-    if (w_exp && apply) {
-        if (sl == 0) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) wabs = fmaxf(wabs, __shfl_xor_sync(0xffffffffu, wabs, o));
-            if ((threadIdx.x & 31) == 0 && wabs > 0.f) atomicMax(reinterpret_cast<unsigned *>(w_exp + 3), __float_as_uint(wabs));
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            const int ticket = atomicAdd(w_exp + 2, 1);
-            if (ticket == (int)gridDim.x - 1) {
-                __threadfence();
-                const unsigned mb = atomicExch(reinterpret_cast<unsigned *>(w_exp + 3), 0u);
-                w_exp[0] = kexp;
-                w_exp[1] = weight_exp_for(__uint_as_float(mb));
-                w_exp[2] = 0;
-            }
-        }
-    }
+    reduce_adam_tail(red, n_tot, nW, Cout, CoutPad, CinKK, w, wt, bias, m_w, v_w, m_b, v_b, grad_w, grad_b, apply, sc, w_mma, Cin, KHKW,
+                     KW, w_exp, kexp);
 }
 
 static int wg_n_ci_chunks(const dcll_conv_layer *L) {
@@ -389,10 +382,11 @@ int launch_bucket_adam(const dcll_conv_layer *L, dcll_train_args *a, const float
         ProfScope ps(KC_ADAM, 0, st);
         launch_k(reduce_adam_kernel, ceil_div(n_tot, 64), 256, 0, st, bucket, 1, n_tot, g.nW, L->Cout, g.CoutPad, L->Cin * L->KH * L->KW,
                  L->weight, L->weight_t, L->bias, o.m_w, o.v_w, o.m_b, o.v_b, (float *)nullptr, (float *)nullptr, 1, sc,
-                 (L->quantized || prec_f16(L)) ? nullptr : reinterpret_cast<__nv_bfloat16 *>(L->weight_mma), L->Cin, L->KH * L->KW, L->KW);
+                 L->quantized ? nullptr : reinterpret_cast<__nv_bfloat16 *>(L->weight_mma), L->Cin, L->KH * L->KW, L->KW,
+                 (prec_f16(L) && !L->quantized) ? L->w_exp : (int *)nullptr);   // F16X2: same image / exponent protocol as the single-GPU step
         DCLL_LAUNCH_OK("reduce_adam_kernel");
         a->adam_i2h.step += 1;
-        if (L->quantized || prec_f16(L)) {                   // (F16X2: the fp16 image and its exponent come from the synchronisation path)
+        if (L->quantized) {
             int rc = sync_kernel_weights(L, st);
             if (rc != DCLL_OK) return rc;
         }
@@ -460,7 +454,7 @@ int launch_wgrad(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st) 
                                                                o.m_w, o.v_w, o.m_b, o.v_b, a->grad_w, a->grad_b,
                                                                a->apply_update, sc,
                                                                L->quantized ? nullptr : reinterpret_cast<__nv_bfloat16 *>(L->weight_mma),
-                                                               L->Cin, L->KH * L->KW, L->KW);
+                                                               L->Cin, L->KH * L->KW, L->KW, (int *)nullptr);
     DCLL_LAUNCH_OK("reduce_adam_kernel");
     // reduce_adam_kernel refreshed weight_t and the tensor-core split itself; only the quantised image needs a pass
     if (a->apply_update && L->quantized) return sync_kernel_weights(L, st);

@@ -65,7 +65,7 @@ def _worker(rank, world, port, precision, out_q):
 
 
 @two_gpus
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16x2"])
 def test_dp_two_gpus_matches_single_process(precision):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
@@ -129,7 +129,7 @@ def _worker_single(port, precision, out_q):
 single_gpu = pytest.mark.skipif(torch.cuda.device_count() < 1, reason="needs a GPU")
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16x2"])
 def test_dp_driver_single_rank_equals_learn_window(precision):
     port = _free_port()
     ctx = mp.get_context("spawn")

@@ -160,24 +160,26 @@ def _train_eval(mode, eval_modes, seed, snr, res=16, B=256, T=300, burnin=50, n_
     return out
 
 
+@pytest.mark.parametrize("tc", ["bf16x3", "f16x2"])
 @pytest.mark.parametrize("snr", [6.0, 18.0])
-def test_accuracy_same_weights_within_half_point(snr):
+def test_accuracy_same_weights_within_half_point(snr, tc):
     """Accuracy clause, the part that is not chaotic: ONE set of trained weights (trained in either mode), held-out vote
-    accuracy of the FP32 and the bf16x3 inference paths on 8192 synthetic records -> within 0.5 pt per layer.
+    accuracy of the FP32 and the tensor-core (bf16x3 / f16x2) inference paths on 8192 synthetic records -> within 0.5 pt per layer.
     (1024 records are too few to resolve 0.5 pt: a handful of marginal votes that change either way give a paired standard
     error of ~0.5 pt -- measured 0.3-0.7 pt apart at 6 dB; with 8192 records that error is ~0.2 pt.)  The per-sample votes of the
     two paths must also agree on >= 97 % of the records in every layer."""
-    for train_mode in ("fp32", "bf16x3"):
-        acc = _train_eval(train_mode, ("fp32", "bf16x3"), seed=1, snr=snr, n_test=32, votes=True)
-        d = np.abs(acc["fp32"] - acc["bf16x3"])
-        agree = (acc["fp32_votes"] == acc["bf16x3_votes"]).mean(1)
-        print("trained in %s at %g dB: fp32 %s bf16x3 %s vote agreement %s" % (train_mode, snr, np.round(acc["fp32"], 4),
-                                                                               np.round(acc["bf16x3"], 4), np.round(agree, 4)))
-        assert d.max() <= 0.005 + 1e-9, (train_mode, snr, acc["fp32"], acc["bf16x3"])
+    for train_mode in ("fp32", tc):
+        acc = _train_eval(train_mode, ("fp32", tc), seed=1, snr=snr, n_test=32, votes=True)
+        d = np.abs(acc["fp32"] - acc[tc])
+        agree = (acc["fp32_votes"] == acc[tc + "_votes"]).mean(1)
+        print("trained in %s at %g dB: fp32 %s %s %s vote agreement %s" % (train_mode, snr, np.round(acc["fp32"], 4), tc,
+                                                                           np.round(acc[tc], 4), np.round(agree, 4)))
+        assert d.max() <= 0.005 + 1e-9, (train_mode, snr, acc["fp32"], acc[tc])
         assert agree.min() >= 0.97, agree
 
 
-def test_accuracy_trained_per_mode_seed_sweep():
+@pytest.mark.parametrize("tc_mode", ["bf16x3", "f16x2"])
+def test_accuracy_trained_per_mode_seed_sweep(tc_mode):
     """Accuracy clause through TRAINING in each mode.  Single runs cannot be compared point for point: training is
     chaotic (two FP32 runs that differ only in the summation order of the weight-gradient partials end 4.6 pt apart at one
     layer), so the claim is statistical: over five initialisation seeds at 6 dB the PAIRED per-layer
@@ -186,11 +188,11 @@ def test_accuracy_trained_per_mode_seed_sweep():
     or statistically indistinguishable from no difference."""
     seeds = (1, 2, 3, 4, 5)
     fp = np.array([_train_eval("fp32", ("fp32",), sd, 6.0)["fp32"] for sd in seeds])
-    tc = np.array([_train_eval("bf16x3", ("bf16x3",), sd, 6.0)["bf16x3"] for sd in seeds])
+    tc = np.array([_train_eval(tc_mode, (tc_mode,), sd, 6.0)[tc_mode] for sd in seeds])
     d = tc - fp                                            # [seed, layer]
     mean, se = d.mean(0), d.std(0, ddof=1) / np.sqrt(len(seeds))
-    print("fp32 mean %s  bf16x3 mean %s  paired diff mean %s  SE %s" % (np.round(fp.mean(0), 4), np.round(tc.mean(0), 4),
-                                                                       np.round(mean, 4), np.round(se, 4)))
+    print("fp32 mean %s  %s mean %s  paired diff mean %s  SE %s" % (np.round(fp.mean(0), 4), tc_mode, np.round(tc.mean(0), 4),
+                                                                   np.round(mean, 4), np.round(se, 4)))
     bound = np.maximum(0.005, 2.776 * se)
     assert (np.abs(mean) <= bound + 1e-9).all(), (mean, se, bound)
     # and the two modes learn equally well in absolute terms: best layer well above chance (1/24) in every seed
