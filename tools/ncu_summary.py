@@ -38,7 +38,7 @@ def launches(path):
         if hdr and len(r) == len(hdr):
             d = dict(zip(hdr, r))
             if d.get("Metric Name") == "gpu__time_duration.sum":
-                name = re.sub(r"[<(].*", "", d["Kernel Name"]).replace("void ", "")
+                name = re.sub(r"\(.*", "", d["Kernel Name"].replace("void ", "")).replace("dcll::", "")
                 agg[name][0] += 1
                 agg[name][1] += float(d["Metric Value"].replace(",", "")) * scale.get(d["Metric Unit"], 1.0)
     tot = sum(v[1] for v in agg.values())

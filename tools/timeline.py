@@ -40,7 +40,7 @@ def main():
     bench.WORKLOADS[a.workload] = tuple(w)
     spec, res, batch, train, arp, burnin, _ = bench.workload(a.workload, 1)
     net = bench.build_net(a.workload, 1)
-    net.set_precision(os.environ.get("DCLL_PRECISION", "bf16x3"))
+    net.set_precision(os.environ.get("DCLL_PRECISION", "f16x2"))
     x, y = bench.synth(batch, 1)
     np.random.seed(1)
     cells, _ = iq2spiketrain(x.cuda(), y.cuda(), out_w=res, out_h=res, min_I=-1, max_I=1, min_Q=-1, max_Q=1, max_duration=a.timesteps,
