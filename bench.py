@@ -12,7 +12,10 @@ and Adam step per layer per timestep), or of inference for the infer workloads. 
                ConvNetwork.learn_window -> device vote -> D2H of the per-sample predictions, all timed
   roofline     the kernel class with the largest share of the step (CUDA events sampled inside the timed region on the
                launching stream), plus the other big kernels under roofline.kernels
+  precision    default f16x2: tcgen05 tensor cores, fp16 traces against split-fp16 weights / local gradients, two products per
+               MAC (spike-flip rate <= 1e-3, held-out accuracy within 0.5 pt of FP32 -- both tested)
   fp32_mode    the same workload in the FP32-exact parity mode (BASELINE.json configs[0] says FP32), short run
+  bf16x3_mode  the same workload in the three-product split-bf16 tensor-core mode, short run
   other_workloads   the other BASELINE.json configs (mnist_conv, quantised radio_ml_conv_ref, 16x16 script geometry,
                inference sweep points), short runs through the same public API
   cpu_baseline the reference's own classes (oracle/_ref, vendored unmodified by oracle/make_ref.py) on the box's host

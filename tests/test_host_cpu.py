@@ -175,3 +175,32 @@ def test_every_kernel_waits_for_its_predecessor_and_every_launch_is_chained():
             assert "pdl_entry();" in body, "kernel near %s:%d has no pdl_entry()" % (os.path.basename(path), src[:m.start()].count("\n") + 1)
             n_kernels += 1
     assert n_kernels >= 30
+
+
+def test_f16x2_host_side_exponents_and_layer_selection(cpu_modules):
+    """'f16x2' host logic (no GPU): which layers get the fp16 form, and the power-of-two exponents the host derives --
+    trace image: 2^a_exp * tau_s/(1-alphas) * tau_m/(1-alpha) <= 2^15 (fp16 maximum 65504) and within a factor 2 of it;
+    gradient image: 2^g_exp * 16 * max|Wo| / (4 B) <= 2^14."""
+    import math
+    import types
+    import numpy as np
+    import torch
+    L, _ = cpu_modules
+    np.random.seed(0)
+    torch.manual_seed(0)
+    core = L.ContinuousConv2D(32, 32, kernel_size=7, padding=3, random_tau=False)
+    core.precision = "f16x2"
+    assert core.tensor_core_ok() and core.f16_ok(128, 128) and core.f16_ok(16, 16) and core.f16_ok(40, 24)
+    assert not core.f16_ok(21, 45) and not core.f16_ok(16, 20)            # odd conv height / conv width not a multiple of 8
+    first = L.ContinuousConv2D(1, 32, kernel_size=7, padding=3, random_tau=False)
+    first.precision = "f16x2"
+    assert first.tensor_core_ok() and not first.f16_ok(128, 128)          # one input channel keeps the split-bf16 kernels
+    a_exp = core._trace_exp()
+    bound = float(core.tau_s__dt / (1 - core.alphas) * core.tau_m__dt / (1 - core.alpha))
+    assert bound * 2.0 ** a_exp <= 32768.0 < bound * 2.0 ** (a_exp + 1)
+    lay = types.SimpleNamespace(i2o=torch.nn.Linear(8, 4))
+    g_exp = L.Conv2dDCLLlayer._grad_exp(lay, 64)
+    gb = float(lay.i2o.weight.detach().abs().max()) / (4 * 64) * 16
+    assert gb * 2.0 ** g_exp <= 16384.0 < gb * 2.0 ** (g_exp + 1)
+    assert L.Conv2dDCLLlayer._grad_exp(lay, 64) == g_exp                   # cached per (weight version, batch)
+    assert math.isfinite(a_exp) and math.isfinite(g_exp)
