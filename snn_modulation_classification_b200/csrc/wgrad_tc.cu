@@ -110,6 +110,24 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
         const int cgw = warp & 3;                 // channel group (of eps1 and of g_u) this warp stages
         const int l96 = ((warp >> 2) - 1) * 32 + lane;   // 0..95 within the group
         const size_t xcs = (size_t)p.H * p.W, gcs = (size_t)p.Hc * p.Wc;
+        static_assert(G::TH * G::TW <= 3 * 96, "three positions per loader thread and channel group");
+        // g_u values of one unit for this thread: positions l96, l96 + 96, l96 + 192 of the 16 x 16 tile x 8 channels
+        auto load_g = [&](int u, float (&v)[3][8]) {
+            const int b = u / tiles, tile = u - b * tiles;
+            const int th_i = tile / p.tiles_w, tw_i = tile - th_i * p.tiles_w;
+#pragma unroll
+            for (int h = 0; h < 3; ++h) {
+                const int itt = l96 + h * 96;
+                const int r = itt / G::TW, c = itt - r * G::TW;
+                const int oh = th_i * G::TH + r, ow = tw_i * G::TW + c;
+                const bool ok = itt < G::TH * G::TW && oh < p.Hc && ow < p.Wc;
+                const size_t off = ok ? ((size_t)(b * G::COUT + cgw * 8) * p.Hc + oh) * p.Wc + ow : 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[h][k] = ok ? __ldg(gg + off + k * gcs) : 0.f;
+            }
+        };
+        float gv[3][8];
+        if (u_first < p.n_units) load_g(u_first, gv);
         int i = 0;
         for (int u = u_first; u < p.n_units; u += u_step, ++i) {
             const int buf = i & 1;
@@ -207,36 +225,35 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
                     *reinterpret_cast<uint4 *>(dst + G::X_PART) = *reinterpret_cast<const uint4 *>(lo);
                 }
             }
-            // ---- g_u tile: [cog][row][col][8 co], bf16 hi | lo (zero outside the image)
-            for (int it = l96; it < G::TH * G::TW; it += 2 * 96) {
-                float v[2][8];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int itt = it + h * 96;
-                    const int r = itt / G::TW, c = itt - r * G::TW;
-                    const int oh = h0 + r, ow = w0 + c;
-                    const bool ok = itt < G::TH * G::TW && oh < p.Hc && ow < p.Wc;
-                    const size_t off = ok ? ((size_t)(b * G::COUT + cgw * 8) * p.Hc + oh) * p.Wc + ow : 0;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) v[h][k] = ok ? __ldg(gg + off + k * gcs) : 0.f;
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int itt = it + h * 96;
-                    if (itt >= G::TH * G::TW) continue;
-                    const int r = itt / G::TW, c = itt - r * G::TW;
-                    __align__(16) __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        if (grp == 0) gsum[k] += v[h][k];
-                        hi[k] = __float2bfloat16_rn(v[h][k]);
-                        lo[k] = __float2bfloat16_rn(v[h][k] - __bfloat162float(hi[k]));
-                    }
-                    unsigned char *dst = sG + cgw * G::G_PLANE + r * G::G_ROW + c * 16;
-                    *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
-                    *reinterpret_cast<uint4 *>(dst + G::G_PART) = *reinterpret_cast<const uint4 *>(lo);
-                }
+            // ---- g_u tile: [cog][row][col][8 co], bf16 hi | lo (zero outside the image).  The values of THIS unit were requested
+            //      while the previous one was converted (gv), so their DRAM latency is covered by that work and by the wait for
+            //      the free buffer above; the next unit's are requested now.  (Loading and converting in the same iteration left
+            //      the loaders waiting on every load: ncu long-scoreboard stalls at the first conversion, 1.4 TB/s.)
+            float gn[3][8];
+            {
+                const int un = u + u_step;
+                if (un < p.n_units) load_g(un, gn);
             }
+#pragma unroll
+            for (int h = 0; h < 3; ++h) {
+                const int itt = l96 + h * 96;
+                if (itt >= G::TH * G::TW) continue;
+                const int r = itt / G::TW, c = itt - r * G::TW;
+                __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (grp == 0) gsum[k] += gv[h][k];
+                    hi[k] = __float2bfloat16_rn(gv[h][k]);
+                    lo[k] = __float2bfloat16_rn(gv[h][k] - __bfloat162float(hi[k]));
+                }
+                unsigned char *dst = sG + cgw * G::G_PLANE + r * G::G_ROW + c * 16;
+                *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
+                *reinterpret_cast<uint4 *>(dst + G::G_PART) = *reinterpret_cast<const uint4 *>(lo);
+            }
+#pragma unroll
+            for (int h = 0; h < 3; ++h)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) gv[h][k] = gn[h][k];
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             fence_async_smem();   // this thread's smem writes -> async proxy
             __syncwarp();
