@@ -194,13 +194,24 @@ WsLayout ws_layout(const dcll_conv_layer *L);
 // Launchers implemented in the individual .cu files (all asynchronous on `st`).
 // write_spikes = false (window driver, tensor-core path): nobody reads this step's spike tensor -- the consumer is the trace
 // update fused into this launch's epilogue, or there is none (last layer) -- so the epilogue does not store it.
+// spike_io: SPK_WRITE as above; SPK_PACKED: the spikes leave as one uint16 word per (sample, 16 channels, position) in the
+// same buffer instead of 32 floats per position (window drivers, between two tensor-core layers: the consumer is the next layer's
+// trace kernel, which then reads 2 bytes instead of 32 per position and channel group); SPK_X_PACKED: this layer's input is
+// such a word array.  The per-step API always moves float spikes.
+enum { SPK_WRITE = 1, SPK_PACKED = 2, SPK_X_PACKED = 4 };
+bool tc_spikes_packable(const dcll_conv_layer *L, const dcll_conv_layer *next);
+static inline int spike_io_of(const dcll_conv_layer *layers, int l, int n_layers, bool fuse_next, bool trace_done) {
+    const bool read = l + 1 < n_layers && !fuse_next;
+    return (read ? SPK_WRITE : 0) | ((read && tc_spikes_packable(&layers[l], &layers[l + 1])) ? SPK_PACKED : 0) |
+           ((l > 0 && !trace_done && tc_spikes_packable(&layers[l - 1], &layers[l])) ? SPK_X_PACKED : 0);
+}
 int launch_conv_fwd(const dcll_conv_layer *L, const void *x, cudaStream_t st, const dcll_conv_layer *next = nullptr,
-                    bool trace_done = false, bool write_spikes = true);
+                    bool trace_done = false, int spike_io = SPK_WRITE);
 // tcgen05, split-bf16 x3.  Window driver only: `next` != null makes the epilogue also apply the NEXT layer's trace update
 // (its input is exactly the spike the epilogue thread just produced) and write that layer's operand image;
 // `trace_done` says the previous layer already did so for this one.
 int launch_conv_fwd_tc(const dcll_conv_layer *L, const void *x, cudaStream_t st, const dcll_conv_layer *next = nullptr,
-                       bool trace_done = false, bool write_spikes = true);
+                       bool trace_done = false, int spike_io = SPK_WRITE);
 bool tc_trace_fusable(const dcll_conv_layer *L, const dcll_conv_layer *next);
 int launch_weight_mma(const dcll_conv_layer *L, const float *w, cudaStream_t st);
 int sync_kernel_weights(const dcll_conv_layer *L, cudaStream_t st);   // weight -> weight_t / weight_mma (quantised or not)

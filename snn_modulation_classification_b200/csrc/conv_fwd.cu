@@ -416,10 +416,11 @@ int sync_kernel_weights(const dcll_conv_layer *L, cudaStream_t st) {
 }
 
 int launch_conv_fwd(const dcll_conv_layer *L, const void *x, cudaStream_t st, const dcll_conv_layer *next, bool trace_done,
-                    bool write_spikes) {
+                    int spike_io) {
     // "bf16x3" = tensor cores wherever a shape is instantiated; the rest stays on the FMA pipe
-    if (prec_tc(L) && tc_supported(L)) return launch_conv_fwd_tc(L, x, st, next, trace_done, write_spikes);
-    DCLL_REQUIRE(!next && !trace_done, DCLL_EINVAL, "fused next-layer trace needs the tensor-core path");
+    if (prec_tc(L) && tc_supported(L)) return launch_conv_fwd_tc(L, x, st, next, trace_done, spike_io);
+    DCLL_REQUIRE(!next && !trace_done && !(spike_io & (SPK_PACKED | SPK_X_PACKED)), DCLL_EINVAL,
+                 "fused next-layer trace / packed spikes need the tensor-core path");
     Geo g = geo_of(L);
     FwdP p;
     p.x = L->x_mode == DCLL_X_DENSE ? (const float *)x : nullptr;

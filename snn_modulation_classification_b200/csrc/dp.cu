@@ -27,7 +27,7 @@ namespace dcll {
 // defined in wgrad.cu / net.cu
 int launch_bucket_adam(const dcll_conv_layer *L, dcll_train_args *a, const float *bucket, cudaStream_t st);
 int dp_step_fwd(dcll_conv_layer *L, const void *x, const float *target, int loss_kind, int32_t *clout, cudaStream_t st,
-                const dcll_conv_layer *next, bool trace_done, bool write_spikes, int layer);
+                const dcll_conv_layer *next, bool trace_done, int spike_io, int layer);
 int dp_step_bwd(dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st, int layer);
 int dp_check(const dcll_conv_layer *layers, const dcll_train_args *train, int n_layers);
 
@@ -183,7 +183,7 @@ extern "C" __attribute__((visibility("default"))) int dcll_net_window_dp(dcll_dp
             const bool fuse_next = l + 1 < n_layers && tc_trace_fusable(L, &layers[l + 1]);
             const bool trace_done = l > 0 && tc_trace_fusable(&layers[l - 1], L);
             rc = dp_step_fwd(L, x, do_train ? tgt : nullptr, do_train ? train[l].loss_kind : 0, co, st, fuse_next ? &layers[l + 1] : nullptr,
-                             trace_done, l + 1 < n_layers && !fuse_next, l);
+                             trace_done, spike_io_of(layers, l, n_layers, fuse_next, trace_done), l);
             if (rc != DCLL_OK) return rc;
             if (do_train) {
                 rc = dp_step_bwd(L, &train[l], st, l);

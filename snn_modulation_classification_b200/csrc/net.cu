@@ -157,12 +157,12 @@ unsigned long long *timeline_buf(int kind) {
 int prof_layer() { return g_layer; }
 
 static int step_fwd(dcll_conv_layer *L, const void *x, const float *target, int loss_kind, int32_t *clout, float *loss_out,
-                    cudaStream_t st, const dcll_conv_layer *next = nullptr, bool trace_done = false, bool write_spikes = true) {
+                    cudaStream_t st, const dcll_conv_layer *next = nullptr, bool trace_done = false, int spike_io = SPK_WRITE) {
     prof_begin_layer_step();
     int rc;
     {
         ProfScope ps(KC_CONV_FWD, g_layer, st);
-        rc = launch_conv_fwd(L, x, st, next, trace_done, write_spikes);
+        rc = launch_conv_fwd(L, x, st, next, trace_done, spike_io);
     }
     if (rc != DCLL_OK) return rc;
     L->cur ^= 1;
@@ -210,9 +210,9 @@ static int check_train(const dcll_conv_layer *L, const dcll_train_args *a, const
 
 // entry points of the data-parallel driver (dp.cu) into the per-layer steps above
 int dp_step_fwd(dcll_conv_layer *L, const void *x, const float *target, int loss_kind, int32_t *clout, cudaStream_t st,
-                const dcll_conv_layer *next, bool trace_done, bool write_spikes, int layer) {
+                const dcll_conv_layer *next, bool trace_done, int spike_io, int layer) {
     g_layer = layer;
-    return step_fwd(L, x, target, loss_kind, clout, nullptr, st, next, trace_done, write_spikes);
+    return step_fwd(L, x, target, loss_kind, clout, nullptr, st, next, trace_done, spike_io);
 }
 int dp_step_bwd(dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st, int layer) {
     g_layer = layer;
@@ -516,10 +516,10 @@ extern "C" __attribute__((visibility("default"))) int dcll_net_window_stats(dcll
             // the trace update of layer l+1 rides in the epilogue of layer l's tensor-core convolution where that is free
             const bool fuse_next = l + 1 < n_layers && tc_trace_fusable(L, &layers[l + 1]);
             const bool trace_done = l > 0 && tc_trace_fusable(&layers[l - 1], L);
-            // the spike tensor of this step is stored only when somebody reads it: the next layer's own trace pass
-            const bool spikes_read = l + 1 < n_layers && !fuse_next;
+            // the spike tensor of this step is stored only when somebody reads it -- the next layer's own trace pass -- and then as
+            // packed bits between two tensor-core layers
             int rc = step_fwd(L, x, do_train ? tgt : nullptr, do_train ? train[l].loss_kind : 0, co, nullptr, st,
-                              fuse_next ? &layers[l + 1] : nullptr, trace_done, spikes_read);
+                              fuse_next ? &layers[l + 1] : nullptr, trace_done, spike_io_of(layers, l, n_layers, fuse_next, trace_done));
             if (rc != DCLL_OK) return rc;
             if (hist && (it % hist_every) == 0 && hist_n[l] < hist_cap) {          // DCLLBase.forward :658-661
                 Geo g = geo_of(L);
