@@ -571,6 +571,19 @@ __global__ void __launch_bounds__(256, 3) wout_grad_adam2_kernel(const float *__
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
     }
+    // the Adam tail reads w, m, v of this thread's outputs in dependent rounds: pull their lines into L2 now, while the batch streams
+    // (no measurable effect at 128x128, B = 64 -- 0.102 ms either way -- kept because it is free)
+    if (fok && apply) {
+#pragma unroll
+        for (int k = 0; k < KH; ++k) {
+            if (kbase + k < K) {
+                const size_t o = (size_t)(kbase + k) * F + f;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(wout + o));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(m_w + o));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(v_w + o));
+            }
+        }
+    }
     float2 acc[KH];
 #pragma unroll
     for (int k = 0; k < KH; ++k) acc[k] = make_float2(0.f, 0.f);
@@ -826,20 +839,33 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
             const float g_scale = prec_f16(L) ? pow2i(L->g_exp) : 0.f;   // F16X2: the image is fp16 {hi,lo} of g_u * 2^g_exp
             // 8 rows in flight per thread, next group prefetched: 128 registers, 2 CTAs per SM (4 rows at 3 CTAs per SM was slower)
             // image form of g_u (bf16 {hi,lo} planes in the same buffer) when the row-pair weight-gradient kernel consumes it
-#define RB2(KM)                                                                                                                    \
+#define RB2_M(KM, MB)                                                                                                              \
     do {                                                                                                                           \
         if (wgrad_tc2_supported(L)) {                                                                                              \
-            DCLL_SMEM_ATTR((readout_bwd2_kernel<KM, 8, 2, true>), ring_bytes);                                                     \
-            launch_k(readout_bwd2_kernel<KM, 8, 2, true>, grid1, 256, ring_bytes, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u, hw, slices, g_scale); \
+            DCLL_SMEM_ATTR((readout_bwd2_kernel<KM, 8, MB, true>), ring_bytes);                                                    \
+            launch_k(readout_bwd2_kernel<KM, 8, MB, true>, grid1, 256, ring_bytes, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u, hw, slices, g_scale); \
         } else {                                                                                                                   \
-            DCLL_SMEM_ATTR((readout_bwd2_kernel<KM, 8, 2, false>), ring_bytes);                                                    \
-            launch_k(readout_bwd2_kernel<KM, 8, 2, false>, grid1, 256, ring_bytes, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u, hw, slices, 0.f); \
+            DCLL_SMEM_ATTR((readout_bwd2_kernel<KM, 8, MB, false>), ring_bytes);                                                   \
+            launch_k(readout_bwd2_kernel<KM, 8, MB, false>, grid1, 256, ring_bytes, st, L->pv, L->wo, g_o, L->B, g.F, L->K, b_per, L->g_u, hw, slices, 0.f); \
         }                                                                                                                          \
+    } while (0)
+            // CTAs per SM: two.  With the rows in the cp.async ring instead of registers three fit for K <= 24 (80 registers, a few
+            // bytes of spill) but run SLOWER (measured, 128x128 B = 64: 0.084 / 0.121 ms against 0.075 / 0.102); DCLL_RB2_MINB=3 selects it
+            static int minb = -1;
+            if (minb < 0) {
+                const char *e = getenv("DCLL_RB2_MINB");
+                minb = (e && atoi(e) == 3) ? 3 : 2;
+            }
+#define RB2(KM)                  \
+    do {                         \
+        if (minb == 3 && KM <= 24) RB2_M(KM, 3); \
+        else RB2_M(KM, 2);       \
     } while (0)
             if (L->K <= 16) { RB2(16); }
             else if (L->K <= 24) { RB2(24); }
             else { RB2(32); }
 #undef RB2
+#undef RB2_M
         } else if (L->K <= 16)
             RB_LAUNCH(16, false, grid, b_per, nf, nf, nf, nf, nf, nf, nf, nf, 0, sc);
         else if (L->K <= 24)
