@@ -364,7 +364,11 @@ __global__ void __launch_bounds__(256, MINB) readout_bwd2_kernel(const float *__
         // warp = one channel of the group, lanes = 64 consecutive positions: the pv / Wo loads stay 256-byte contiguous per warp
         // (with lanes = 8 channels x 8 positions they were 8 scattered sectors: +0.02 ms per launch, measured); the 4-byte image
         // stores of a warp land as 16-byte runs in 8 lines, whose other runs come from the 7 sibling warps of this CTA
-        const int co8 = tid >> 5, c8 = pb * 8 + ((tid & 31) >> 2), pr = tid & 3;
+        // (round 2: a warp covers TWO adjacent channels x 32 positions instead of one x 64, so that the 4-byte image stores of a
+        //  warp fill whole 32-byte sectors -- the 16-byte runs of two adjacent channels are neighbours in the image; measured with
+        //  the stores removed they cost 0.023 ms per launch as half sectors, the conversions 0.012)
+        const int wq = tid >> 5, ln = tid & 31;
+        const int co8 = (wq & 3) * 2 + (ln >> 4), c8 = pb * 8 + (wq >> 2) * 4 + ((ln >> 2) & 3), pr = ln & 3;
         f = (cog * 8 + co8) * hw + c8 * 8 + 2 * pr;
         fok = c8 < chunks && f < F;
         img_word = ((cog * chunks + c8) * 8 + co8) * 4 + pr;
