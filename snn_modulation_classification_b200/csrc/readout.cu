@@ -832,7 +832,18 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
             RB_LAUNCH(32, true, grid, L->B, L->wout, L->bout, o.m_w, o.v_w, o.m_b, o.v_b, a->grad_wout, a->grad_bout, a->apply_update, sc);
     } else {
         // enough CTAs for >= 4 waves of 3 CTAs per SM (a 2.3-wave grid loses 23 % to the partial last wave): slice the batch
-        int slices = max(1, min(ceil_div(L->B, 32), ceil_div(4 * 3 * 148, fblk)));
+        // (packed kernel, round 2: with the pv rows in the cp.async ring a CTA's fixed cost -- its Wo columns and g_o rows, one DRAM
+        //  round trip before the first multiply -- is what more slices multiply; two waves of 2 CTAs per SM are enough.  Measured at
+        //  128x128, B = 64: one slice 0.066 / 0.083 ms against 0.074 / 0.089 with two.)
+        int slices = max(1, min(ceil_div(L->B, 32), ceil_div((packed ? 2 * 2 : 4 * 3) * 148, fblk)));
+        {
+            static int sl_env = -1;                                       // DCLL_RB2_SLICES=n: force the number of batch slices (A/B)
+            if (sl_env < 0) {
+                const char *e = getenv("DCLL_RB2_SLICES");
+                sl_env = e ? atoi(e) : 0;
+            }
+            if (sl_env > 0) slices = sl_env;
+        }
         int b_per = ceil_div(ceil_div(L->B, slices), 32) * 32;
         slices = ceil_div(L->B, b_per);
         dim3 grid(fblk, slices);
