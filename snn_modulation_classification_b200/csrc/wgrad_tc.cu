@@ -60,8 +60,19 @@ struct WgTcGeoT {
     static constexpr int BUF = X_BYTES + G_BYTES;            // one pipeline stage
     static constexpr int NT = 512;
     static constexpr int LOADER_WARPS = 12;                  // warps 4..15
-    static constexpr int SMEM = 2 * BUF + 128 + 16 * 8 * 4;
-    static constexpr int TMEM_COLS = NACC * ACC_COLS <= 256 ? 256 : 512;
+    // CIN = 1 with the forward's operand image (the shipped case): g_u is STREAMED -- 134 MB per launch against 32 MMAs per unit --
+    // so the loaders keep two units of raw fp32 g_u in flight in a thread-private cp.async ring (RAW_UNIT bytes per unit: 24
+    // values per loader thread) and the small X tiles in a ring of 4 slots, requested two units ahead (slots 0, 1 are the X
+    // areas of the two stage buffers, slots 2, 3 extra).  With the
+    // values prefetched into REGISTERS (first version) the six scoreboards of a warp alias: the first conversion of a unit
+    // waited for the loads of the NEXT unit issued just before it (ncu: 28 % of the samples on that F2F, 1.6 TB/s).
+    static constexpr int XRING = CIN == 1 ? 2 : 0, RAW_UNIT = CIN == 1 ? 24 * LOADER_WARPS * 32 * 4 : 0, RAW_SLOTS = 2;
+    static constexpr int XRING_OFF = 2 * BUF + 128 + 16 * 8 * 4, RAW_OFF = XRING_OFF + XRING * X_BYTES;
+    static constexpr int SMEM = RAW_OFF + RAW_SLOTS * RAW_UNIT;
+    static constexpr int NISS_ACC = CIN == 1 ? 2 : 1;        // CIN = 1: the two issuer warps take alternate rows into accumulators of their own
+    static constexpr int TMEM_COLS = NACC * NISS_ACC * ACC_COLS <= 256 ? 256 : 512;
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+    __host__ __device__ static constexpr int xslot(int i) { return (i & 3) < 2 ? (i & 3) * BUF : XRING_OFF + ((i & 3) - 2) * X_BYTES; }
     static_assert(G_PART == 4 * G_PLANE, "{hi,lo} x channel-group must be uniformly strided for the N = 2*Cout operand");
     static_assert(CIN == 32 || CIN == 1, "instantiated for 32 and 1 input channels");
 };
@@ -77,11 +88,14 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
     uint64_t *full = bars, *empty = bars + 2, *done = bars + 4;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
     float *bias_red = reinterpret_cast<float *>(smem + 2 * G::BUF + 128);   // [16 warps][8]
+    uint32_t *iss_used = tmem_slot + 2;                                      // [2]: issuer warp w has written its accumulator
+    const bool ring = G::CIN == 1 && p.img != nullptr;                       // streamed g_u (see WgTcGeoT)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) mbar_init(full + i, G::LOADER_WARPS), mbar_init(empty + i, 2);
         mbar_init(done, 2);
+        iss_used[0] = iss_used[1] = 0;
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -126,6 +140,92 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
                 for (int k = 0; k < 8; ++k) v[h][k] = ok ? __ldg(gg + off + k * gcs) : 0.f;
             }
         };
+        if (G::CIN == 1 && ring) {
+            // Lean instruction stream (the loaders, not DRAM, paced the first version: ~820 instructions per warp and unit, most of
+            // them address arithmetic): everything that does not depend on the unit is computed once per thread.
+            const int lt = tid - 128;                                        // 0..383
+            float *raw = reinterpret_cast<float *>(smem + G::RAW_OFF);
+            const uint32_t hw = (uint32_t)(p.H * p.W), gcs32 = (uint32_t)(p.Hc * p.Wc);
+            // X tile: only the halo rows 0..21 feed real kernel rows (dy <= 6); piece (row xr, column xc) of both parts
+            constexpr int XR_USED = G::TH + G::KH - 1;
+            const int xr = lt >> 4, xc = lt & 15;
+            const bool x_mine = xr < XR_USED;
+            const uint32_t x_dst = (uint32_t)(xr * G::X_RP + xc * 16);
+            // g_u: positions l96 + 96 h of the tile, 8 channels each (element offsets relative to the tile origin fit 32 bits)
+            int g_r[3], g_c[3];
+            uint32_t g_off[3], g_dst[3];
+#pragma unroll
+            for (int h = 0; h < 3; ++h) {
+                const int itt = l96 + h * 96;
+                g_r[h] = itt >> 4, g_c[h] = itt & 15;
+                g_off[h] = (uint32_t)((cgw * 8 * p.Hc + g_r[h]) * p.Wc + g_c[h]);
+                g_dst[h] = (uint32_t)(cgw * G::G_PLANE + g_r[h] * G::G_ROW + g_c[h] * 16);
+            }
+            const bool h2_mine = l96 + 192 < G::TH * G::TW;                  // the third position exists for l96 < 64 only
+            // group C_i = { X tile of the CTA's i-th unit -> X slot i & 3,  raw g_u of that unit -> raw slot i & 1 }
+            auto issue = [&](int u, int i) {
+                if (u < p.n_units) {
+                    const unsigned b = (unsigned)u / (unsigned)tiles, tile = (unsigned)u - b * (unsigned)tiles;
+                    const unsigned th_i = tile / (unsigned)p.tiles_w, tw_i = tile - th_i * (unsigned)p.tiles_w;
+                    const int h0 = (int)th_i * G::TH, w0 = (int)tw_i * G::TW;
+                    if (x_mine) {
+                        const int gh = h0 - p.padH + xr, gw = w0 + xc;
+                        const bool in = gh >= 0 && gh < p.H && gw < p.W;
+                        const uint4 *src = in ? p.img + (size_t)b * 2 * hw + (uint32_t)(gh * p.W + gw) : p.img;
+                        const uint32_t dst = smem_u32(smem + G::xslot(i)) + x_dst;
+                        const uint32_t sz = in ? 16u : 0u;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + G::X_PART), "l"(in ? src + hw : src), "r"(sz) : "memory");
+                    }
+                    const uint32_t rs = smem_u32(raw + (size_t)(i & 1) * (G::RAW_UNIT / 4) + lt);
+                    const float *tile0 = gg + ((size_t)b * G::COUT * p.Hc + h0) * p.Wc + w0;
+#pragma unroll
+                    for (int h = 0; h < 3; ++h) {
+                        if (h == 2 && !h2_mine) break;
+                        const bool ok = h0 + g_r[h] < p.Hc && w0 + g_c[h] < p.Wc;
+                        const float *src = ok ? tile0 + g_off[h] : gg;
+                        const uint32_t step = ok ? gcs32 : 0u, sz = ok ? 4u : 0u;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(rs + (h * 8 + k) * (G::LOADER_WARPS * 32 * 4)),
+                                         "l"(src + k * step), "r"(sz)
+                                         : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            issue(u_first, 0);
+            issue(u_first + u_step, 1);
+            int i = 0;
+            for (int u = u_first; u < p.n_units; u += u_step, ++i) {
+                const int buf = i & 1;
+                unsigned char *sG = smem + buf * G::BUF + G::X_BYTES;
+                if (i >= 2) mbar_wait(empty + buf, ((i >> 1) - 1) & 1);   // MMAs of unit i-2 done: this G half and X slot (i+2) & 3 are free
+                asm volatile("cp.async.wait_group 1;" ::: "memory");      // C_i has landed (C_{i+1} may still be in flight)
+                const float *rv = raw + (size_t)(i & 1) * (G::RAW_UNIT / 4) + lt;
+#pragma unroll
+                for (int h = 0; h < 3; ++h) {
+                    if (h == 2 && !h2_mine) break;
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int k = 0; k < 8; k += 2) {
+                        // two channels per conversion instruction (cvt.rn.bf16x2.f32: low half = first value)
+                        const float v0 = rv[(h * 8 + k) * (G::LOADER_WARPS * 32)], v1 = rv[(h * 8 + k + 1) * (G::LOADER_WARPS * 32)];
+                        gsum[k] += v0, gsum[k + 1] += v1;
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+                        const uint32_t hb = *reinterpret_cast<const uint32_t *>(&h2);
+                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(v0 - __uint_as_float(hb << 16), v1 - __uint_as_float(hb & 0xffff0000u));
+                        hi[k >> 1] = hb, lo[k >> 1] = *reinterpret_cast<const uint32_t *>(&l2);
+                    }
+                    *reinterpret_cast<uint4 *>(sG + g_dst[h]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(sG + g_dst[h] + G::G_PART) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full + buf);
+                issue(u + 2 * u_step, i + 2);                              // refills the raw slot this thread has just read
+            }
+        } else {
         float gv[3][8];
         if (u_first < p.n_units) load_g(u_first, gv);
         int i = 0;
@@ -259,6 +359,7 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(full + buf);
         }
+        }
     } else if (warp < 2) {
         // ================= MMA issuer =================
         // a_major = b_major = MN (bits 15,16), bf16 x bf16 -> f32, N = 32, M = 128
@@ -271,16 +372,31 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
         // short MMAs): warp 0 owns the accumulators of kernel columns 0..3, warp 1 those of 4..6
         const int kw0 = warp == 0 ? 0 : 4, kw1 = G::NACC == 1 ? (warp == 0 ? 1 : 0) : (warp == 0 ? 4 : G::KW);
         int i = 0;
+        uint32_t iss_started = 0u;
         for (int u = u_first; u < p.n_units; u += u_step, ++i) {
             const int buf = i & 1;
             const int tile = u % tiles;
             const int h0 = (tile / p.tiles_w) * G::TH;
             const int rows = min(G::TH, p.Hc - h0);
-            const uint32_t a_base = desc_lo(smem_u32(smem + buf * G::BUF), 128);               // LBO: next 8 positions (K)
+            const uint32_t a_base = desc_lo(smem_u32(smem + (ring ? G::xslot(i) : buf * G::BUF)), 128);   // LBO: next 8 positions (K)
             const uint32_t b_base = desc_lo(smem_u32(smem + buf * G::BUF + G::X_BYTES), 128);
             mbar_wait(full + buf, (i >> 1) & 1);
             fence_after();
-            if (elected) {
+            if (G::CIN == 1) {
+                // one MMA pair per output row: the two issuer warps take alternate rows into accumulators of their own (summed
+                // when draining), so that the issue rate of one thread (~54 cycles per MMA) does not pace the stream
+                if (elected) {
+                    for (int r = warp; r < rows; r += 2) {
+                        const uint64_t b = desc(B_HI, b_base + r * G::TW);
+                        const uint32_t a_lo0 = a_base + ((r * G::X_RP) >> 4);
+                        const uint32_t d = tmem_base + warp * G::ACC_COLS;
+                        mma_bf16(d, desc(A_HI, a_lo0), b, IDESC_N2, iss_started);
+                        mma_bf16(d, desc(A_HI, a_lo0 + (G::X_PART >> 4)), b, IDESC_N1, 1);
+                        iss_started = 1u;
+                    }
+                    commit(empty + buf);
+                }
+            } else if (elected) {
                 for (int r = 0; r < rows; ++r) {
                     const uint64_t b = desc(B_HI, b_base + r * G::TW);
                     const uint32_t acc = (i == 0 && r == 0) ? 0u : 1u;
@@ -296,13 +412,17 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
             }
             __syncwarp();
         }
-        if (elected) commit(done);
+        if (elected) {
+            if (G::CIN == 1) iss_used[warp] = iss_started;
+            commit(done);
+        }
         __syncwarp();
     }
     // ---- drain: once every MMA has completed (`done` flips), add the two accumulator halves and scatter into the
     //      [Cout,Cin,KH,KW] layout.  The two CTAs of a pair own complementary kernel rows and SHARE one partial block
     //      (every element is written by exactly one of them: no zero fill, half as many blocks to reduce).
     float *out = p.partial + (size_t)(G::NG == 2 ? blockIdx.x >> 1 : blockIdx.x) * p.n_tot;
+    if (G::CIN == 1) __syncthreads();                                    // iss_used[] of both issuers is visible below
     mbar_wait(done, 0);
     fence_after();
     {
@@ -335,15 +455,23 @@ __global__ void __launch_bounds__(512, 1) wgrad_tc_kernel(const WgTcP p) {
                 if (e < run) out[(size_t)cc * (G::KH * G::KW) + G::DY * grp * G::KW + e] = stg[cc * PITCH + e];
             }
         } else {
-            for (int a = (warp >> 2); a < G::NACC; a += 4) {
-                uint32_t v[32], v2[32];
-                ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS, v);
-                ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS + G::COUT, v2);
+            if (warp < 4) {
+                // (row parity 0: hi + lo products) + (row parity 1: hi + lo products), in that fixed order
+                float sum[32];
+#pragma unroll
+                for (int co = 0; co < 32; ++co) sum[co] = 0.f;
+                for (int a = 0; a < G::NISS_ACC; ++a) {
+                    if (!iss_used[a]) continue;                              // that issuer never had a row (single-row images)
+                    uint32_t v[32], v2[32];
+                    ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS, v);
+                    ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * G::ACC_COLS + G::COUT, v2);
+#pragma unroll
+                    for (int co = 0; co < 32; ++co) sum[co] += __uint_as_float(v[co]) + __uint_as_float(v2[co]);
+                }
                 const int kw = m & 7;
                 if (kh < G::KH && lane_ok) {
 #pragma unroll
-                    for (int co = 0; co < 32; ++co)
-                        out[((size_t)(co * G::CIN + ci) * G::KH + kh) * G::KW + kw] = __uint_as_float(v[co]) + __uint_as_float(v2[co]);
+                    for (int co = 0; co < 32; ++co) out[((size_t)(co * G::CIN + ci) * G::KH + kh) * G::KW + kw] = sum[co];
                 }
             }
         }
