@@ -318,18 +318,21 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
 // its own half-used L2 sector).  The block -> feature map follows the image: a CTA = 8 channels x 64 consecutive positions.
 // q32 = 32-bit address of the bf16 pair in the hi part of the sample; the lo part starts F/2 words later.
 // F16X2 (g_scale != 0): fp16 {hi,lo} of g_u * g_scale, saturated to the fp16 range (the scale comes from a bound on |g_u|)
+// (packed conversions: one F2FP per pair on the ALU pipe instead of two half-rate F2F and a byte permute)
 __device__ __forceinline__ void store_gu_img_f16(uint32_t *q32, int half_f, float2 v, float g_scale) {
     const float x = fminf(fmaxf(__fmul_rn(v.x, g_scale), -65504.f), 65504.f), y = fminf(fmaxf(__fmul_rn(v.y, g_scale), -65504.f), 65504.f);
-    const __half h0 = __float2half_rn(x), h1 = __float2half_rn(y);
-    const __half l0 = __float2half_rn(x - __half2float(h0)), l1 = __float2half_rn(y - __half2float(h1));
-    q32[0] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    q32[half_f] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    const __half2 h = __floats2half2_rn(x, y);                              // low half = x
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+    q32[0] = *reinterpret_cast<const uint32_t *>(&h);
+    q32[half_f] = *reinterpret_cast<const uint32_t *>(&l);
 }
 __device__ __forceinline__ void store_gu_img(uint32_t *q32, int half_f, float2 v) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
-    q32[0] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    q32[half_f] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+    const uint32_t hb = *reinterpret_cast<const uint32_t *>(&h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v.x - __uint_as_float(hb << 16), v.y - __uint_as_float(hb & 0xffff0000u));
+    q32[0] = hb;
+    q32[half_f] = *reinterpret_cast<const uint32_t *>(&l);
 }
 
 // pv rows reach the thread through a ring of thread-PRIVATE shared-memory slots filled by 8-byte cp.async (LDGSTS): NG groups of
