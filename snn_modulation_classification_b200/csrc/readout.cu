@@ -591,6 +591,25 @@ __global__ void __launch_bounds__(256, 3) wout_grad_adam2_kernel(const float *__
             }
         }
     }
+    // The Adam tail's w, m, v rows travel through the SAME ring as extra groups behind the last pv rows (TG = KH / 2 groups of
+    // 2 outputs x {w, m, v}), requested RB2_NG - 1 groups ahead like everything else: their DRAM latency is covered by the last
+    // multiplies and by the Adam arithmetic of the groups before them.  (Loading them in dependent rounds after the sweep left
+    // every CTA waiting four times: 18 % of the samples on the first use of each round.)
+    constexpr int TG = KH / 2;
+    static_assert(KH % 2 == 0 && 6 <= UB, "tail groups of two outputs fit a ring group");
+    const bool chain_ok = apply && K == KMAX;
+    bool chained = false;
+    int ng_last = 0;
+    auto request_tail = [&](int tg) {
+        const uint32_t dst = ring0 + ((ng_last + tg) % RB2_NG) * (UB * 256 * 8);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const size_t o = (size_t)(kbase + 2 * tg + j) * F + f;
+            cp_async8(dst + (3 * j + 0) * (256 * 8), wout + o);
+            cp_async8(dst + (3 * j + 1) * (256 * 8), m_w + o);
+            cp_async8(dst + (3 * j + 2) * (256 * 8), v_w + o);
+        }
+    };
     float2 acc[KH];
 #pragma unroll
     for (int k = 0; k < KH; ++k) acc[k] = make_float2(0.f, 0.f);
@@ -618,6 +637,8 @@ __global__ void __launch_bounds__(256, 3) wout_grad_adam2_kernel(const float *__
             int bb = 0;
             {
                 const int ng = nb / UB;
+                const bool chain = chain_ok && b0 + 64 >= B && ng >= RB2_NG - 1;   // last batch block: the tail follows in the ring
+                if (chain) chained = true, ng_last = ng;
                 if (b0 != 0) {
 #pragma unroll
                     for (int g = 0; g < RB2_NG - 1; ++g) {
@@ -627,6 +648,7 @@ __global__ void __launch_bounds__(256, 3) wout_grad_adam2_kernel(const float *__
                 }
                 for (int g = 0; g < ng; ++g, bb += UB) {
                     if (g + RB2_NG - 1 < ng) request(b0, g + RB2_NG - 1);
+                    else if (chain && g + RB2_NG - 1 - ng < TG) request_tail(g + RB2_NG - 1 - ng);
                     asm volatile("cp.async.commit_group;" ::: "memory");
                     asm volatile("cp.async.wait_group %0;" ::"n"(RB2_NG - 1) : "memory");
                     const float2 *stage = rb2_ring + (g % RB2_NG) * (UB * 256) + tid;
@@ -636,13 +658,33 @@ __global__ void __launch_bounds__(256, 3) wout_grad_adam2_kernel(const float *__
 #pragma unroll
                     for (int u = 0; u < UB; ++u) sample(bb + u, cur[u]);
                 }
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                if (!chain) asm volatile("cp.async.wait_group 0;" ::: "memory");
                 pvp += (size_t)ng * UB * rowF;
             }
             for (; bb < nb; ++bb, pvp += rowF) sample(bb, __ldg(reinterpret_cast<const float2 *>(pvp)));
         }
     }
-    if (fok) {
+    if (fok && chained) {
+#pragma unroll
+        for (int tg = 0; tg < TG; ++tg) {
+            if (tg + RB2_NG - 1 < TG) request_tail(tg + RB2_NG - 1);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(RB2_NG - 1) : "memory");
+            const float2 *stage = rb2_ring + ((ng_last + tg) % RB2_NG) * (UB * 256) + tid;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const size_t o = (size_t)(kbase + 2 * tg + j) * F + f;
+                float2 w = stage[(3 * j + 0) * 256], m = stage[(3 * j + 1) * 256], v = stage[(3 * j + 2) * 256];
+                const float2 g = acc[2 * tg + j];
+                if (grad_w) *reinterpret_cast<float2 *>(grad_w + o) = g;
+                adam_elem(w.x, g.x, m.x, v.x, sc);
+                adam_elem(w.y, g.y, m.y, v.y, sc);
+                *reinterpret_cast<float2 *>(wout + o) = w;
+                *reinterpret_cast<float2 *>(m_w + o) = m;
+                *reinterpret_cast<float2 *>(v_w + o) = v;
+            }
+        }
+    } else if (fok) {
         // Adam tail on this thread's own outputs, TB rows at a time with every load issued before the first store
         constexpr int TB = (KH % 3 == 0) ? 3 : 4;
         static_assert(KH % TB == 0, "tail groups");
