@@ -153,8 +153,23 @@ __global__ void __launch_bounds__(1024) readout_finish_kernel(const float *__res
     const int b = blockIdx.x, tid = threadIdx.x;
     const int kk = tid & 63, sl = tid >> 6, n_sl = blockDim.x >> 6;
     float s = 0.f;
-    if (kk < Ktot)
-        for (int c = sl; c < n_part; c += n_sl) s += partial[((size_t)c * B + b) * Ktot + kk];
+    if (kk < Ktot) {
+        // FIN_U loads in flight per thread, added in the same fixed order as a serial walk (a rolled loop paid one L2 round trip
+        // per partial block: ~8 us per launch, three launches per timestep on the critical path)
+        constexpr int FIN_U = 10;
+        const float *src = partial + (size_t)b * Ktot + kk;
+        const size_t pitch = (size_t)B * Ktot;
+        // (unconditional loads -- past the end the slice's last block is read again -- so that they are issued back to back)
+        const int c_hi = sl + n_sl * ((n_part - 1 - sl) / n_sl);
+        for (int c0 = sl; c0 < n_part; c0 += n_sl * FIN_U) {
+            float t[FIN_U];
+#pragma unroll
+            for (int u = 0; u < FIN_U; ++u) t[u] = src[(size_t)min(c0 + u * n_sl, c_hi) * pitch];
+#pragma unroll
+            for (int u = 0; u < FIN_U; ++u)
+                if (c0 + u * n_sl < n_part) s += t[u];
+        }
+    }
     red[sl][kk] = s;
     __syncthreads();
     float lsum = 0.f;

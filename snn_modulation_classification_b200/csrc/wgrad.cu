@@ -187,12 +187,13 @@ __global__ void __launch_bounds__(8 * wg_ci_t(KH) * KH) wgrad_kernel(const WgP p
 //   * the LAST block to finish (ticket in w_exp[2]) publishes slot 0 = the exponent this launch wrote the image with -- what the
 //     next convolution must undo -- and slot 1 = the exponent for the next image from this step's maximum, and resets 2 and 3.
 //     It is the only writer of the slots, and by then every other block has read slot 1.
+constexpr int RED_U = 10;   // partial-block loads in flight per thread in the reducers below
 __device__ __forceinline__ void reduce_adam_tail(float (&red)[4][64], int n_tot, int nW, int Cout, int CoutPad, int CinKK,
                                                  float *__restrict__ w, float *__restrict__ wt, float *__restrict__ bias,
                                                  float *__restrict__ m_w, float *__restrict__ v_w, float *__restrict__ m_b,
                                                  float *__restrict__ v_b, float *__restrict__ grad_w, float *__restrict__ grad_b, int apply,
                                                  const AdamScalars &sc, __nv_bfloat16 *__restrict__ w_mma, int Cin, int KHKW, int KW,
-                                                 int *__restrict__ w_exp, int kexp) {
+                                                 int *__restrict__ w_exp, int kexp, float w_pre, float m_pre, float v_pre) {
     const int e = threadIdx.x & 63, sl = threadIdx.x >> 6;
     const int i = blockIdx.x * 64 + e;
     float wabs = 0.f;
@@ -201,7 +202,7 @@ __device__ __forceinline__ void reduce_adam_tail(float (&red)[4][64], int n_tot,
         if (i < nW) {
             if (grad_w) grad_w[i] = g;
             if (apply) {
-                float wv = w[i], m = m_w[i], v = v_w[i];
+                float wv = w_pre, m = m_pre, v = v_pre;                   // loaded by the caller BEFORE the reduction (one round trip less)
                 adam_elem(wv, g, m, v, sc);
                 w[i] = wv, m_w[i] = m, v_w[i] = v;
                 wabs = fabsf(wv);
@@ -272,13 +273,27 @@ __global__ void __launch_bounds__(256) reduce_adam_kernel(const float *__restric
     const int e = threadIdx.x & 63, sl = threadIdx.x >> 6;
     const int i = blockIdx.x * 64 + e;
     const int kexp = w_exp ? *reinterpret_cast<volatile int *>(w_exp + 1) : 0;
-    float g = 0.f;
-    if (i < n_tot)
-        for (int s = sl; s < S; s += 4) g += __ldg(partial + (size_t)s * n_tot + i);
+    float g = 0.f, w_pre = 0.f, m_pre = 0.f, v_pre = 0.f;
+    if (sl == 0 && i < nW && apply) w_pre = w[i], m_pre = m_w[i], v_pre = v_w[i];
+    if (i < n_tot) {
+        // RED_U loads in flight per thread, added in the same fixed order as a serial walk (a rolled loop waited one L2 round trip
+        // per block: this kernel is pure latency, 10-12 us for 5 MB)
+        // (the loads are UNCONDITIONAL, past the end the slice's last block is read again: predicated loads were scheduled
+        //  load - add - load - add, one round trip each)
+        const int s_hi = sl + 4 * ((S - 1 - sl) >> 2);                       // last block of this slice (S > sl inside the loop)
+        for (int s0 = sl; s0 < S; s0 += 4 * RED_U) {
+            float t[RED_U];
+#pragma unroll
+            for (int u = 0; u < RED_U; ++u) t[u] = __ldg(partial + (size_t)min(s0 + 4 * u, s_hi) * n_tot + i);
+#pragma unroll
+            for (int u = 0; u < RED_U; ++u)
+                if (s0 + 4 * u < S) g += t[u];
+        }
+    }
     red[sl][e] = g;
     __syncthreads();
     reduce_adam_tail(red, n_tot, nW, Cout, CoutPad, CinKK, w, wt, bias, m_w, v_w, m_b, v_b, grad_w, grad_b, apply, sc, w_mma, Cin, KHKW,
-                     KW, w_exp, kexp);
+                     KW, w_exp, kexp, w_pre, m_pre, v_pre);
 }
 
 // Same reduction + Adam tail for the partial blocks of wgrad_tc2_kernel (wgrad_tc2.cu): one compact block per CTA,
@@ -301,7 +316,8 @@ __global__ void __launch_bounds__(256) reduce_adam_rp_kernel(const float *__rest
     // F16X2: the image written below is fp16 {hi,lo} of w * 2^k, k = w_exp[1] -- read by every block before any block can have
     // finished (the last block to finish is the only writer of the slots, see the end of the kernel)
     const int kexp = w_exp ? *reinterpret_cast<volatile int *>(w_exp + 1) : 0;
-    float g = 0.f;
+    float g = 0.f, w_pre = 0.f, m_pre = 0.f, v_pre = 0.f;
+    if (sl == 0 && i < nW && apply) w_pre = w[i], m_pre = m_w[i], v_pre = v_w[i];
     if (i < nW) {
         const int cc = i / KHKW, tap = i - cc * KHKW;            // cc = co * Cin + ci
         const int kh = tap / KW, kw = tap - kh * KW;
@@ -309,17 +325,38 @@ __global__ void __launch_bounds__(256) reduce_adam_rp_kernel(const float *__rest
         const int a = roleA ? kw : kw - 4;
         const int c_first = roleA ? 0 : 2 * nA, c_last = roleA ? 2 * nA : 2 * (nA + nB);
         const size_t base = (size_t)cc * 20 + a * 5;
-        for (int c = c_first + sl; c < c_last; c += 4) {
-            const int grp = c & 1;
-            if (grp == 0 ? kh <= 3 : kh >= 3) g += __ldg(partial + (size_t)c * blk + base + (grp == 0 ? kh + 1 : kh - 3));
+        // slice sl walks the blocks c = c_first + sl + 4 j, whose group (c & 1) is the parity of sl: either all or none of them
+        // hold this element, and the slot is the same for all (RED_U loads in flight, fixed order as before)
+        const int grp = (c_first + sl) & 1;
+        if (grp == 0 ? kh <= 3 : kh >= 3) {
+            const float *src = partial + base + (grp == 0 ? kh + 1 : kh - 3);
+            const int c_hi = c_first + sl + 4 * ((c_last - 1 - c_first - sl) >> 2);   // last block of this slice (unconditional loads, see above)
+            for (int c0 = c_first + sl; c0 < c_last; c0 += 4 * RED_U) {
+                float t[RED_U];
+#pragma unroll
+                for (int u = 0; u < RED_U; ++u) t[u] = __ldg(src + (size_t)min(c0 + 4 * u, c_hi) * blk);
+#pragma unroll
+                for (int u = 0; u < RED_U; ++u)
+                    if (c0 + 4 * u < c_last) g += t[u];
+            }
         }
     } else if (i < n_tot) {
-        for (int c = 2 * nA + sl; c < 2 * (nA + nB); c += 4) g += __ldg(partial + (size_t)c * blk + nw_blk + (i - nW));
+        const int c_last = 2 * (nA + nB);
+        const float *src = partial + nw_blk + (i - nW);
+        const int c_hi = 2 * nA + sl + 4 * ((c_last - 1 - 2 * nA - sl) >> 2);
+        for (int c0 = 2 * nA + sl; c0 < c_last; c0 += 4 * RED_U) {
+            float t[RED_U];
+#pragma unroll
+            for (int u = 0; u < RED_U; ++u) t[u] = __ldg(src + (size_t)min(c0 + 4 * u, c_hi) * blk);
+#pragma unroll
+            for (int u = 0; u < RED_U; ++u)
+                if (c0 + 4 * u < c_last) g += t[u];
+        }
     }
     red[sl][e] = g;
     __syncthreads();
     reduce_adam_tail(red, n_tot, nW, Cout, CoutPad, CinKK, w, wt, bias, m_w, v_w, m_b, v_b, grad_w, grad_b, apply, sc, w_mma, Cin, KHKW,
-                     KW, w_exp, kexp);
+                     KW, w_exp, kexp, w_pre, m_pre, v_pre);
 }
 
 static int wg_n_ci_chunks(const dcll_conv_layer *L) {
