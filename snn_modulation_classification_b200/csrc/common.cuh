@@ -224,6 +224,8 @@ int readout_tc_blocks(const dcll_conv_layer *L);
 int launch_readout_tc(const dcll_conv_layer *L, float *partial, cudaStream_t st);   // tcgen05, split-bf16 x3
 int launch_loss_grad(const dcll_conv_layer *L, const float *target, int loss_kind, float *loss_out, cudaStream_t st);
 int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st);
+bool readout_bwd_tc_supported(const dcll_conv_layer *L, int hw, int F);                   // readout_bwd_tc.cu (DCLL_RB_TC=1)
+int launch_readout_bwd_tc(const dcll_conv_layer *L, const float *g_o, int hw, int F, float g_scale, cudaStream_t st);
 int launch_wgrad(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_t st);
 int wgrad_splits(const dcll_conv_layer *L);
 bool wgrad_tc_supported(const dcll_conv_layer *L);

@@ -912,6 +912,9 @@ int launch_readout_bwd(const dcll_conv_layer *L, dcll_train_args *a, cudaStream_
             const unsigned grid1 = (unsigned)fblk * slices;                   // 1-D: the slices of a feature block are adjacent
             constexpr int ring_bytes = RB2_NG * 8 * 256 * 8;
             const float g_scale = prec_f16(L) ? pow2i(L->g_exp) : 0.f;   // F16X2: the image is fp16 {hi,lo} of g_u * 2^g_exp
+            // DCLL_RB_TC=1: the K-sum as a skinny tcgen05 GEMM per 128 features (readout_bwd_tc.cu), F16X2 image form only
+            if (g_scale != 0.f && wgrad_tc2_supported(L) && readout_bwd_tc_supported(L, hw, g.F))
+                return launch_readout_bwd_tc(L, g_o, hw, g.F, g_scale, st);
             // 8 rows in flight per thread, next group prefetched: 128 registers, 2 CTAs per SM (4 rows at 3 CTAs per SM was slower)
             // image form of g_u (bf16 {hi,lo} planes in the same buffer) when the row-pair weight-gradient kernel consumes it
 #define RB2_M(KM, MB)                                                                                                              \

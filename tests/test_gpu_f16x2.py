@@ -204,3 +204,18 @@ def test_f16x2_inference_free_running_flip_rate_and_votes():
     for i, s in enumerate(net.dcll_slices):
         agree = (np.array(s.clout) == np.array(onet.clout[i])).mean()
         assert agree >= 0.98, (i, agree)
+
+
+def test_f16x2_tensor_core_backward_readout_opt_in():
+    """DCLL_RB_TC=1 selects csrc/readout_bwd_tc.cu (the K-sum of the backward read-out as a skinny tcgen05 GEMM; experimental,
+    slower than readout_bwd2_kernel at 128x128 and therefore off by default).  It must satisfy the same bounds.  The switch is
+    read once per process, hence the subprocess; the -k expression does not match this test."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DCLL_RB_TC="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        "-k", "weight_gradient or bench_config"], env=env, capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "skipped" not in r.stdout.splitlines()[-1], r.stdout[-500:]
