@@ -13,8 +13,8 @@
 // Numerics: the K = 24 sum carries ~2^-16 relative rounding (bf16 x3) instead of fp32's 2^-24 -- F16X2 only, whose g_u image
 // is fp16 {hi,lo} anyway and whose tests bound the first Adam step statistically (tests/util_build.py).
 // EXPERIMENTAL, off unless DCLL_RB_TC=1: correct (tests/test_gpu_f16x2.py runs the f16x2 bounds with the switch on) but
-// measured 0.116 ms against 0.085 ms for readout_bwd2_kernel at 128x128, B = 64 -- 4096 short-lived CTAs pay TMEM allocation,
-// a Wo round trip, the MMA round trip and four pv round trips in series, and store 16-byte runs.  DESIGN.md section 4.4 (g).
+// measured 0.102 ms against 0.085 ms for readout_bwd2_kernel at 128x128, B = 64 -- 4096 short-lived CTAs pay TMEM allocation,
+// a Wo round trip, the MMA round trip and the pv round trips in series, and store 16-byte runs.  DESIGN.md section 4.4 (g).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -59,7 +59,7 @@ __device__ __forceinline__ void store_row(unsigned char *base, int f8, int row, 
 }
 }  // namespace rbtc
 
-__global__ void __launch_bounds__(rbtc::NT, 6) readout_bwd_tc_kernel(const RbTcP p) {
+__global__ void __launch_bounds__(rbtc::NT, 5) readout_bwd_tc_kernel(const RbTcP p) {
     using namespace rbtc;
     using namespace tc;
     __shared__ __align__(128) unsigned char sA[A_BYTES];
@@ -90,29 +90,39 @@ __global__ void __launch_bounds__(rbtc::NT, 6) readout_bwd_tc_kernel(const RbTcP
     const uint32_t tmem_base = tmem_slot;
     pdl_entry();
 
-    // ---- A: this thread's Wo column (row m = tid of the tile), K-major [k/8][m][8]
-    {
-        float w[KP];
-#pragma unroll
-        for (int k = 0; k < KP; ++k) w[k] = __ldg(p.wo + (size_t)min(k, p.K - 1) * p.F + f);   // unconditional: all in flight at once
-#pragma unroll
-        for (int k = 0; k < KP; ++k) w[k] = k < p.K ? w[k] : 0.f;
-        store_row(sA, A_F8, tid, w, false);
-    }
+    // ---- A: this thread's Wo column (row m = tid of the tile), K-major [k/8][m][8].  The g_o rows of the first batch block are
+    //      requested together with it (one round trip instead of two); loads are unconditional (clamped) so that all fly at once.
     constexpr uint32_t IDESC = idesc_bf16(128, 64, false, false);
     constexpr uint32_t SBO128 = desc_hi(128);
     const bool even = (lane & 1) == 0;
+    auto load_g = [&](int b0, int nb, float (&g)[KP]) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) g[k] = __ldg(p.g_o + (size_t)(b0 + min(tid & 63, nb - 1)) * p.K + min(k, p.K - 1));
+    };
+    // the image's power-of-two scale rides in the B operand (exact), so the epilogue has no multiply for it
+    auto store_g = [&](int nb, float (&g)[KP]) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) g[k] = (tid < nb && k < p.K) ? __fmul_rn(g[k], p.g_scale) : 0.f;
+        store_row(sB, B_F8, tid, g, true);
+    };
+    {
+        float w[KP], g[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) w[k] = __ldg(p.wo + (size_t)min(k, p.K - 1) * p.F + f);
+        if (tid < 64) load_g(0, min(64, p.B), g);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) w[k] = k < p.K ? w[k] : 0.f;
+        store_row(sA, A_F8, tid, w, false);
+        if (tid < 64) store_g(min(64, p.B), g);
+    }
+    const float *pvf = p.pv + f;
     uint32_t phase = 0;
     for (int b0 = 0; b0 < p.B; b0 += 64) {
         const int nb = min(64, p.B - b0);
-        // ---- B: g_o rows of this batch block, K-major [k/8][n][8] (rows past the batch are zero)
-        if (tid < 64) {
+        if (b0 != 0 && tid < 64) {                                        // later batch blocks: g_o rows, K-major [k/8][n][8]
             float g[KP];
-#pragma unroll
-            for (int k = 0; k < KP; ++k) g[k] = __ldg(p.g_o + (size_t)(b0 + min(tid, nb - 1)) * p.K + min(k, p.K - 1));
-#pragma unroll
-            for (int k = 0; k < KP; ++k) g[k] = (tid < nb && k < p.K) ? g[k] : 0.f;
-            store_row(sB, B_F8, tid, g, true);
+            load_g(b0, nb, g);
+            store_g(nb, g);
         }
         fence_async_smem();
         __syncthreads();
@@ -126,38 +136,51 @@ __global__ void __launch_bounds__(rbtc::NT, 6) readout_bwd_tc_kernel(const RbTcP
             }
             __syncwarp();
         }
+        // ---- epilogue: thread = feature f, columns = samples.  Rows go in batches of 16 with the NEXT batch's pv values already
+        //      requested (the first before the MMAs have finished).  Within a pair of rows the even lane converts and stores the
+        //      position pair of the even row, the odd lane that of the odd row: one shuffle, one conversion per row and lane.
+        auto load_pv = [&](int r0, float (&v)[16]) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = __ldg(pvf + (size_t)(b0 + min(r0 + u, nb - 1)) * p.F);
+        };
+        uint32_t *img = reinterpret_cast<uint32_t *>(p.g_u) + img_word;
+        const int half_f = p.F >> 1;
+        float pa[16], pb[16];
+        load_pv(0, pa);
         mbar_wait(&bar, phase);
         phase ^= 1u;
         fence_after();
-        // ---- epilogue: thread = feature f, columns = samples; 32 samples per pass, 16 pv loads in flight
-        uint32_t *img = reinterpret_cast<uint32_t *>(p.g_u) + img_word + (even ? 0 : (p.F >> 1));
+        auto batch = [&](const uint32_t (&d)[32], int dj, int r0, const float (&v)[16]) {
+#pragma unroll
+            for (int u = 0; u < 16; u += 2) {
+                // s * (1 - pv) * pv in the FP32 kernel's order (s already carries the image scale)
+                const float x0 = __fmul_rn(__fmul_rn(__uint_as_float(d[dj + u]), __fmaf_rn(v[u], -1.f, 1.f)), v[u]);
+                const float x1 = __fmul_rn(__fmul_rn(__uint_as_float(d[dj + u + 1]), __fmaf_rn(v[u + 1], -1.f, 1.f)), v[u + 1]);
+                const float got = __shfl_xor_sync(0xffffffffu, even ? x1 : x0, 1);   // the partner's value of MY row
+                const float mine = even ? x0 : x1;
+                const float a = even ? mine : got, b = even ? got : mine;            // (even position, odd position)
+                uint32_t hh;
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hh) : "f"(b), "f"(a));   // low half = even position
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&hh));
+                uint32_t ll;
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(ll) : "f"(b - hf.y), "f"(a - hf.x));
+                const int row = r0 + u + (even ? 0 : 1);
+                if (row < nb) {
+                    uint32_t *q = img + (size_t)(b0 + row) * p.F;
+                    q[0] = hh;
+                    q[half_f] = ll;
+                }
+            }
+        };
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             if (32 * h >= nb) break;
             uint32_t d[32];
             ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 32 * h, d);
-#pragma unroll
-            for (int j0 = 0; j0 < 32; j0 += 16) {
-                float pvv[16];
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const int bb = 32 * h + j0 + u;
-                    pvv[u] = __ldg(p.pv + (size_t)(b0 + min(bb, nb - 1)) * p.F + f);   // unconditional (predicated loads get serialised)
-                }
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const int bb = 32 * h + j0 + u;
-                    // s * (1 - pv) * pv in the FP32 kernel's order, then the image's power-of-two scale, saturated to fp16
-                    float x = __fmul_rn(__fmul_rn(__uint_as_float(d[j0 + u]), __fmaf_rn(pvv[u], -1.f, 1.f)), pvv[u]);
-                    x = fminf(fmaxf(__fmul_rn(x, p.g_scale), -65504.f), 65504.f);
-                    const float y = __shfl_xor_sync(0xffffffffu, x, 1);
-                    const float a = even ? x : y, b = even ? y : x;             // (even position, odd position) of the pair
-                    const __half2 hh = __floats2half2_rn(a, b);
-                    const float2 hf = __half22float2(hh);
-                    const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
-                    if (bb < nb) img[(size_t)(b0 + bb) * p.F] = even ? *reinterpret_cast<const uint32_t *>(&hh) : *reinterpret_cast<const uint32_t *>(&ll);
-                }
-            }
+            load_pv(32 * h + 16, pb);
+            batch(d, 0, 32 * h, pa);
+            if (h == 0) load_pv(32, pa);
+            batch(d, 16, 32 * h + 16, pb);
         }
         fence_before();
         __syncthreads();   // accumulator and sB are free for the next batch block
